@@ -1,0 +1,117 @@
+"""Generate the golden fixtures in this directory from the UNMODIFIED reference.
+
+Run in the build container only (``/root/reference`` does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+It imports ``sparse_graph_model`` / ``layers`` straight from ``/root/reference`` (no copy),
+runs them in fp32 on CPU on seeded synthetic inputs and writes, per workload, one
+``<name>.npz`` holding inputs, the reference ``state_dict``, forward outputs
+(logits, adjacency, h_max_indices), the sorted top-k neighbour sets / softmax weights the
+reference derives from its own adjacency, the layer-level outputs of ``GraphLearner`` and
+``NeighbourhoodGraphConvolution`` on materialised neighbourhoods, and all parameter
+gradients of ``MultiLabelSoftMarginLoss``.  The files pin both ``oracle/vqa_oracle.py`` and the
+CUDA path to the reference's actual behaviour.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "vqa-project_b200"))
+from vqa_b200.synthetic import WORKLOADS, make_batch, make_wemb  # noqa: E402
+
+REF = "/root/reference"
+
+
+def load_reference():
+    sys.path.insert(0, REF)
+    for m in ("layers", "sparse_graph_model"):
+        sys.modules.pop(m, None)
+    import sparse_graph_model as ref_model  # noqa
+    import layers as ref_layers  # noqa
+    assert ref_model.__file__.startswith(REF) and ref_layers.__file__.startswith(REF)
+    sys.path.remove(REF)
+    return ref_model, ref_layers
+
+
+def main():
+    warnings.filterwarnings("ignore")
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref_model, ref_layers = load_reference()
+    for name in ("tiny", "small"):
+        w = WORKLOADS[name]
+        torch.manual_seed(1000)
+        model = ref_model.Model(pretrained_wemb=make_wemb(w), **w.model_kwargs())
+        # make the Gaussian widths less degenerate than U(0,1) can be (a width ~1e-3 underflows every
+        # kernel -> 0/0 rows, which the reference leaves as NaN; that case has its own unit test)
+        with torch.no_grad():
+            for gc in (model.graph_convolution_1, model.graph_convolution_2):
+                gc.precision_rho.clamp_(min=0.05)
+                gc.precision_theta.clamp_(min=0.05)
+        model.train()  # dropout p = 0 in these workloads -> deterministic
+        batch = make_batch(w, seed=1000)
+        q, img, K, qlen, tgt = batch["question"], batch["image"], batch["K"], batch["qlen"], batch["target"]
+
+        logits, adj, arg = model(q, img, K, qlen)
+        loss = torch.nn.MultiLabelSoftMarginLoss()(logits, tgt)
+        model.zero_grad()
+        loss.backward()
+
+        out = {}
+        out["in.question"] = q.numpy()
+        out["in.image"] = img.numpy()
+        out["in.qlen"] = np.array([int(x) for x in qlen], dtype=np.int64)
+        out["in.target"] = tgt.numpy()
+        for k, v in model.state_dict().items():
+            out["param." + k] = v.detach().numpy()
+        for k, v in model.named_parameters():
+            # weight_norm exposes weight_g / weight_v as the parameters
+            out["grad." + k] = (v.grad if v.grad is not None else torch.zeros_like(v)).numpy()
+        out["out.logits"] = logits.detach().numpy()
+        out["out.adjacency"] = adj.detach().numpy()
+        out["out.h_max_indices"] = arg.numpy()
+        out["out.loss"] = np.array(loss.item(), dtype=np.float64)
+
+        # what the reference derives from its own adjacency (sparse_graph_model.py:225-227)
+        vals, idx = torch.topk(adj.detach(), k=w.neighbourhood, dim=-1, sorted=False)
+        alpha = torch.softmax(vals, dim=-1)
+        order = idx.argsort(dim=-1)
+        out["nbr.idx_sorted"] = torch.gather(idx, -1, order).numpy()
+        out["nbr.alpha_sorted"] = torch.gather(alpha, -1, order).numpy()
+        # margin between the nb-th and (nb+1)-th largest entry per row: rows with a tiny margin may
+        # legitimately flip under fp32 re-association, tests skip those rows for the exact-set check
+        srt = adj.detach().sort(dim=-1, descending=True).values
+        out["nbr.margin"] = (srt[..., w.neighbourhood - 1] - srt[..., w.neighbourhood]).numpy()
+
+        # layer-level API on materialised neighbourhoods
+        with torch.no_grad():
+            centres = img[:, :, -4:-2] + 0.5 * (img[:, :, -2:] - img[:, :, -4:-2])
+            pseudo = model._compute_pseudo(centres)
+            nbr_img, nbr_pseudo = model._create_neighbourhood(img, pseudo, adj.detach(), w.neighbourhood, weight=True)
+            gc1 = model.graph_convolution_1
+            if name == "tiny":  # large; the tests rebuild it from image/adjacency for other workloads
+                out["layer.nbr_feat"] = nbr_img.numpy()
+            out["layer.nbr_pseudo"] = nbr_pseudo.numpy()
+            out["layer.gauss_w"] = gc1.get_gaussian_weights(nbr_pseudo).numpy()
+            out["layer.gc1_out"] = gc1(nbr_img, nbr_pseudo).numpy()
+            emb = model.wembed(q)
+            packed = torch.nn.utils.rnn.pack_padded_sequence(emb, qlen, batch_first=True, enforce_sorted=False)
+            _, hid = model.q_gru(packed)
+            out["layer.qenc"] = hid[0].numpy()
+            nodes = torch.cat((img, hid[0].unsqueeze(1).repeat(1, w.n_obj, 1)), dim=-1)
+            if name == "tiny":
+                out["layer.graph_nodes"] = nodes.numpy()
+            out["layer.adjacency"] = model.adjacency_1(nodes).numpy()
+
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB), loss={loss.item():.6f}")
+
+
+if __name__ == "__main__":
+    main()
