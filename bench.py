@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Train-step throughput of the conditioned-graph VQA hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload vqa2_b512]
+
+One "step" = zero_grad -> Model.forward -> MultiLabelSoftMarginLoss -> backward (-> bucketed NCCL all-reduce when
+N > 1) -> Adam step, on one synthetic batch of BASELINE.json configs[1] (VQA2: B=512/GPU, K=36, F=2052, nb=16,
+nk=8, 3000 answers, dropout 0.5).  Prints ONE JSON line (see the task contract): `value` = questions/s with
+inputs resident in HBM, `e2e` = the same through the public Model API with pinned-host inputs copied every step,
+`roofline` = the layer-1 graph-convolution kernel against the measured HBM peak, `cpu_baseline` = the oracle port
+on the host cores.  `--impl reference` times the reference algorithm (oracle port, PyTorch CPU) instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "vqa-project_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="vqa2_b512")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="questions per CPU step (bounded sample of the workload)")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_train_steps(workload, sample, steps, warmup, threads):
+    """The reference's algorithm (oracle/vqa_oracle.py restatement, PyTorch CPU, autograd) on the host cores."""
+    from oracle import vqa_oracle as O
+    from vqa_b200.synthetic import make_batch
+    torch.set_num_threads(threads)
+    w = workload
+    params = O.init_params(w.vocab, w.emb_dim, w.feat_dim, w.hid_dim, w.out_dim, w.n_kernels)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    opt = torch.optim.Adam(list(leaves.values()), lr=1e-4)
+    batch = make_batch(w, seed=1000, batch=sample)
+    q, img, tgt = batch["question"], batch["image"], batch["target"]
+    qlen = [int(x) for x in batch["qlen"]]
+    gen = torch.Generator().manual_seed(0)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        logits, _, _ = O.forward(leaves, q, img, qlen, w.neighbourhood, w.n_kernels, dropout_p=w.dropout,
+                                 training=True, generator=gen)
+        loss = O.multilabel_soft_margin_loss(logits, tgt)
+        loss.backward()
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times, float(loss.detach())
+
+
+def run_reference(args, workload):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    times, _ = cpu_train_steps(workload, args.cpu_sample, args.steps, args.warmup, cores)
+    total = sum(times)
+    value = args.cpu_sample * len(times) / total
+    sample = f"{args.cpu_sample} of {workload.batch} questions per step, {len(times)} steps, PyTorch CPU autograd through oracle/vqa_oracle.py"
+    line = {
+        "impl": "reference", "metric": "train questions/sec (fwd+bwd)", "value": round(value, 3), "unit": "questions/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / len(times), 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(workload, args, 1) | {"cpu_sample_batch": args.cpu_sample},
+        "cpu_baseline": {"value": round(value, 3), "unit": "questions/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": "questions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(w, args, world):
+    return {"workload": f"{w.name}: VQA2 conditioned-graph train step, per-GPU batch {w.batch}, K={w.n_obj} boxes x {w.feat_dim}-d, "
+                        f"<= {w.max_qlen}-token questions, top-k={w.neighbourhood}, {w.n_kernels} Gaussian kernels, {w.out_dim} answers, dropout {w.dropout}",
+            "global_batch": w.batch * world, "step": "zero_grad+forward+MultiLabelSoftMarginLoss+backward+allreduce+Adam",
+            "parallelism": f"dp{world}", "gemm_precision": "tf32x3 (fp32-grade)" if args.precision != "tf32" else "tf32",
+            "l2_policy": "inputs larger than L2 (image batch 151 MB > 126 MB), 3 rotating batches"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args, workload):
+    import torch.distributed as dist
+    from vqa_b200 import kernels as kn, ops
+    from vqa_b200.ddp import GradReducer, broadcast_parameters
+    from vqa_b200.synthetic import make_batch, make_wemb
+    import sparse_graph_model as M
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device: the vqa_b200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ops.set_precision(args.precision)
+    w = workload
+
+    torch.manual_seed(1000)
+    model = M.Model(pretrained_wemb=make_wemb(w), **w.model_kwargs()).to(dev)
+    broadcast_parameters(model)
+    model.train()
+    criterion = torch.nn.MultiLabelSoftMarginLoss()
+    reducer = GradReducer(model.parameters())
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+    torch.manual_seed(1234 + rank)       # rank-offset dropout streams
+
+    # host batches (pinned) and device-resident copies; rank-offset seeds = different data per rank
+    NB = 3
+    host = []
+    for i in range(NB):
+        b = make_batch(w, seed=1000 + 17 * rank + i)
+        host.append({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()})
+    resident = [{k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in b.items()} for b in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for k, v in host[0].items() if torch.is_tensor(v))
+
+    def step(b):
+        reducer.zero_grad()
+        logits, _, _ = model(b["question"], b["image"], b["K"], b["qlen"])
+        loss = criterion(logits, b["target"])
+        loss.backward()
+        reducer.finish()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return ms
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    for i in range(args.warmup):
+        step(resident[i % NB])
+    GC, ADJ, GEMM = "vqa_graphconv_fwd_f32", "vqa_adjacency_topk_fwd_f32", "vqa_gemm_f32"
+    kn.enable_timing(GC, ADJ, "vqa_graphconv_bwd_f32", "vqa_graphconv_pool_fwd_f32", "vqa_adjacency_topk_bwd_f32")
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    launches0 = kn.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(resident[i % NB])
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = (kn.LAUNCHES - launches0) // max(args.steps, 1)
+    sampler.stop_flag = True
+    timers = {k: [a.elapsed_time(b) for a, b in v] for k, v in kn.TIMERS.items()}
+    kn.enable_timing()
+    ms_step = ms_total / args.steps
+    value = w.batch * world / (ms_step * 1e-3)
+
+    # ---- end to end through the public API: pinned host -> device every step, loss read back ---------------
+    copy_stream = torch.cuda.Stream()
+    slots = [dict(), dict()]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i, slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            hb = host[i % NB]
+            slots[slot] = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}
+            ready[slot].record(copy_stream)
+
+    def e2e_loop(n):
+        for s in (0, 1):
+            consumed[s].record()
+        prefetch(0, 0)
+        last = None
+        for i in range(n):
+            if i + 1 < n:
+                prefetch(i + 1, (i + 1) % 2)          # next step's H2D overlaps this step's compute
+            torch.cuda.current_stream().wait_event(ready[i % 2])
+            loss = step(slots[i % 2])
+            consumed[i % 2].record()
+            last = loss.item()                         # D2H read of the step's result, every step
+        return last
+
+    e2e_loop(max(2, args.warmup // 2))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last_loss = e2e_loop(args.steps)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    e2e_value = w.batch * world / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the graph kernels (algorithmic bytes, SURVEY.md 8d / DESIGN.md) --------------------------
+    hbm_peak, tf_peak, peak_src = peaks()
+    B, K, nb, H = w.batch, w.n_obj, w.neighbourhood, w.hid_dim
+    Mrows = B * K
+
+    def med(xs):
+        xs = sorted(xs)
+        return xs[len(xs) // 2] if xs else None
+
+    gc_ms = med(timers.get(GC, []))
+    gc_bytes = 2 * Mrows * 2 * H * 4 + 2 * Mrows * nb * 4 + Mrows * 16      # read Y1 + write G1 + idx/alpha + boxes
+    roof = None
+    extra = {}
+    if gc_ms:
+        ach = gc_bytes / (gc_ms * 1e-3) / 1e9
+        roof = {"kernel": "graphconv_fwd_kernel (layer 1: Gaussian weights + gather + aggregate + ReLU + dropout)", "bound": "hbm",
+                "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "traffic": None,
+                "algorithmic_bytes": gc_bytes, "us_per_launch": round(gc_ms * 1e3, 2), "peak_source": peak_src}
+    alg = {ADJ: Mrows * 512 * 4 + Mrows * K * 4 + 2 * Mrows * nb * 4,
+           "vqa_graphconv_pool_fwd_f32": Mrows * H * 4 + Mrows * nb * 4 + Mrows * 16 + 4 * B * H * 4,
+           "vqa_adjacency_topk_bwd_f32": 2 * Mrows * 512 * 4 + 3 * Mrows * nb * 4}
+    for k, nbytes in alg.items():
+        m = med(timers.get(k, []))
+        if m:
+            extra[k] = {"us": round(m * 1e3, 2), "GB/s": round(nbytes / (m * 1e-3) / 1e9, 1), "frac": round(nbytes / (m * 1e-3) / 1e9 / hbm_peak, 4)}
+    bw = sorted(timers.get("vqa_graphconv_bwd_f32", []))
+    if bw:
+        extra["vqa_graphconv_bwd_f32"] = {"us_median_over_both_layers": round(med(bw) * 1e3, 2)}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        from vqa_b200.synthetic import WORKLOADS
+        cores = os.cpu_count() or 1
+        t, _ = cpu_train_steps(WORKLOADS["vqa2_b64"], args.cpu_sample, 4, 1, cores)
+        v = args.cpu_sample * len(t) / sum(t)
+        cpu = {"value": round(v, 3), "unit": "questions/s", "cores": cores, "kind": "port",
+               "sample": f"{len(t)} train steps of {args.cpu_sample} questions (BASELINE config[0] shapes), oracle port, PyTorch CPU"}
+
+    line = {
+        "metric": "train questions/sec (fwd+bwd)", "value": round(value, 1), "unit": "questions/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(w, args, world),
+        "e2e": {"value": round(e2e_value, 1), "unit": "questions/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": round(ms_e2e, 4), "last_loss": last_loss},
+        "gpu_launches": int(launches),
+        "roofline": roof, "roofline_other_kernels": extra, "cpu_baseline": cpu,
+        "clocks": sampler.summary(), "final_loss": float(loss.detach()),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    from vqa_b200.synthetic import WORKLOADS
+    workload = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, workload)
+    else:
+        run_b200(args, workload)
+
+
+if __name__ == "__main__":
+    main()

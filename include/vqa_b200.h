@@ -1,0 +1,125 @@
+/* libvqa_sm100.so -- C ABI of the B200-native conditioned-graph VQA hot path.
+ *
+ * The reference (Originofamonia/vqa-project) has no FFI layer: its hot path is a chain of torch library calls
+ * inside sparse_graph_model.py / layers.py.  This header is the boundary a maintainer binds instead (ctypes stub
+ * in INTEGRATION.md); each entry point names the reference lines it replaces (paths relative to the reference).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer borrowed from the caller (torch owns all buffers, incl. workspaces);
+ *   - kernels are enqueued on `stream`, never allocate, never synchronise;
+ *   - return 0 on success, negative on error; vqa_last_error() gives the (thread-local) message;
+ *   - row-major fp32 everywhere; index tensors are int32 (neighbour ids) or int64 (argmax, as the reference
+ *     returns it); B = images, K = nodes/image (<= 128), nb = neighbourhood size (<= K), nk = Gaussian kernels.
+ */
+#ifndef VQA_B200_H_
+#define VQA_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* vqa_stream_t; /* cudaStream_t */
+
+#define VQA_ABI_VERSION 1
+
+/* GEMM precision modes */
+#define VQA_PREC_TF32X3 0 /* 3-pass split TF32 on tcgen05: fp32-grade results (parity mode)      */
+#define VQA_PREC_TF32 1   /* single-pass TF32 on tcgen05                                           */
+
+/* GEMM epilogue flags */
+#define VQA_GEMM_RELU 1
+#define VQA_GEMM_ATOMIC_ADD 4 /* set internally for split-K: C must be zero-filled by the caller */
+
+/* graph-conv flags */
+#define VQA_GC_RELU 1
+
+const char* vqa_last_error(void);
+int vqa_abi_version(void);
+
+/* C[M,N] = epi( sum_k A[m,k] * B[n,k] ) on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulator, TMA operands).
+ * Operand storage: x_mn_major = 0 -> (MN rows, K contiguous) e.g. activations / nn.Linear weight (out,in);
+ *                  x_mn_major = 1 -> (K rows, MN contiguous) e.g. dY and X in dW = dY^T X.
+ * epi(v) : v += rowbcast[(m / group), n] ; v += bias[n] ; relu ; aux-mask: v = aux[m,n] > 0 ? v*aux_scale : 0.
+ * Replaces: F.linear / weight-norm Linear of layers.py:185-190, the nk conv Linears layers.py:140-142 (one GEMM),
+ * sparse_graph_model.py:154-157, and autograd's mm/addmm backward nodes for all of them.
+ * split_k > 1 accumulates partial tiles with fp32 atomics into a caller-zeroed C (plain epilogue only).
+ * tile_n in {0 (auto), 64, 128, 256}. */
+int vqa_gemm_f32(const float* A, long long lda, int a_mn_major, const float* B, long long ldb, int b_mn_major,
+                 float* C, long long ldc, int M, int N, int Kc, const float* bias, const float* rowbcast,
+                 long long ldrb, int group, const float* aux, long long ldaux, float aux_scale, int flags,
+                 int precision, int split_k, int tile_n, vqa_stream_t stream);
+
+/* y = x * keep / (1-p), keep ~ Bernoulli(1-p) from Philox4x32-10(seed; counter = (element/4, offset)).
+ * Replaces nn.Dropout on the image tensor and the classifier hidden (sparse_graph_model.py:111,156). */
+int vqa_dropout_f32(const float* x, float* y, long long n, float p, unsigned long long seed,
+                    unsigned long long offset, vqa_stream_t stream);
+
+/* Old-style weight norm (dim=0): w[r,:] = v[r,:] * (g[r] / ||v[r,:]||).  torch._weight_norm at layers.py:171-172,
+ * sparse_graph_model.py:88-89.  bwd: given dw returns dv, dg. */
+int vqa_weight_norm_fwd_f32(const float* v, const float* g, float* w, int rows, int cols, vqa_stream_t stream);
+int vqa_weight_norm_bwd_f32(const float* dw, const float* v, const float* g, float* dv, float* dg, int rows,
+                            int cols, vqa_stream_t stream);
+
+/* out[c] = sum_r x[r,c]  (bias gradients; deterministic two-stage reduction, `scratch` >= 256*cols floats) */
+int vqa_colsum_f32(const float* x, long long ldx, float* out, float* scratch, long long rows, int cols,
+                   vqa_stream_t stream);
+/* out[s,c] = sum_{i<seg_len} x[s*seg_len+i, c]  (gradient of the per-image broadcast question term) */
+int vqa_segment_sum_f32(const float* x, float* out, int segments, int seg_len, int cols, vqa_stream_t stream);
+
+/* Fused graph-learner tail: per image A = h h^T (fp32 FMA), per-row top-nb selection and softmax.
+ * h (B,K,C) -> adjacency (B,K,K), idx (B,K,nb) int32 in DESCENDING value order, alpha (B,K,nb).
+ * Replaces layers.py:193-195 and sparse_graph_model.py:225-227 (topk sorted=False + K softmax launches). */
+int vqa_adjacency_topk_fwd_f32(const float* h, float* adjacency, int* idx, float* alpha, int B, int K, int C,
+                               int nb, vqa_stream_t stream);
+/* Same selection/softmax from a GIVEN adjacency (used for the bit-exact index parity test and the layer API). */
+int vqa_topk_softmax_f32(const float* adjacency, int* idx, float* alpha, int B, int K, int nb, vqa_stream_t stream);
+/* Backward of the above: dalpha (B,K,nb) [+ optional dadj (B,K,K)] -> dh (B,K,C), already multiplied by the
+ * ReLU mask (h > 0) of the layer that produced h. */
+int vqa_adjacency_topk_bwd_f32(const float* h, const int* idx, const float* alpha, const float* dalpha,
+                               const float* dadj, float* dh, int B, int K, int C, int nb, vqa_stream_t stream);
+
+/* Fused graph convolution, project-first: Y = X W_all^T comes from vqa_gemm_f32; this kernel computes the
+ * Gaussian patch weights over polar pseudo-coordinates of the box centres (boxes = xyxy, row stride ldbox floats),
+ * normalises them over the kernel axis, gathers neighbours and aggregates:
+ *   out[b,i, chunk k] = act( sum_m w[b,i,m,k] * alpha[b,i,m] * Y[b, idx[b,i,m], chunk k] ),  chunk = out_dim/nk.
+ * gauss = {mean_rho[nk], precision_rho[nk], mean_theta[nk], precision_theta[nk]}.  alpha may be NULL (== 1).
+ * Optional fused dropout (p > 0) after the ReLU.  Replaces sparse_graph_model.py:161-195,239-240,244-269 and
+ * layers.py:100-144 (+ relu/dropout :137-138,148). */
+int vqa_graphconv_fwd_f32(const float* Y, long long ldy, const int* idx, const float* alpha, const float* boxes,
+                          long long ldbox, const float* gauss, float* out, long long ldo, int B, int K, int nb,
+                          int nk, int out_dim, int flags, float dropout_p, unsigned long long seed,
+                          unsigned long long offset, vqa_stream_t stream);
+/* Second layer with the pooling tail fused: relu, max over the K nodes (first index on ties), gate with relu(q):
+ * pooled (B,out), argmax (B,out) int64, hq = relu(q) * pooled.  sparse_graph_model.py:146-151. */
+int vqa_graphconv_pool_fwd_f32(const float* Y, long long ldy, const int* idx, const float* boxes, long long ldbox,
+                               const float* gauss, const float* q, float* pooled, long long* argmax, float* hq,
+                               int B, int K, int nb, int nk, int out_dim, vqa_stream_t stream);
+/* Backward data path of the aggregate.  Upstream gradient is either dense dO (B,K,out) (already ReLU/dropout
+ * masked) or, for the pooled layer, dpooled (B,out) + argmax (scatter by argmax is done on the fly).
+ * Writes dY (B,K,out) and the per-edge, per-kernel dot products P (B,K,nb,nk) = <dO[i,chunk k], Y[idx,chunk k]>. */
+int vqa_graphconv_bwd_f32(const float* dO, long long lddo, const float* dpooled, const long long* argmax,
+                          const float* Y, long long ldy, const int* idx, const float* alpha, const float* boxes,
+                          long long ldbox, const float* gauss, float* dY, long long lddy, float* P, int B, int K,
+                          int nb, int nk, int out_dim, vqa_stream_t stream);
+/* Edge-level finish of the backward: from P computes dalpha (B,K,nb) (NULL when alpha is NULL) and the partial
+ * sums of the four Gaussian parameter gradients, dgauss_partial (nblocks, 4*nk) with nblocks returned by
+ * vqa_graphconv_edge_blocks(); reduce them with vqa_colsum_f32.  SURVEY.md 9.2. */
+int vqa_graphconv_edge_blocks(int B, int K, int nb);
+int vqa_graphconv_edge_bwd_f32(const float* P, const int* idx, const float* alpha, const float* boxes,
+                               long long ldbox, const float* gauss, float* dalpha, float* dgauss_partial, int B,
+                               int K, int nb, int nk, vqa_stream_t stream);
+
+/* Gaussian patch weights for explicit pseudo-coordinates (n,2) -> (n,nk): NeighbourhoodGraphConvolution.
+ * get_gaussian_weights, layers.py:100-125 (layer-level API). */
+int vqa_gaussian_weights_f32(const float* pseudo, const float* gauss, float* w, long long n, int nk,
+                             vqa_stream_t stream);
+
+/* Gate/pool backward: dpooled = pooled > 0 ? dhq * relu(q) : 0 ;  dq = q > 0 ? dhq * pooled : 0.
+ * sparse_graph_model.py:150-151 (autograd of max + relu*mul). */
+int vqa_gate_bwd_f32(const float* dhq, const float* q, const float* pooled, float* dpooled, float* dq, long long n,
+                     vqa_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQA_B200_H_ */

@@ -1,0 +1,324 @@
+"""Kernel-level parity: every C-ABI entry point against the oracle / fp64 torch maths on the same inputs.
+
+All tests call through ``libvqa_sm100.so`` (ctypes) on the GPU; the oracle (``oracle/vqa_oracle.py``) and
+plain fp64 torch expressions are only the checkers.  Tolerances are max-norm relative errors
+(``conftest.rel_err``); fp32 budget from BASELINE.json north_star: 1e-3.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, golden_params, rel_err
+from oracle import vqa_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def kn():
+    from vqa_b200 import kernels
+    return kernels
+
+
+def _pack_gauss(p, prefix, device=DEV, dtype=torch.float32):
+    return torch.cat([p[f"{prefix}.{k}"].reshape(-1) for k in
+                      ("mean_rho", "precision_rho", "mean_theta", "precision_theta")]).to(device=device, dtype=dtype).contiguous()
+
+
+# --------------------------------------------------------------------------------------------- GEMM
+GEMM_CASES = [
+    # M, N, K, a_mn, b_mn, tile_n
+    (128, 256, 64, False, False, 0),
+    (300, 520, 132, False, False, 0),      # ragged M/N/K tails (TMA zero fill + predicated epilogue)
+    (256, 512, 2052, False, False, 256),   # F = 2052: K not a multiple of the 32-wide k-block
+    (256, 128, 96, False, False, 128),
+    (64, 64, 32, False, False, 64),
+    (200, 264, 160, False, True, 0),       # dX = dY . W : B stored (K, N)
+    (264, 200, 300, True, True, 0),        # dW = dY^T . X : both operands MN-major
+    (128, 3000, 512, True, True, 256),
+    (36, 512, 3076, False, False, 0),      # GraphLearner layer-1 shape on one image
+]
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,tile_n", GEMM_CASES)
+@pytest.mark.parametrize("prec,tol", [(0, 5e-5), (1, 3e-3)])  # x3: tensor-core accumulators truncate (~K*2^-24)
+def test_gemm_matches_fp64(kn, M, N, K, a_mn, b_mn, tile_n, prec, tol):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn(N, K, generator=g)
+    ref = a.double() @ b.double().t()
+    a_dev = (a.t().contiguous() if a_mn else a).to(DEV)
+    b_dev = (b.t().contiguous() if b_mn else b).to(DEV)
+    out = kn.gemm(a_dev, b_dev, a_mn=a_mn, b_mn=b_mn, precision=prec, tile_n=tile_n)
+    torch.cuda.synchronize()
+    assert out.shape == (M, N)
+    assert rel_err(out.cpu(), ref) < tol
+
+
+def test_gemm_epilogues_and_views(kn):
+    g = torch.Generator().manual_seed(5)
+    B, Kn, F, N = 5, 12, 40, 72
+    M = B * Kn
+    x = torch.randn(M, F, generator=g)
+    wfull = torch.randn(N, F + 16, generator=g)          # weight with extra columns: use a column sub-view (ld != K)
+    w = wfull[:, :F]
+    bias = torch.randn(N, generator=g)
+    rb = torch.randn(B, N, generator=g)
+    aux = torch.randn(M, N, generator=g)
+    ref = x.double() @ w.double().t() + rb.double().repeat_interleave(Kn, 0) + bias.double()
+    ref_relu = ref.clamp(min=0)
+    out = kn.gemm(x.to(DEV), wfull.to(DEV)[:, :F], bias=bias.to(DEV), rowbcast=rb.to(DEV), group=Kn, relu=True)
+    assert rel_err(out.cpu(), ref_relu) < 5e-5
+    # aux mask + scale (ReLU / dropout backward fused into the dX GEMM)
+    out2 = kn.gemm(x.to(DEV), w.contiguous().to(DEV), aux=aux.to(DEV), aux_scale=2.0)
+    ref2 = torch.where(aux > 0, 2.0 * (x.double() @ w.double().t()), torch.zeros((), dtype=torch.float64))
+    assert rel_err(out2.cpu(), ref2) < 5e-5
+    # write into a column slice of a wider buffer (ldc != N)
+    big = torch.zeros(M, N + 24, device=DEV)
+    kn.gemm(x.to(DEV), w.contiguous().to(DEV), out=big[:, 8:8 + N])
+    assert rel_err(big[:, 8:8 + N].cpu(), x.double() @ w.double().t()) < 5e-5
+    assert big[:, :8].abs().max() == 0 and big[:, 8 + N:].abs().max() == 0
+
+
+@pytest.mark.parametrize("split", [2, 5, 16])
+def test_gemm_split_k(kn, split):
+    g = torch.Generator().manual_seed(9)
+    Kc, M, N = 1000, 96, 200
+    a = torch.randn(Kc, M, generator=g)
+    b = torch.randn(Kc, N, generator=g)
+    out = kn.gemm(a.to(DEV), b.to(DEV), a_mn=True, b_mn=True, split_k=split)
+    assert rel_err(out.cpu(), a.double().t() @ b.double()) < 5e-5
+
+
+def test_gemm_rejects_bad_arguments(kn):
+    a = torch.randn(8, 30, device=DEV)     # ld = 30: not a multiple of 4 floats -> TMA illegal
+    b = torch.randn(8, 30, device=DEV)
+    with pytest.raises(RuntimeError):
+        kn.gemm(a, b)
+    with pytest.raises(RuntimeError):
+        kn.gemm(torch.randn(8, 32), torch.randn(8, 32))   # CPU tensors: no fallback
+
+
+# --------------------------------------------------------------------------------------------- small kernels
+def test_dropout_statistics_and_determinism(kn):
+    x = torch.ones(1 << 20, device=DEV)
+    for p in (0.5, 0.4, 0.1):
+        y = kn.dropout(x, p, seed=1234, offset=7)
+        keep = (y != 0).float().mean().item()
+        assert abs(keep - (1 - p)) < 4e-3
+        assert torch.allclose(y[y != 0], torch.full((), 1 / (1 - p), device=DEV))
+        assert torch.equal(y, kn.dropout(x, p, seed=1234, offset=7))
+        assert not torch.equal(y, kn.dropout(x, p, seed=1234, offset=8))
+    y = kn.dropout(torch.randn(1003, device=DEV), 0.0, 1, 1)   # ragged tail, p = 0 is the identity
+    assert y.shape == (1003,)
+
+
+def test_weight_norm_fwd_bwd(kn):
+    torch.manual_seed(3)
+    v = torch.randn(70, 133, device=DEV, requires_grad=True)
+    g = torch.rand(70, 1, device=DEV, requires_grad=True) + 0.5
+    g = g.detach().requires_grad_(True)
+    w_ref = torch._weight_norm(v, g, 0)
+    w = kn.weight_norm_fwd(v.detach(), g.detach())
+    assert rel_err(w.cpu(), w_ref.detach().cpu()) < 1e-6
+    dw = torch.randn_like(w_ref)
+    w_ref.backward(dw)
+    dv, dg = kn.weight_norm_bwd(dw, v.detach(), g.detach())
+    assert rel_err(dv.cpu(), v.grad.cpu()) < 1e-5
+    assert rel_err(dg.cpu(), g.grad.cpu()) < 1e-5
+
+
+def test_reductions_and_gate(kn):
+    torch.manual_seed(4)
+    x = torch.randn(36 * 17, 200, device=DEV)
+    assert rel_err(kn.colsum(x).cpu(), x.double().sum(0).cpu()) < 1e-6
+    assert rel_err(kn.colsum(x[:, 8:72]).cpu(), x[:, 8:72].double().sum(0).cpu()) < 1e-6
+    assert rel_err(kn.segment_sum(x, 36).cpu(), x.double().view(17, 36, 200).sum(1).cpu()) < 1e-6
+    dhq, q, pooled = torch.randn(3, 50, device=DEV), torch.randn(3, 50, device=DEV), torch.randn(3, 50, device=DEV).clamp(min=0)
+    dpooled, dq = kn.gate_bwd(dhq, q, pooled)
+    assert torch.allclose(dpooled, torch.where((pooled > 0) & (q > 0), dhq * q, torch.zeros_like(q)))
+    assert torch.allclose(dq, torch.where(q > 0, dhq * pooled, torch.zeros_like(q)))
+
+
+# --------------------------------------------------------------------------------------------- graph learner tail
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_topk_indices_bit_exact_given_reference_adjacency(kn, name):
+    """north_star: top-k neighbourhood indices bit-exact when given the reference's adjacency."""
+    g = load_golden(name)
+    adj = torch.from_numpy(g["out.adjacency"]).to(DEV)
+    nb = g["nbr.idx_sorted"].shape[-1]
+    idx, alpha = kn.topk_softmax(adj, nb)
+    order = idx.long().argsort(-1)
+    assert np.array_equal(torch.gather(idx.long(), -1, order).cpu().numpy(), g["nbr.idx_sorted"])
+    assert rel_err(torch.gather(alpha, -1, order).cpu(), g["nbr.alpha_sorted"]) < 1e-6
+    # emitted in descending value order
+    vals = torch.gather(adj, -1, idx.long())
+    assert (vals[..., :-1] >= vals[..., 1:]).all()
+
+
+@pytest.mark.parametrize("B,K,C,nb", [(7, 36, 512, 16), (3, 51, 512, 19), (2, 100, 512, 32), (4, 12, 64, 5), (2, 128, 128, 128), (3, 5, 8, 1)])
+def test_adjacency_topk_fwd(kn, B, K, C, nb):
+    torch.manual_seed(B * 100 + K)
+    h = torch.randn(B, K, C, device=DEV).clamp(min=0)
+    adj, idx, alpha = kn.adjacency_topk_fwd(h, nb)
+    ref = h.double() @ h.double().transpose(1, 2)
+    assert rel_err(adj.cpu(), ref.cpu()) < 5e-5
+    assert torch.equal(adj, adj.transpose(1, 2))            # symmetric by construction
+    # selection is exact w.r.t. the adjacency the kernel itself produced
+    tv, ti = torch.topk(adj, nb, dim=-1)
+    assert torch.equal(idx.long().sort(-1).values, ti.sort(-1).values)
+    a_ref = torch.softmax(torch.gather(adj, -1, idx.long()).double(), -1)
+    assert rel_err(alpha.cpu(), a_ref.cpu()) < 1e-6
+
+
+def test_topk_tie_rule(kn):
+    adj = torch.zeros(1, 6, 6, device=DEV)
+    adj[0, :, 2] = 1.0
+    adj[0, :, 4] = 1.0
+    idx, alpha = kn.topk_softmax(adj, 3)
+    # ties: lower index first; any index whose value equals the k-th value is a valid member (SURVEY.md trap 1)
+    assert idx[0, 0].tolist() == [2, 4, 0]
+    assert torch.allclose(alpha.sum(-1), torch.ones(1, 6, device=DEV))
+
+
+@pytest.mark.parametrize("B,K,C,nb,with_dadj", [(5, 36, 512, 16, False), (2, 51, 512, 19, True), (2, 100, 256, 32, False), (3, 12, 64, 5, True)])
+def test_adjacency_topk_bwd(kn, B, K, C, nb, with_dadj):
+    torch.manual_seed(K)
+    hpre = torch.randn(B, K, C, device=DEV, dtype=torch.float64) * 0.08   # keep the softmax unsaturated: fp32 cancellation otherwise
+    hpre.requires_grad_(True)
+    h = torch.relu(hpre)
+    adj = h @ h.transpose(1, 2)
+    _, idx32, alpha32 = kn.adjacency_topk_fwd(h.detach().float(), nb)
+    idx = idx32.long()
+    alpha = torch.softmax(torch.gather(adj, -1, idx), -1)
+    dalpha = torch.randn(B, K, nb, device=DEV, dtype=torch.float64)
+    dadj = torch.randn(B, K, K, device=DEV, dtype=torch.float64) if with_dadj else None
+    loss = (alpha * dalpha).sum() + ((adj * dadj).sum() if with_dadj else 0.0)
+    (gref,) = torch.autograd.grad(loss, hpre)
+    got = kn.adjacency_topk_bwd(h.detach().float(), idx32, alpha32, dalpha.float(), None if dadj is None else dadj.float())
+    assert rel_err(got.cpu(), gref.cpu()) < 2e-5
+
+
+# --------------------------------------------------------------------------------------------- graph convolution
+def _gc_reference(Y, idx, alpha, image, gauss_p, prefix, nk):
+    """fp64 oracle of the project-first aggregate: gather rows of Y with the oracle's own Gaussian weights."""
+    B, K, nb = idx.shape
+    cen = O.box_centres(image)
+    pseudo = O.gather_pseudo(O.polar_pseudo_coordinates(cen), idx)
+    w = O.gaussian_kernel_weights(pseudo, gauss_p, prefix).view(B, K, nb, nk)
+    D = Y.shape[-1] // nk
+    nbr = O.gather_neighbours(Y.view(B, K, -1), idx).view(B, K, nb, nk, D)
+    coef = w if alpha is None else w * alpha.unsqueeze(-1)
+    return (coef.unsqueeze(-1) * nbr).sum(2).reshape(B, K, nk * D)
+
+
+def _gc_inputs(B, K, nb, nk, out_dim, F=12, seed=0, dtype=torch.float64):
+    g = torch.Generator().manual_seed(seed)
+    image = torch.rand(B, K, F, generator=g, dtype=dtype)
+    xy1 = torch.rand(B, K, 2, generator=g, dtype=dtype) * 0.7
+    image[..., -4:-2] = xy1
+    image[..., -2:] = xy1 + torch.rand(B, K, 2, generator=g, dtype=dtype) * 0.25 + 0.05
+    Y = torch.randn(B, K, out_dim, generator=g, dtype=dtype)
+    idx = torch.stack([torch.stack([torch.randperm(K, generator=g)[:nb] for _ in range(K)]) for _ in range(B)])
+    alpha = torch.softmax(torch.randn(B, K, nb, generator=g, dtype=dtype), -1)
+    gp = {"gc.mean_rho": torch.rand(nk, 1, generator=g, dtype=dtype), "gc.mean_theta": (torch.rand(nk, 1, generator=g, dtype=dtype) * 2 - 1) * math.pi,
+          "gc.precision_rho": torch.rand(nk, 1, generator=g, dtype=dtype) * 0.9 + 0.1, "gc.precision_theta": torch.rand(nk, 1, generator=g, dtype=dtype) * 0.9 + 0.1}
+    return image, Y, idx, alpha, gp
+
+
+GC_CASES = [(4, 36, 16, 8, 2048), (3, 36, 16, 8, 1024), (2, 51, 19, 4, 512), (2, 51, 36, 32, 1024), (1, 100, 32, 8, 512),
+            (3, 12, 5, 4, 32), (2, 12, 5, 4, 16), (2, 7, 7, 2, 24)]
+
+
+@pytest.mark.parametrize("B,K,nb,nk,out_dim", GC_CASES)
+@pytest.mark.parametrize("use_alpha", [True, False])
+def test_graphconv_fwd(kn, B, K, nb, nk, out_dim, use_alpha):
+    image, Y, idx, alpha, gp = _gc_inputs(B, K, nb, nk, out_dim, seed=K + nb)
+    ref = torch.relu(_gc_reference(Y, idx, alpha if use_alpha else None, image, gp, "gc", nk))
+    gauss = _pack_gauss(gp, "gc")
+    out = kn.graphconv_fwd(Y.float().view(B * K, -1).to(DEV), idx.int().to(DEV), alpha.float().to(DEV) if use_alpha else None,
+                           image.float().to(DEV), gauss, B, K, relu=True)
+    assert rel_err(out.view(B, K, -1).cpu(), ref) < 2e-5
+
+
+def test_graphconv_fused_dropout(kn):
+    B, K, nb, nk, out_dim = 6, 36, 16, 8, 2048
+    image, Y, idx, alpha, gp = _gc_inputs(B, K, nb, nk, out_dim, seed=11)
+    args = (Y.float().view(B * K, -1).to(DEV), idx.int().to(DEV), alpha.float().to(DEV), image.float().to(DEV), _pack_gauss(gp, "gc"), B, K)
+    base = kn.graphconv_fwd(*args, relu=True)
+    dropped = kn.graphconv_fwd(*args, relu=True, dropout_p=0.5, seed=42, offset=3)
+    kept = dropped != 0
+    assert torch.allclose(dropped[kept], 2.0 * base[kept])
+    pos = base > 0
+    assert abs((kept & pos).sum().item() / pos.sum().item() - 0.5) < 0.01
+    assert torch.equal(dropped, kn.graphconv_fwd(*args, relu=True, dropout_p=0.5, seed=42, offset=3))
+
+
+@pytest.mark.parametrize("B,K,nb,nk,out_dim", GC_CASES)
+def test_graphconv_pool_fwd(kn, B, K, nb, nk, out_dim):
+    image, Y, idx, alpha, gp = _gc_inputs(B, K, nb, nk, out_dim, seed=2 * K + nb)
+    g2 = torch.relu(_gc_reference(Y, idx, None, image, gp, "gc", nk))
+    pooled_ref, arg_ref = g2.max(1)
+    q = torch.randn(B, out_dim, dtype=torch.float64)
+    pooled, arg, hq = kn.graphconv_pool_fwd(Y.float().view(B * K, -1).to(DEV), idx.int().to(DEV), image.float().to(DEV),
+                                            _pack_gauss(gp, "gc"), q.float().to(DEV), B, K)
+    assert rel_err(pooled.cpu(), pooled_ref) < 2e-5
+    assert rel_err(hq.cpu(), torch.relu(q) * pooled_ref) < 2e-5
+    assert arg.dtype == torch.int64
+    top2 = g2.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 1e-4 * top2[:, 0].abs().clamp(min=1e-3)
+    assert torch.equal(arg.cpu()[safe], arg_ref[safe])
+    # all-zero columns (every node <= 0 after ReLU): first index, as torch.max on CPU
+    zero_cols = pooled_ref == 0
+    assert (arg.cpu()[zero_cols] == 0).all()
+
+
+@pytest.mark.parametrize("B,K,nb,nk,out_dim", GC_CASES)
+@pytest.mark.parametrize("mode", ["dense_alpha", "dense", "pooled"])
+def test_graphconv_bwd(kn, B, K, nb, nk, out_dim, mode):
+    image, Y, idx, alpha, gp = _gc_inputs(B, K, nb, nk, out_dim, seed=3 * K + nb)
+    Yr = Y.clone().requires_grad_(True)
+    ar = alpha.clone().requires_grad_(True)
+    gpr = {k: v.clone().requires_grad_(True) for k, v in gp.items()}
+    use_alpha = mode == "dense_alpha"
+    out = _gc_reference(Yr, idx, ar if use_alpha else None, image, gpr, "gc", nk)
+    g = torch.Generator().manual_seed(1)
+    gauss = _pack_gauss(gp, "gc")
+    common = (Y.float().view(B * K, -1).to(DEV), idx.int().to(DEV), alpha.float().to(DEV) if use_alpha else None, image.float().to(DEV), gauss, B, K)
+    if mode == "pooled":
+        arg = torch.randint(0, K, (B, out_dim), generator=g)
+        dpooled = torch.randn(B, out_dim, generator=g, dtype=torch.float64)
+        dO = torch.zeros(B, K, out_dim, dtype=torch.float64).scatter_(1, arg.unsqueeze(1), dpooled.unsqueeze(1))
+        dY, dalpha, dgauss = kn.graphconv_bwd(*common, dpooled=dpooled.float().to(DEV), argmax=arg.to(DEV))
+    else:
+        dO = torch.randn(B, K, out_dim, generator=g, dtype=torch.float64)
+        dY, dalpha, dgauss = kn.graphconv_bwd(*common, dO=dO.float().view(B * K, -1).to(DEV))
+    wanted = [Yr] + [gpr[f"gc.{k}"] for k in ("mean_rho", "precision_rho", "mean_theta", "precision_theta")] + ([ar] if use_alpha else [])
+    grads = torch.autograd.grad((out * dO).sum(), wanted)
+    assert rel_err(dY.view(B, K, -1).cpu(), grads[0]) < 2e-5
+    dg_ref = torch.cat([x.reshape(-1) for x in grads[1:5]])
+    assert rel_err(dgauss.cpu(), dg_ref) < 2e-4
+    if use_alpha:
+        assert rel_err(dalpha.cpu(), grads[5]) < 2e-5
+    else:
+        assert dalpha is None
+
+
+def test_gaussian_weights_match_reference_golden(kn):
+    g = load_golden("tiny")
+    p = golden_params(g)
+    w = kn.gaussian_weights(torch.from_numpy(g["layer.nbr_pseudo"]).to(DEV), _pack_gauss(p, "graph_convolution_1"))
+    assert rel_err(w.cpu(), g["layer.gauss_w"]) < 1e-5
+
+
+def test_graphconv_argument_errors(kn):
+    image, Y, idx, alpha, gp = _gc_inputs(2, 12, 5, 4, 32)
+    gauss = _pack_gauss(gp, "gc")
+    with pytest.raises(RuntimeError):   # out_dim / nk not a multiple of 4
+        kn.graphconv_fwd(torch.randn(24, 24, device=DEV), idx.int().to(DEV), None, image.float().to(DEV), gauss, 2, 12)
+    with pytest.raises(RuntimeError):   # nb > K
+        kn.topk_softmax(torch.randn(1, 4, 4, device=DEV), 5)

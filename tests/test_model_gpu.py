@@ -1,0 +1,172 @@
+"""Module-level parity on the GPU: the drop-in Model / GraphLearner / NeighbourhoodGraphConvolution loaded with the
+REFERENCE's state_dict must reproduce the reference's golden outputs and gradients (fp32 budget: 1e-3 relative,
+BASELINE.json north_star).  Golden vectors: tests/golden/*.npz (generated from /root/reference by make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, golden_params, rel_err
+from oracle import vqa_oracle as O
+from vqa_b200.synthetic import WORKLOADS, make_batch, make_wemb
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-3          # north_star budget
+TIGHT = 2e-4        # what the tf32x3 path actually achieves on these shapes
+
+
+def _build(name, g):
+    import sparse_graph_model as M
+    w = WORKLOADS[name]
+    model = M.Model(pretrained_wemb=make_wemb(w), **w.model_kwargs())
+    model.load_state_dict({k: v for k, v in golden_params(g).items()})
+    return w, model.to(DEV)
+
+
+def _inputs(g):
+    q = torch.from_numpy(g["in.question"]).to(DEV)
+    img = torch.from_numpy(g["in.image"]).to(DEV)
+    qlen = [torch.tensor(int(x)) for x in g["in.qlen"]]
+    K = torch.full((q.shape[0], 1), img.shape[1], dtype=torch.int64, device=DEV)
+    tgt = torch.from_numpy(g["in.target"]).to(DEV)
+    return q, img, K, qlen, tgt
+
+
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_model_forward_backward_matches_reference(name):
+    g = load_golden(name)
+    w, model = _build(name, g)
+    model.train()          # dropout p = 0 in these workloads
+    q, img, K, qlen, tgt = _inputs(g)
+    logits, adj, arg = model(q, img, K, qlen)
+    assert logits.shape == g["out.logits"].shape and adj.shape == g["out.adjacency"].shape
+    assert arg.dtype == torch.int64 and arg.shape == g["out.h_max_indices"].shape
+    e_log, e_adj = rel_err(logits.detach().cpu(), g["out.logits"]), rel_err(adj.detach().cpu(), g["out.adjacency"])
+    print(f"{name}: logits rel err {e_log:.2e}, adjacency rel err {e_adj:.2e}")
+    assert e_log < TIGHT and e_adj < TIGHT
+
+    # neighbour sets: identical wherever the nb-th / (nb+1)-th margin is not a rounding artefact
+    from vqa_b200 import kernels as kn
+    idx, _ = kn.topk_softmax(adj.detach(), w.neighbourhood)
+    got = idx.long().sort(-1).values.cpu().numpy()
+    safe = g["nbr.margin"] > 1e-4 * np.abs(g["out.adjacency"]).max()
+    assert safe.mean() > 0.9
+    assert np.array_equal(got[safe], g["nbr.idx_sorted"][safe])
+
+    # argmax over nodes: compare where the reference's top-2 gap is meaningful
+    p = golden_params(g)
+    _, _, _, inter = O.forward(p, torch.from_numpy(g["in.question"]), torch.from_numpy(g["in.image"]),
+                               [int(x) for x in g["in.qlen"]], w.neighbourhood, w.n_kernels, return_intermediates=True)
+    top2 = inter["g2"].topk(2, dim=1).values
+    ok = (top2[:, 0] - top2[:, 1]) > 1e-3 * top2[:, 0].abs().clamp(min=1e-3)
+    assert torch.equal(arg.cpu()[ok], torch.from_numpy(g["out.h_max_indices"])[ok])
+
+    loss = torch.nn.MultiLabelSoftMarginLoss()(logits, tgt)
+    assert abs(loss.item() - float(g["out.loss"])) < 1e-5
+    model.zero_grad()
+    loss.backward()
+    worst = ("", 0.0)
+    for k, v in model.named_parameters():
+        e = rel_err(v.grad.cpu(), g["grad." + k])
+        if e > worst[1]:
+            worst = (k, e)
+        assert e < TOL, (k, e)
+    print(f"{name}: worst gradient rel err {worst[1]:.2e} ({worst[0]})")
+    assert worst[1] < 5e-4
+
+
+def test_eval_mode_and_no_grad_match_train_mode_without_dropout():
+    g = load_golden("tiny")
+    _, model = _build("tiny", g)
+    q, img, K, qlen, _ = _inputs(g)
+    model.eval()
+    with torch.no_grad():
+        logits, adj, arg = model(q, img, K, qlen)
+    assert rel_err(logits.cpu(), g["out.logits"]) < TIGHT
+
+
+def test_layer_api_graph_learner_and_graph_convolution():
+    g = load_golden("tiny")
+    w, model = _build("tiny", g)
+    nodes = torch.from_numpy(g["layer.graph_nodes"]).to(DEV)
+    adj = model.adjacency_1(nodes)
+    assert rel_err(adj.detach().cpu(), g["layer.adjacency"]) < TIGHT
+    nbr = torch.from_numpy(g["layer.nbr_feat"]).to(DEV)
+    pseudo = torch.from_numpy(g["layer.nbr_pseudo"]).to(DEV)
+    gc1 = model.graph_convolution_1
+    assert rel_err(gc1.get_gaussian_weights(pseudo).detach().cpu(), g["layer.gauss_w"]) < 1e-5
+    out = gc1(nbr, pseudo)
+    assert out.shape == g["layer.gc1_out"].shape
+    assert rel_err(out.detach().cpu(), g["layer.gc1_out"]) < TIGHT
+    # gradients flow through the layer API too (checked against the fp64 oracle)
+    p = {k: v.double().requires_grad_(True) for k, v in golden_params(g).items()}
+    ref = O.graph_convolution(nbr.cpu().double(), pseudo.cpu().double(), p, "graph_convolution_1", w.n_kernels)
+    go = torch.randn(ref.shape, generator=torch.Generator().manual_seed(0), dtype=torch.float64)
+    names = ["graph_convolution_1.mean_rho", "graph_convolution_1.precision_theta", "graph_convolution_1.conv_weights.1.weight"]
+    gref = torch.autograd.grad((ref * go).sum(), [p[n] for n in names])
+    model.zero_grad()
+    (out * go.float().to(DEV)).sum().backward()
+    got = [gc1.mean_rho.grad, gc1.precision_theta.grad, gc1.conv_weights[1].weight.grad]
+    for n, a, b in zip(names, got, gref):
+        assert rel_err(a.cpu(), b) < TOL, n
+    # GraphLearner backward
+    nodes.requires_grad_(True)
+    a = model.adjacency_1(nodes)
+    a.sum().backward()
+    assert nodes.grad is not None and torch.isfinite(nodes.grad).all()
+
+
+def test_fused_dropout_training_step_is_stochastic_but_seeded():
+    g = load_golden("tiny")
+    w, model = _build("tiny", g)
+    model.dropout.p = 0.5
+    model.train()
+    q, img, K, qlen, tgt = _inputs(g)
+    torch.manual_seed(7)
+    a = model(q, img, K, qlen)[0]
+    torch.manual_seed(7)
+    b = model(q, img, K, qlen)[0]
+    c = model(q, img, K, qlen)[0]
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    loss = torch.nn.MultiLabelSoftMarginLoss()(c, tgt)
+    loss.backward()
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+
+
+def test_shape_errors_raise_before_launch():
+    g = load_golden("tiny")
+    _, model = _build("tiny", g)
+    q, img, K, qlen, _ = _inputs(g)
+    with pytest.raises(ValueError):
+        model(q, img[:, :-1], K, qlen)           # n_obj != K
+    with pytest.raises(ValueError):
+        model(q, img[:, :, :-4].contiguous(), K, qlen)   # wrong feat_dim
+
+
+def test_full_size_properties_vqa2_b512():
+    """BASELINE.json config[1] sizes: size-independent properties instead of a (too slow) oracle run."""
+    import sparse_graph_model as M
+    w = WORKLOADS["vqa2_b512"]
+    torch.manual_seed(1000)
+    model = M.Model(pretrained_wemb=make_wemb(w), **w.model_kwargs()).to(DEV)
+    with torch.no_grad():   # avoid degenerate Gaussian widths (0/0 rows are legal but make every check NaN)
+        for gc in (model.graph_convolution_1, model.graph_convolution_2):
+            gc.precision_rho.clamp_(min=0.05); gc.precision_theta.clamp_(min=0.05)
+    model.eval()
+    batch = make_batch(w, seed=3, batch=128)
+    q, img, K = batch["question"].to(DEV), batch["image"].to(DEV), batch["K"].to(DEV)
+    with torch.no_grad():
+        logits, adj, arg = model(q, img, K, batch["qlen"])
+        # (1) per-sample independence: a sub-batch gives the same rows
+        l2, a2, g2 = model(q[5:37], img[5:37], K[5:37], batch["qlen"][5:37])
+    assert torch.isfinite(logits).all()
+    assert rel_err(l2.cpu(), logits[5:37].cpu()) < 1e-5 and torch.equal(a2, adj[5:37])
+    # (2) adjacency symmetric PSD-diagonal, (3) argmax within range
+    assert torch.equal(adj, adj.transpose(1, 2)) and (adj.diagonal(dim1=1, dim2=2) >= 0).all()
+    assert arg.min() >= 0 and arg.max() < w.n_obj
+    # (4) permuting the nodes of an image permutes the adjacency and leaves the logits unchanged
+    perm = torch.randperm(w.n_obj, device=DEV)
+    with torch.no_grad():
+        lp, ap, _ = model(q[:16], img[:16][:, perm], K[:16], batch["qlen"][:16])
+    assert rel_err(lp.cpu(), logits[:16].cpu()) < 1e-4
+    assert rel_err(ap.cpu(), adj[:16][:, perm][:, :, perm].cpu()) < 1e-5

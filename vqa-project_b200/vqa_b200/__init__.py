@@ -1,0 +1,7 @@
+"""vqa_b200: host side of the B200-native conditioned-graph VQA hot path.
+
+``layers.py`` / ``sparse_graph_model.py`` next to this package are the drop-in modules; this package holds the
+ctypes binding of ``libvqa_sm100.so`` (``_cabi``), tensor-level kernel wrappers (``kernels``), the autograd
+operators (``ops``), the data-parallel gradient reducer (``ddp``) and the synthetic workload generator.
+"""
+__all__ = ["_cabi", "kernels", "ops", "ddp", "synthetic"]

@@ -1,0 +1,256 @@
+"""Tensor-level wrappers over the C ABI: argument checking, output allocation, stream plumbing.
+
+PyTorch is used here only for device memory and streams.  Every function enqueues hand-written
+sm_100a kernels from ``libvqa_sm100.so`` on the current CUDA stream and returns immediately.
+``LAUNCHES`` counts kernel launches issued through this module (bench.py reports it).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import PREC_TF32, PREC_TF32X3, GEMM_RELU, GC_RELU
+
+LAUNCHES = 0
+_LAUNCH_COST = {"vqa_colsum_f32": 2}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (the vqa_b200 path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# name -> list of (start_event, end_event): filled when a caller (bench.py) asks for in-stream kernel timing
+TIMERS = {}
+
+
+def enable_timing(*names: str) -> None:
+    """Record CUDA events on the launching stream around every launch of the named entry points."""
+    TIMERS.clear()
+    for n in names:
+        TIMERS[n] = []
+
+
+def _call(name, *args):
+    global LAUNCHES
+    rec = TIMERS.get(name)
+    if rec is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _cabi.call(name, *args)
+        e1.record()
+        rec.append((e0, e1))
+    else:
+        _cabi.call(name, *args)
+    LAUNCHES += _LAUNCH_COST.get(name, 1)
+
+
+def _rows_view(t: torch.Tensor, name: str) -> Tuple[torch.Tensor, int]:
+    """2-D tensor whose rows are contiguous -> (tensor, leading dimension in elements)."""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise RuntimeError(f"{name}: need a 2-D tensor with unit inner stride, got shape {tuple(t.shape)} strides {t.stride()}")
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+    return t, ld
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, out: Optional[torch.Tensor] = None,
+         bias: Optional[torch.Tensor] = None, rowbcast: Optional[torch.Tensor] = None, group: int = 1,
+         aux: Optional[torch.Tensor] = None, aux_scale: float = 1.0, relu: bool = False,
+         precision: int = PREC_TF32X3, split_k: int = 1, tile_n: int = 0) -> torch.Tensor:
+    """C[M,N] = epi(A . B^T) on tcgen05.  ``a`` is (M,K) [a_mn=False] or (K,M) [a_mn=True]; same for ``b`` with N."""
+    _chk(a, "gemm A"); _chk(b, "gemm B")
+    a, lda = _rows_view(a, "gemm A")
+    b, ldb = _rows_view(b, "gemm B")
+    M, Ka = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    if Ka != Kb:
+        raise RuntimeError(f"gemm: contraction mismatch {Ka} vs {Kb}")
+    if lda % 4 or ldb % 4 or a.data_ptr() % 16 or b.data_ptr() % 16:
+        raise RuntimeError("gemm: TMA needs 16-byte aligned operands with leading dimensions that are multiples of 4 floats "
+                           f"(lda={lda}, ldb={ldb}); pad the feature dimension")
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32)
+        if split_k > 1:
+            out.zero_()
+    else:
+        _chk(out, "gemm out")
+        if out.shape != (M, N):
+            raise RuntimeError(f"gemm: out has shape {tuple(out.shape)}, expected {(M, N)}")
+    out, ldc = _rows_view(out, "gemm out")
+    ldrb = ldaux = 0
+    if rowbcast is not None:
+        rowbcast, ldrb = _rows_view(_chk(rowbcast, "gemm rowbcast"), "gemm rowbcast")
+    if aux is not None:
+        aux, ldaux = _rows_view(_chk(aux, "gemm aux"), "gemm aux")
+    _call("vqa_gemm_f32", a.data_ptr(), lda, int(a_mn), b.data_ptr(), ldb, int(b_mn), out.data_ptr(), ldc, M, N, Ka,
+          _ptr(bias), _ptr(rowbcast), ldrb, group, _ptr(aux), ldaux, float(aux_scale), GEMM_RELU if relu else 0,
+          precision, split_k, tile_n, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------- elementwise
+def dropout(x: torch.Tensor, p: float, seed: int, offset: int) -> torch.Tensor:
+    x = _chk(x, "dropout x").contiguous()
+    y = torch.empty_like(x)
+    _call("vqa_dropout_f32", x.data_ptr(), y.data_ptr(), x.numel(), float(p), seed, offset, _stream())
+    return y
+
+
+def weight_norm_fwd(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    v = _chk(v, "weight_norm v").contiguous(); g = _chk(g, "weight_norm g").contiguous()
+    w = torch.empty_like(v)
+    _call("vqa_weight_norm_fwd_f32", v.data_ptr(), g.data_ptr(), w.data_ptr(), v.shape[0], v.shape[1], _stream())
+    return w
+
+
+def weight_norm_bwd(dw: torch.Tensor, v: torch.Tensor, g: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    dw = _chk(dw, "weight_norm dw").contiguous(); v = v.contiguous(); g = g.contiguous()
+    dv = torch.empty_like(v)
+    dg = torch.empty_like(g)
+    _call("vqa_weight_norm_bwd_f32", dw.data_ptr(), v.data_ptr(), g.data_ptr(), dv.data_ptr(), dg.data_ptr(),
+          v.shape[0], v.shape[1], _stream())
+    return dv, dg
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    x, ldx = _rows_view(_chk(x, "colsum x"), "colsum x")
+    out = torch.empty(x.shape[1], device=x.device, dtype=torch.float32)
+    scratch = torch.empty(256 * x.shape[1], device=x.device, dtype=torch.float32)
+    _call("vqa_colsum_f32", x.data_ptr(), ldx, out.data_ptr(), scratch.data_ptr(), x.shape[0], x.shape[1], _stream())
+    return out
+
+
+def segment_sum(x: torch.Tensor, seg_len: int) -> torch.Tensor:
+    x = _chk(x, "segment_sum x").contiguous()
+    rows, cols = x.shape
+    if rows % seg_len:
+        raise RuntimeError("segment_sum: rows not divisible by segment length")
+    out = torch.empty((rows // seg_len, cols), device=x.device, dtype=torch.float32)
+    _call("vqa_segment_sum_f32", x.data_ptr(), out.data_ptr(), rows // seg_len, seg_len, cols, _stream())
+    return out
+
+
+def gate_bwd(dhq, q, pooled):
+    dhq = _chk(dhq, "gate dhq").contiguous(); q = q.contiguous(); pooled = pooled.contiguous()
+    dpooled = torch.empty_like(dhq)
+    dq = torch.empty_like(dhq)
+    _call("vqa_gate_bwd_f32", dhq.data_ptr(), q.data_ptr(), pooled.data_ptr(), dpooled.data_ptr(), dq.data_ptr(),
+          dhq.numel(), _stream())
+    return dpooled, dq
+
+
+# ------------------------------------------------------------------------------------------- graph learner tail
+def adjacency_topk_fwd(h: torch.Tensor, nb: int):
+    """h (B,K,C) -> adjacency (B,K,K), idx (B,K,nb) int32 (descending value), alpha (B,K,nb)."""
+    h = _chk(h, "adjacency h").contiguous()
+    B, K, Cdim = h.shape
+    adj = torch.empty((B, K, K), device=h.device, dtype=torch.float32)
+    idx = torch.empty((B, K, nb), device=h.device, dtype=torch.int32)
+    alpha = torch.empty((B, K, nb), device=h.device, dtype=torch.float32)
+    _call("vqa_adjacency_topk_fwd_f32", h.data_ptr(), adj.data_ptr(), idx.data_ptr(), alpha.data_ptr(), B, K, Cdim, nb, _stream())
+    return adj, idx, alpha
+
+
+def topk_softmax(adj: torch.Tensor, nb: int):
+    adj = _chk(adj, "topk adjacency").contiguous()
+    B, K, _ = adj.shape
+    idx = torch.empty((B, K, nb), device=adj.device, dtype=torch.int32)
+    alpha = torch.empty((B, K, nb), device=adj.device, dtype=torch.float32)
+    _call("vqa_topk_softmax_f32", adj.data_ptr(), idx.data_ptr(), alpha.data_ptr(), B, K, nb, _stream())
+    return idx, alpha
+
+
+def adjacency_topk_bwd(h, idx, alpha, dalpha, dadj=None):
+    h = _chk(h, "adjacency h").contiguous()
+    B, K, Cdim = h.shape
+    nb = idx.shape[-1]
+    dalpha = _chk(dalpha, "dalpha").contiguous()
+    if dadj is not None:
+        dadj = _chk(dadj, "dadj").contiguous()
+    dh = torch.empty_like(h)
+    _call("vqa_adjacency_topk_bwd_f32", h.data_ptr(), idx.data_ptr(), alpha.data_ptr(), dalpha.data_ptr(), _ptr(dadj),
+          dh.data_ptr(), B, K, Cdim, nb, _stream())
+    return dh
+
+
+# ------------------------------------------------------------------------------------------- graph convolution
+def _boxes_view(image: torch.Tensor):
+    """(B,K,F) image -> pointer to the first box column + row stride; no copy."""
+    _chk(image, "image")
+    if image.dim() != 3 or image.stride(2) != 1 or image.stride(0) != image.shape[1] * image.stride(1):
+        raise RuntimeError("image must be (B,K,F) with contiguous rows")
+    return image.data_ptr() + (image.shape[2] - 4) * 4, image.stride(1)
+
+
+def graphconv_fwd(Y, idx, alpha, image, gauss, B, K, relu=True, dropout_p=0.0, seed=0, offset=0):
+    Y, ldy = _rows_view(_chk(Y, "graphconv Y"), "graphconv Y")
+    nb = idx.shape[-1]
+    nk = gauss.numel() // 4
+    out_dim = Y.shape[1]
+    bptr, ldbox = _boxes_view(image)
+    out = torch.empty((B * K, out_dim), device=Y.device, dtype=torch.float32)
+    _call("vqa_graphconv_fwd_f32", Y.data_ptr(), ldy, idx.data_ptr(), _ptr(alpha), bptr, ldbox, gauss.data_ptr(),
+          out.data_ptr(), out_dim, B, K, nb, nk, out_dim, GC_RELU if relu else 0, float(dropout_p), seed, offset, _stream())
+    return out
+
+
+def graphconv_pool_fwd(Y, idx, image, gauss, q, B, K):
+    Y, ldy = _rows_view(_chk(Y, "graphconv Y"), "graphconv Y")
+    nb = idx.shape[-1]
+    nk = gauss.numel() // 4
+    out_dim = Y.shape[1]
+    bptr, ldbox = _boxes_view(image)
+    q = _chk(q, "q").contiguous()
+    pooled = torch.empty((B, out_dim), device=Y.device, dtype=torch.float32)
+    argmax = torch.empty((B, out_dim), device=Y.device, dtype=torch.int64)
+    hq = torch.empty((B, out_dim), device=Y.device, dtype=torch.float32)
+    _call("vqa_graphconv_pool_fwd_f32", Y.data_ptr(), ldy, idx.data_ptr(), bptr, ldbox, gauss.data_ptr(), q.data_ptr(),
+          pooled.data_ptr(), argmax.data_ptr(), hq.data_ptr(), B, K, nb, nk, out_dim, _stream())
+    return pooled, argmax, hq
+
+
+def graphconv_bwd(Y, idx, alpha, image, gauss, B, K, dO=None, dpooled=None, argmax=None):
+    """-> dY (B*K,out), dalpha (B,K,nb) or None, dgauss (4*nk,)"""
+    Y, ldy = _rows_view(_chk(Y, "graphconv Y"), "graphconv Y")
+    nb = idx.shape[-1]
+    nk = gauss.numel() // 4
+    out_dim = Y.shape[1]
+    bptr, ldbox = _boxes_view(image)
+    dY = torch.empty((B * K, out_dim), device=Y.device, dtype=torch.float32)
+    P = torch.empty((B, K, nb, nk), device=Y.device, dtype=torch.float32)
+    lddo = 0
+    if dO is not None:
+        dO, lddo = _rows_view(_chk(dO, "graphconv dO"), "graphconv dO")
+    else:
+        dpooled = _chk(dpooled, "dpooled").contiguous()
+    _call("vqa_graphconv_bwd_f32", _ptr(dO), lddo, _ptr(dpooled), _ptr(argmax), Y.data_ptr(), ldy, idx.data_ptr(),
+          _ptr(alpha), bptr, ldbox, gauss.data_ptr(), dY.data_ptr(), out_dim, P.data_ptr(), B, K, nb, nk, out_dim, _stream())
+    nblk = _cabi.load().vqa_graphconv_edge_blocks(B, K, nb)
+    partial = torch.empty((nblk, 4 * nk), device=Y.device, dtype=torch.float32)
+    dalpha = torch.empty((B, K, nb), device=Y.device, dtype=torch.float32) if alpha is not None else None
+    _call("vqa_graphconv_edge_bwd_f32", P.data_ptr(), idx.data_ptr(), _ptr(alpha), bptr, ldbox, gauss.data_ptr(),
+          _ptr(dalpha), partial.data_ptr(), B, K, nb, nk, _stream())
+    dgauss = colsum(partial)
+    return dY, dalpha, dgauss
+
+
+def gaussian_weights(pseudo: torch.Tensor, gauss: torch.Tensor) -> torch.Tensor:
+    pseudo = _chk(pseudo, "pseudo").contiguous().view(-1, 2)
+    nk = gauss.numel() // 4
+    w = torch.empty((pseudo.shape[0], nk), device=pseudo.device, dtype=torch.float32)
+    _call("vqa_gaussian_weights_f32", pseudo.data_ptr(), gauss.data_ptr(), w.data_ptr(), pseudo.shape[0], nk, _stream())
+    return w

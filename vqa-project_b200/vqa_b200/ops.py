@@ -1,0 +1,280 @@
+"""Autograd operators of the conditioned-graph VQA hot path, built on the sm_100a kernels.
+
+``ConditionedGraphFn`` is the fused entry ``Model.forward`` uses: everything between the question
+encoding and the logits (reference ``sparse_graph_model.py:106-157`` minus the embedding/GRU) as one
+autograd node whose forward and backward are sequences of hand-written CUDA kernels -- tcgen05 GEMMs
+for the dense projections, the fused adjacency/top-k/softmax kernel, the fused graph-convolution
+kernels and their backward counterparts (SURVEY.md section 9 is the maths).  Nothing is materialised that
+the reference materialises only because of its operator granularity: no (B,K,F+H) concat, no
+(B,K,nb,F) gathers, no dense (B,K,K,2) pseudo-coordinates, no per-kernel slices.
+
+The smaller Functions (``LinearFn``, ``AdjacencyFn``, ``GaussianWeightsFn``) back the layer-level
+module API (``layers.GraphLearner`` / ``layers.NeighbourhoodGraphConvolution``).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import kernels as kn
+from ._cabi import PREC_TF32, PREC_TF32X3
+
+_PRECISION = PREC_TF32X3
+_PRECISION_NAMES = {"fp32": PREC_TF32X3, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
+
+
+def set_precision(name: str) -> None:
+    """'fp32'/'tf32x3' (default, fp32-grade 3-pass split on the tensor cores) or 'tf32' (single pass)."""
+    global _PRECISION
+    _PRECISION = _PRECISION_NAMES[name]
+
+
+def get_precision() -> str:
+    return "tf32x3" if _PRECISION == PREC_TF32X3 else "tf32"
+
+
+def _gemm(a, b, **kw):
+    return kn.gemm(a, b, precision=_PRECISION, **kw)
+
+
+def _split_for(out_rows: int, out_cols: int, contraction: int) -> int:
+    """Split-K factor for dW = dY^T X products whose output has too few tiles to fill 148 SMs."""
+    tiles = ((out_rows + 127) // 128) * ((out_cols + 255) // 256)
+    kblocks = (contraction + 31) // 32
+    s = max(1, min(148 // max(tiles, 1), kblocks // 8))
+    return s
+
+
+def next_philox(device: torch.device):
+    """(seed, offset) for one fused-dropout call, drawn from (and advancing) torch's CUDA generator state,
+    so ``torch.manual_seed`` controls the masks exactly as it does for nn.Dropout."""
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    off = gen.get_offset()
+    gen.set_offset(off + 4)
+    return gen.initial_seed() & 0xFFFFFFFFFFFFFFFF, off // 4 + 1
+
+
+def pack_gauss(mean_rho, precision_rho, mean_theta, precision_theta) -> torch.Tensor:
+    return torch.cat((mean_rho.reshape(-1), precision_rho.reshape(-1), mean_theta.reshape(-1), precision_theta.reshape(-1))).contiguous()
+
+
+def flat_weight(ws: Sequence[torch.Tensor]) -> torch.Tensor:
+    """The nk per-kernel conv weights (D,in) as ONE (nk*D, in) matrix; zero-copy when they already are
+    consecutive views of one buffer (layers.NeighbourhoodGraphConvolution arranges that)."""
+    w0 = ws[0]
+    d, fin = w0.shape
+    step = d * fin * w0.element_size()
+    if all(w.is_contiguous() and w.data_ptr() == w0.data_ptr() + i * step for i, w in enumerate(ws)):
+        try:
+            return w0.detach().as_strided((len(ws) * d, fin), (fin, 1))
+        except RuntimeError:
+            pass
+    return torch.cat([w.detach() for w in ws], dim=0)
+
+
+class ConditionedGraphFn(torch.autograd.Function):
+    """(image, qenc, parameters) -> (logits, adjacency, h_max_indices)."""
+
+    @staticmethod
+    def forward(ctx, cfg, image, qenc, v1, g1, b1, v2, g2, b2, mr1, pr1, mt1, pt1, mr2, pr2, mt2, pt2,
+                vo1, go1, bo1, vo2, go2, bo2, *conv_ws):
+        nk, nb, p_drop, training = cfg["n_kernels"], cfg["neighbourhood_size"], float(cfg["dropout"]), bool(cfg["training"])
+        B, K, F = image.shape
+        H = qenc.shape[1]
+        dev = image.device
+        image = image.contiguous()
+        qenc = qenc.contiguous()
+        drop = training and p_drop > 0.0
+        scale = 1.0 / (1.0 - p_drop) if drop else 1.0
+
+        # dropout on the WHOLE image tensor incl. box columns (sparse_graph_model.py:111); box centres are taken
+        # from the un-dropped image inside the graph-conv kernels (:106-108 precede :111)
+        if drop:
+            seed, off = next_philox(dev)
+            X = kn.dropout(image, p_drop, seed, off)
+        else:
+            X = image
+        X2 = X.view(B * K, F)
+
+        # weight-norm effective weights (layers.py:171-172, sparse_graph_model.py:88-89)
+        W1 = kn.weight_norm_fwd(v1, g1)
+        W2 = kn.weight_norm_fwd(v2, g2)
+        Wo1 = kn.weight_norm_fwd(vo1, go1)
+        Wo2 = kn.weight_norm_fwd(vo2, go2)
+
+        # graph learner: [X || q] W1^T = X W1[:, :F]^T + (q W1[:, F:]^T) broadcast over the K nodes  (no concat/repeat)
+        qt = _gemm(qenc, W1[:, F:])
+        h1 = _gemm(X2, W1[:, :F], bias=b1, rowbcast=qt, group=K, relu=True)
+        h2 = _gemm(h1, W2, bias=b2, relu=True)
+        C = h2.shape[1]
+        adj, idx, alpha = kn.adjacency_topk_fwd(h2.view(B, K, C), nb)
+
+        # graph convolution 1 (project first, then fused Gaussian-weight/gather/aggregate + ReLU + dropout)
+        Wc1 = flat_weight(conv_ws[:nk])
+        Wc2 = flat_weight(conv_ws[nk:])
+        gs1 = pack_gauss(mr1, pr1, mt1, pt1)
+        gs2 = pack_gauss(mr2, pr2, mt2, pt2)
+        Y1 = _gemm(X2, Wc1)
+        if drop:
+            seed, off = next_philox(dev)
+            G1 = kn.graphconv_fwd(Y1, idx, alpha, image, gs1, B, K, relu=True, dropout_p=p_drop, seed=seed, offset=off)
+        else:
+            G1 = kn.graphconv_fwd(Y1, idx, alpha, image, gs1, B, K, relu=True)
+        # graph convolution 2 with max-pool over nodes + question gate fused (sparse_graph_model.py:146-151)
+        Y2 = _gemm(G1, Wc2)
+        pooled, argmax, hq = kn.graphconv_pool_fwd(Y2, idx, image, gs2, qenc, B, K)
+
+        # classifier
+        o1 = _gemm(hq, Wo1, bias=bo1, relu=True)
+        if drop:
+            seed, off = next_philox(dev)
+            o1 = kn.dropout(o1, p_drop, seed, off)
+        logits = _gemm(o1, Wo2, bias=bo2)
+
+        ctx.cfg = dict(B=B, K=K, F=F, H=H, nk=nk, nb=nb, scale=scale)
+        ctx.save_for_backward(image, X2, qenc, v1, g1, v2, g2, vo1, go1, vo2, go2, W1, W2, Wo1, Wo2, Wc1, Wc2, gs1, gs2,
+                              h1, h2, idx, alpha, Y1, G1, Y2, pooled, argmax, hq, o1)
+        ctx.mark_non_differentiable(argmax)
+        return logits, adj, argmax
+
+    @staticmethod
+    def backward(ctx, dlogits, dadj, _dargmax):
+        (image, X2, qenc, v1, g1, v2, g2, vo1, go1, vo2, go2, W1, W2, Wo1, Wo2, Wc1, Wc2, gs1, gs2,
+         h1, h2, idx, alpha, Y1, G1, Y2, pooled, argmax, hq, o1) = ctx.saved_tensors
+        c = ctx.cfg
+        B, K, F, H, nk, scale = c["B"], c["K"], c["F"], c["H"], c["nk"], c["scale"]
+        M = B * K
+        dlogits = dlogits.contiguous()
+
+        # classifier
+        dbo2 = kn.colsum(dlogits)
+        dWo2 = _gemm(dlogits, o1, a_mn=True, b_mn=True)
+        do1 = _gemm(dlogits, Wo2, b_mn=True, aux=o1, aux_scale=scale)       # ReLU + dropout mask from the stored output
+        dbo1 = kn.colsum(do1)
+        dWo1 = _gemm(do1, hq, a_mn=True, b_mn=True)
+        dhq = _gemm(do1, Wo1, b_mn=True)
+        dpooled, dq = kn.gate_bwd(dhq, qenc, pooled)
+
+        # graph convolution 2: max-pool scatter by argmax is done inside the kernel
+        dY2, _, dgs2 = kn.graphconv_bwd(Y2, idx, None, image, gs2, B, K, dpooled=dpooled, argmax=argmax)
+        dWc2 = _gemm(dY2, G1, a_mn=True, b_mn=True, split_k=_split_for(Wc2.shape[0], Wc2.shape[1], M))
+        dG1 = _gemm(dY2, Wc2, b_mn=True, aux=G1, aux_scale=scale)
+        # graph convolution 1
+        dY1, dalpha, dgs1 = kn.graphconv_bwd(Y1, idx, alpha, image, gs1, B, K, dO=dG1)
+        dWc1 = _gemm(dY1, X2, a_mn=True, b_mn=True, split_k=_split_for(Wc1.shape[0], Wc1.shape[1], M))
+
+        # graph learner
+        Cdim = h2.shape[1]
+        dh2 = kn.adjacency_topk_bwd(h2.view(B, K, Cdim), idx, alpha, dalpha, dadj).view(M, Cdim)
+        db2 = kn.colsum(dh2)
+        dW2 = _gemm(dh2, h1, a_mn=True, b_mn=True, split_k=_split_for(Cdim, Cdim, M))
+        dh1 = _gemm(dh2, W2, b_mn=True, aux=h1, aux_scale=1.0)
+        db1 = kn.colsum(dh1)
+        s1 = _split_for(Cdim, F, M)
+        dW1 = torch.zeros_like(W1) if s1 > 1 else torch.empty_like(W1)
+        _gemm(dh1, X2, a_mn=True, b_mn=True, out=dW1[:, :F], split_k=s1)
+        dqt = kn.segment_sum(dh1, K)
+        _gemm(dqt, qenc, a_mn=True, b_mn=True, out=dW1[:, F:])
+        dq_gl = _gemm(dqt, W1[:, F:], b_mn=True)
+        dq = dq + dq_gl
+
+        dv1, dg1 = kn.weight_norm_bwd(dW1, v1, g1)
+        dv2, dg2 = kn.weight_norm_bwd(dW2, v2, g2)
+        dvo1, dgo1 = kn.weight_norm_bwd(dWo1, vo1, go1)
+        dvo2, dgo2 = kn.weight_norm_bwd(dWo2, vo2, go2)
+
+        d1 = Wc1.shape[0] // nk
+        d2 = Wc2.shape[0] // nk
+        conv_grads = [dWc1[i * d1:(i + 1) * d1] for i in range(nk)] + [dWc2[i * d2:(i + 1) * d2] for i in range(nk)]
+        gsh = (nk, 1)
+        return (None, None, dq, dv1, dg1, db1, dv2, dg2, db2,
+                dgs1[0:nk].view(gsh), dgs1[nk:2 * nk].view(gsh), dgs1[2 * nk:3 * nk].view(gsh), dgs1[3 * nk:].view(gsh),
+                dgs2[0:nk].view(gsh), dgs2[nk:2 * nk].view(gsh), dgs2[2 * nk:3 * nk].view(gsh), dgs2[3 * nk:].view(gsh),
+                dvo1, dgo1, dbo1, dvo2, dgo2, dbo2, *conv_grads)
+
+
+# ------------------------------------------------------------------------------------------- layer-level operators
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) on the tcgen05 GEMM (x: (M,in), W: (out,in))."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, relu):
+        x = x.contiguous()
+        w = w.contiguous()
+        y = _gemm(x, w, bias=b, relu=relu)
+        ctx.relu = relu
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(x, w, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        if ctx.relu:
+            dy = torch.where(y > 0, dy, torch.zeros_like(dy))
+        dx = _gemm(dy, w, b_mn=True) if ctx.needs_input_grad[0] else None
+        dw = _gemm(dy, x, a_mn=True, b_mn=True, split_k=_split_for(w.shape[0], w.shape[1], x.shape[0]))
+        db = kn.colsum(dy) if ctx.has_bias else None
+        return dx, dw, db, None
+
+
+class WeightNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, g):
+        ctx.save_for_backward(v, g)
+        return kn.weight_norm_fwd(v, g)
+
+    @staticmethod
+    def backward(ctx, dw):
+        v, g = ctx.saved_tensors
+        return kn.weight_norm_bwd(dw, v, g)
+
+
+class AdjacencyFn(torch.autograd.Function):
+    """A = h h^T per image via the fused adjacency kernel (h must be a ReLU output, as in GraphLearner)."""
+
+    @staticmethod
+    def forward(ctx, h):
+        h = h.contiguous()
+        adj, idx, alpha = kn.adjacency_topk_fwd(h, 1)
+        ctx.save_for_backward(h, idx, alpha)
+        return adj
+
+    @staticmethod
+    def backward(ctx, dadj):
+        h, idx, alpha = ctx.saved_tensors
+        return kn.adjacency_topk_bwd(h, idx, alpha, torch.zeros_like(alpha), dadj.contiguous())
+
+
+def _gaussian_weights_torch(pseudo, mr, pr, mt, pt):
+    """Differentiable re-evaluation (torch ops) used only for the BACKWARD of the layer-level API."""
+    import math
+    rho = pseudo[..., 0].reshape(-1, 1)
+    theta = pseudo[..., 1].reshape(-1, 1)
+    wr = torch.exp(-0.5 * (rho - mr.view(1, -1)) ** 2 / (1e-14 + pr.view(1, -1) ** 2))
+    a1 = torch.abs(theta - mt.view(1, -1))
+    a2 = torch.abs(2 * math.pi - a1)
+    wt = torch.exp(-0.5 * torch.minimum(a1, a2) ** 2 / (1e-14 + pt.view(1, -1) ** 2))
+    w = wr * wt
+    w = torch.where(torch.isnan(w), torch.zeros_like(w), w)
+    return w / w.sum(dim=1, keepdim=True)
+
+
+class GaussianWeightsFn(torch.autograd.Function):
+    """get_gaussian_weights of the layer API: forward = CUDA kernel, backward = autograd through the torch formula."""
+
+    @staticmethod
+    def forward(ctx, pseudo, mr, pr, mt, pt):
+        ctx.save_for_backward(pseudo, mr, pr, mt, pt)
+        return kn.gaussian_weights(pseudo, pack_gauss(mr, pr, mt, pt))
+
+    @staticmethod
+    def backward(ctx, dw):
+        pseudo, mr, pr, mt, pt = ctx.saved_tensors
+        with torch.enable_grad():
+            leaves = [t.detach().requires_grad_(True) for t in (mr, pr, mt, pt)]
+            w = _gaussian_weights_torch(pseudo.detach(), *leaves)
+            grads = torch.autograd.grad(w, leaves, dw)
+        return (None, *grads)
