@@ -33,7 +33,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="vqa2_b512")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_strict", "tf32x3", "tf32"])
+    ap.add_argument("--gru-tf32", action="store_true", help="let cuDNN run the (unchanged) GRU in TF32, torch's default; off = fp32 like the parity tests")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=64, help="questions per CPU step (bounded sample of the workload)")
     return ap.parse_args()
@@ -100,7 +101,7 @@ def config_dict(w, args, world):
     return {"workload": f"{w.name}: VQA2 conditioned-graph train step, per-GPU batch {w.batch}, K={w.n_obj} boxes x {w.feat_dim}-d, "
                         f"<= {w.max_qlen}-token questions, top-k={w.neighbourhood}, {w.n_kernels} Gaussian kernels, {w.out_dim} answers, dropout {w.dropout}",
             "global_batch": w.batch * world, "step": "zero_grad+forward+MultiLabelSoftMarginLoss+backward+allreduce+Adam",
-            "parallelism": f"dp{world}", "gemm_precision": "tf32x3 (fp32-grade)" if args.precision != "tf32" else "tf32",
+            "parallelism": f"dp{world}", "gru": "cuDNN tf32" if args.gru_tf32 else "cuDNN fp32", "gemm_precision": "tf32x3 (fp32-grade)" if args.precision != "tf32" else "tf32",
             "l2_policy": "inputs larger than L2 (image batch 151 MB > 126 MB), 3 rotating batches"}
 
 
@@ -148,6 +149,7 @@ def run_b200(args, workload):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ops.set_precision(args.precision)
+    torch.backends.cudnn.allow_tf32 = bool(args.gru_tf32)
     w = workload
 
     torch.manual_seed(1000)

@@ -25,6 +25,7 @@ typedef struct CUstream_st* vqa_stream_t; /* cudaStream_t */
 /* GEMM precision modes */
 #define VQA_PREC_TF32X3 0 /* 3-pass split TF32 on tcgen05: fp32-grade results (parity mode)      */
 #define VQA_PREC_TF32 1   /* single-pass TF32 on tcgen05                                           */
+#define VQA_PREC_TF32X3_HP 2 /* TF32X3 + fp32 promotion of the accumulator every K=128: cuBLAS-fp32-grade */
 
 /* GEMM epilogue flags */
 #define VQA_GEMM_RELU 1

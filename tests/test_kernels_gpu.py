@@ -45,7 +45,7 @@ GEMM_CASES = [
 
 
 @pytest.mark.parametrize("M,N,K,a_mn,b_mn,tile_n", GEMM_CASES)
-@pytest.mark.parametrize("prec,tol", [(0, 5e-5), (1, 3e-3)])  # x3: tensor-core accumulators truncate (~K*2^-24)
+@pytest.mark.parametrize("prec,tol", [(0, 5e-5), (1, 3e-3), (2, 3e-6)])  # x3: tensor-core accumulators truncate (~K*2^-24)
 def test_gemm_matches_fp64(kn, M, N, K, a_mn, b_mn, tile_n, prec, tol):
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
     a = torch.randn(M, K, generator=g)

@@ -11,6 +11,17 @@ from vqa_b200.synthetic import WORKLOADS, make_batch, make_wemb
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _fp32_gru():
+    """The question encoder is an unchanged torch component (nn.GRU -> cuDNN).  torch lets cuDNN use TF32 by default
+    (qenc error 2.6e-4, measured), which the golden vectors - produced by the reference on CPU in fp32 - do not have;
+    pin it to fp32 so that the comparison isolates the kernels of this repo."""
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
 TOL = 1e-3          # north_star budget
 TIGHT = 2e-4        # what the tf32x3 path actually achieves on these shapes
 
@@ -160,7 +171,7 @@ def test_full_size_properties_vqa2_b512():
         # (1) per-sample independence: a sub-batch gives the same rows
         l2, a2, g2 = model(q[5:37], img[5:37], K[5:37], batch["qlen"][5:37])
     assert torch.isfinite(logits).all()
-    assert rel_err(l2.cpu(), logits[5:37].cpu()) < 1e-5 and torch.equal(a2, adj[5:37])
+    assert rel_err(l2.cpu(), logits[5:37].cpu()) < 1e-5 and rel_err(a2.cpu(), adj[5:37].cpu()) < 1e-5   # cuDNN picks batch-dependent GRU algorithms: not bitwise
     # (2) adjacency symmetric PSD-diagonal, (3) argmax within range
     assert torch.equal(adj, adj.transpose(1, 2)) and (adj.diagonal(dim1=1, dim2=2) >= 0).all()
     assert arg.min() >= 0 and arg.max() < w.n_obj

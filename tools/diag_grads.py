@@ -5,6 +5,9 @@ from conftest import load_golden, golden_params, rel_err
 from vqa_b200.synthetic import WORKLOADS, make_wemb
 import sparse_graph_model as M
 from vqa_b200 import kernels as kn
+from vqa_b200 import ops
+torch.backends.cudnn.allow_tf32 = os.environ.get('GRU_TF32', '0') == '1'
+ops.set_precision(os.environ.get("VQA_PREC", "fp32"))
 for name in sys.argv[1:] or ("tiny", "small"):
     g = load_golden(name); w = WORKLOADS[name]
     model = M.Model(pretrained_wemb=make_wemb(w), **w.model_kwargs())

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libvqa_sm100.so")
 ABI_VERSION = 1
 PREC_TF32X3 = 0
 PREC_TF32 = 1
+PREC_TF32X3_HP = 2
 GEMM_RELU = 1
 GC_RELU = 1
 

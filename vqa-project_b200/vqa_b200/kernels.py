@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import PREC_TF32, PREC_TF32X3, GEMM_RELU, GC_RELU
+from ._cabi import PREC_TF32, PREC_TF32X3, PREC_TF32X3_HP, GEMM_RELU, GC_RELU
 
 LAUNCHES = 0
 _LAUNCH_COST = {"vqa_colsum_f32": 2}
