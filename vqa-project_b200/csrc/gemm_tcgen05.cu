@@ -144,7 +144,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   using C = Cfg<BN, PREC>;
   constexpr int S = C::S;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the .shared address space
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * C::STAGE);
   uint64_t* full_raw = bars;
   uint64_t* full_xf = bars + S;

@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <cstring>
 #include "../../include/vqa_b200.h"
 
 namespace vqa {
@@ -119,12 +120,335 @@ __device__ void gc_prologue(const GcParams& p, const GcSmem& L, uint8_t* sm, int
   }
 }
 
+// single-exp form of gauss_val with precomputed -0.5/(eps+sigma^2): exp(a)*exp(b) == exp(a+b) up to 1-2 ulp
+__device__ __forceinline__ float gauss_fast(float rho, float theta, float mr, float cr, float mt, float ct) {
+  const float d = rho - mr;
+  const float a1 = fabsf(theta - mt);
+  const float mn = fminf(a1, fabsf(TWO_PI_F - a1));
+  const float g = expf(fmaf(d * d, cr, mn * mn * ct));
+  return (g != g) ? 0.f : g;
+}
+// packed 2 x fp32 FMA (Blackwell FFMA2): d = a * b + c on both halves, each rounded to nearest like fmaf
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ float lo2(unsigned long long v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi2(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
+// counter-based 32-bit hash (murmur3 finaliser over a seeded 64-bit counter): the fused dropout needs 16 random bits
+// per output element and the kernel is issue-bound, so Philox4x32-10 (~90 instructions / call) is too expensive here.
+__device__ __forceinline__ uint32_t hash32(unsigned long long ctr, unsigned long long seed, unsigned long long offset) {
+  uint32_t x = (uint32_t)ctr * 0x9E3779B1u ^ (uint32_t)(ctr >> 32) * 0x85EBCA77u ^ (uint32_t)seed ^ (uint32_t)(seed >> 32) * 0xC2B2AE3Du ^
+               (uint32_t)offset * 0x27D4EB2Fu;
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  x ^= (uint32_t)ctr; x *= 0x9E3779B1u; x ^= x >> 15;
+  return x;
+}
+
+// ------------------------------------------------------------------------------------------ dense-register aggregate
+// out[r, c] = sum_{r'} M_k[r][r'] * in[r', c]  for every row r of one image, k = kernel owning column c.
+//
+// The neighbourhood aggregate written as a tiny dense matrix product per (image, kernel): M_k is K x K with the
+// <= nb non-zeros per row w[i,m,k]*alpha[i,m] at column idx[i,m] (forward), or its transpose (backward dY = M^T dO).
+// Why dense: a gather out of shared memory needs one 16-byte LDS per 4 FMAs and is bound by the 128 B/clk smem
+// crossbar (measured 22 % of the HBM roofline); here every lane keeps its column slice of ALL K input rows in
+// registers (K independent, coalesced global loads in flight per thread), coefficients arrive as warp-broadcast
+// LDS.128 (4 per load), and the inner loop is >90 % FFMA.  K^2/nb more FLOPs, but FP32-FMA time (K=36: ~38 us for
+// layer 1 at B=512) stays under the HBM time (46 us).  One warp owns a [K x 32*VEC] tile; max-pool over the nodes
+// is a per-lane running max.  CTA = 4 warps = (image, slab of tiles): the Gaussian/alpha coefficient matrices of the
+// slab's kernels are built once per CTA in shared memory.
+enum { DM_FWD = 0, DM_FWD_POOL = 1, DM_BWD_DENSE = 2, DM_BWD_POOLED = 3 };
+constexpr int DN_WARPS = 3;                 // 3 warps x 2 CTAs / SM: leaves ~250 registers per thread for the resident input rows
+constexpr int DN_THREADS = DN_WARPS * 32;
+constexpr int DN_CTA = DN_THREADS;
+
+struct DenseParams {
+  const float* in; long long ldin;           // Y (fwd) or dO (bwd dense)
+  const float* dpooled; const long long* argmax_in;   // bwd pooled upstream
+  const int* idx; const float* alpha; const float* boxes; long long ldbox; const float* gauss;
+  float* out; long long ldo;
+  const float* q; float* pooled; long long* argmax; float* hq;
+  int K, nb, nk, out_dim, D, tiles_per_cta, ntiles, nkc, flags;
+  int nstage, tile_stride, ring_off, bar_off;   // per-warp TMA landing slot: bytes per staged tile, byte offsets in dynamic smem
+  float drop_p, drop_scale;
+  unsigned int drop_thresh16;                // keep iff 16-bit uniform >= thresh
+  unsigned long long seed, offset;
+};
+
+template <int KT, int VEC, int MODE>
+__global__ void __launch_bounds__(DN_CTA, 2)
+graphconv_dense_kernel(const __grid_constant__ CUtensorMap tmIn, const DenseParams p) {
+  static_assert(KT % 4 == 0 && (VEC == 1 || VEC == 2 || VEC == 4), "KT must be a multiple of 4, VEC 1, 2 or 4");
+  constexpr int KP = KT;                      // row stride of the coefficient matrices (floats)
+  constexpr int TWD = 32 * VEC;               // tile width in columns
+  constexpr bool BWD = MODE == DM_BWD_DENSE || MODE == DM_BWD_POOLED;
+  constexpr bool RING = MODE != DM_BWD_POOLED;   // input tiles arrive through a TMA ring (the pooled upstream is synthesised)
+  extern __shared__ uint8_t dsm_raw[];
+  uint8_t* dsm = dsm_raw + ((128u - (smem_u32(dsm_raw) & 127u)) & 127u);   // pointer arithmetic keeps the .shared address space (LDS/STS)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, K = p.K, nb = p.nb, nk = p.nk;
+  const int t0 = blockIdx.x * p.tiles_per_cta;
+  const int nt = min(p.tiles_per_cta, p.ntiles - t0);
+  const int k_lo = (t0 * TWD) / p.D;
+  const int nkc = ((t0 + nt) * TWD - 1) / p.D - k_lo + 1;
+  // Input tiles: every warp owns one shared-memory landing slot.  Lane 0 issues the TMA load of the warp's NEXT tile as
+  // soon as the current one has been copied into registers, so the load overlaps the whole FMA phase; with the
+  // register copy this is a 2-deep pipeline per warp and ~2 x DN_WARPS x 18 KB in flight per SM, no cross-warp sync.
+  uint64_t* full = reinterpret_cast<uint64_t*>(dsm + p.bar_off) + warp;
+  float* slot = reinterpret_cast<float*>(dsm + p.ring_off + (size_t)warp * p.tile_stride);
+  if (RING && lane == 0) {
+    tma_prefetch_desc(&tmIn);
+    mbar_init(full, 1);
+    fence_barrier_init();
+    if (warp < nt) {
+      mbar_arrive_expect_tx(full, (uint32_t)K * TWD * 4);
+      tma_load_2d(slot, &tmIn, full, (t0 + warp) * TWD, b * K);
+    }
+  }
+  __syncwarp();
+  constexpr int DUP = VEC >= 2 ? 2 : 1;       // packed paths: coefficients stored twice ({c,c}) as ready-made FFMA2 operands
+  float* Ms = reinterpret_cast<float*>(dsm);                       // [nkc][K][KP][DUP]
+  float* cen = Ms + p.nkc * K * KP * DUP;                          // [K][2]
+  float* gs = cen + 2 * ((K + 1) & ~1);                            // [4][nk]: mean_rho, -0.5/(eps+prec_rho^2), mean_theta, -0.5/(eps+prec_theta^2)
+  uint8_t* idx8 = reinterpret_cast<uint8_t*>(gs + 4 * nk);         // [K][nb]
+
+  // ---- prologue: zero M, stage neighbour ids / box centres / Gaussian parameters
+  for (int v = tid; v < nkc * K * KP * DUP / 4; v += DN_THREADS) reinterpret_cast<float4*>(Ms)[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int v = tid; v < K * nb; v += DN_THREADS) idx8[v] = (uint8_t)p.idx[(long long)b * K * nb + v];
+  for (int i = tid; i < K; i += DN_THREADS) {
+    const float* bx = p.boxes + ((long long)b * K + i) * p.ldbox;
+    const float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3];
+    cen[2 * i] = x1 + 0.5f * (x2 - x1);                 // sparse_graph_model.py:106-108
+    cen[2 * i + 1] = y1 + 0.5f * (y2 - y1);
+  }
+  for (int k = tid; k < nk; k += DN_THREADS) {
+    const float sr = p.gauss[nk + k], st = p.gauss[3 * nk + k];
+    gs[k] = p.gauss[k];
+    gs[nk + k] = -0.5f / (GAUSS_EPS_F + sr * sr);
+    gs[2 * nk + k] = p.gauss[2 * nk + k];
+    gs[3 * nk + k] = -0.5f / (GAUSS_EPS_F + st * st);
+  }
+  __syncthreads();
+  // ---- per-edge Gaussian weights -> dense coefficient matrices of the slab's kernels
+  for (int e = tid; e < K * nb; e += DN_THREADS) {
+    const int i = e / nb, j = idx8[e];
+    float rho, theta;
+    polar(cen[2 * i], cen[2 * i + 1], cen[2 * j], cen[2 * j + 1], rho, theta);
+    float S = 0.f;
+    for (int k = 0; k < nk; ++k) S += gauss_fast(rho, theta, gs[k], gs[nk + k], gs[2 * nk + k], gs[3 * nk + k]);
+    const float a_over_S = __fdiv_rn(p.alpha ? p.alpha[(long long)b * K * nb + e] : 1.f, S);   // S == 0 -> inf/NaN as in the reference
+    for (int kk = 0; kk < nkc; ++kk) {
+      const int k = k_lo + kk;
+      const float c = gauss_fast(rho, theta, gs[k], gs[nk + k], gs[2 * nk + k], gs[3 * nk + k]) * a_over_S;
+      const int at = BWD ? (kk * K + j) * KP + i      // dY[j] += c * dO[i]
+                         : (kk * K + i) * KP + j;     // out[i] += c * Y[j]
+      if constexpr (DUP == 2) reinterpret_cast<float2*>(Ms)[at] = make_float2(c, c);
+      else Ms[at] = c;
+    }
+  }
+  __syncthreads();
+
+  // ---- main: one [K x TWD] tile per warp iteration, input rows held in registers
+  for (int t = warp; t < nt; t += DN_WARPS) {
+    const int colg = (t0 + t) * TWD + lane * VEC;
+    const float* Mk = Ms + (((t0 + t) * TWD) / p.D - k_lo) * K * KP * DUP;
+    float y[KT][VEC];
+    if constexpr (MODE == DM_BWD_POOLED) {
+      float dp[VEC];
+      int ar[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        dp[v] = p.dpooled[(long long)b * p.out_dim + colg + v];
+        ar[v] = (int)p.argmax_in[(long long)b * p.out_dim + colg + v];
+      }
+#pragma unroll
+      for (int j = 0; j < KT; ++j)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) y[j][v] = (ar[v] == j) ? dp[v] : 0.f;
+    } else {
+      mbar_wait(full, ((t - warp) / DN_WARPS) & 1);
+      const float* src = slot + lane * VEC;
+#pragma unroll
+      for (int j = 0; j < KT; ++j) {
+        if (j < K) {
+          if constexpr (VEC == 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(src + j * TWD);
+            y[j][0] = t4.x; y[j][1] = t4.y; y[j][2] = t4.z; y[j][3] = t4.w;
+          } else if constexpr (VEC == 2) {
+            const float2 t2 = *reinterpret_cast<const float2*>(src + j * TWD);
+            y[j][0] = t2.x; y[j][1] = t2.y;
+          } else {
+            y[j][0] = src[j * TWD];
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) y[j][v] = 0.f;
+        }
+      }
+      __syncwarp();
+      if (lane == 0 && t + DN_WARPS < nt) {        // slot is free again: fetch this warp's next tile under the FMA phase
+        fence_proxy_async();
+        mbar_arrive_expect_tx(full, (uint32_t)K * TWD * 4);
+        tma_load_2d(slot, &tmIn, full, (t0 + t + DN_WARPS) * TWD, b * K);
+      }
+    }
+    float best[VEC];
+    int barg[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { best[v] = -1.f; barg[v] = 0; }
+#pragma unroll 1
+    for (int i = 0; i < K; ++i) {
+      float acc[VEC];
+      if constexpr (VEC == 4) {
+        // packed path, 128 columns per warp: four independent FFMA2 chains (2 column pairs x even/odd j)
+        const ulonglong2* mrow = reinterpret_cast<const ulonglong2*>(Mk + i * KP * 2);
+        unsigned long long a0 = 0ull, a1 = 0ull, b0 = 0ull, b1 = 0ull;
+#pragma unroll
+        for (int j2 = 0; j2 < KT / 2; ++j2) {
+          const ulonglong2 c = mrow[j2];             // {c_j, c_j}, {c_j+1, c_j+1}: warp-broadcast LDS.128
+          a0 = ffma2(c.x, pack2(y[2 * j2][0], y[2 * j2][1]), a0);
+          b0 = ffma2(c.x, pack2(y[2 * j2][2], y[2 * j2][3]), b0);
+          a1 = ffma2(c.y, pack2(y[2 * j2 + 1][0], y[2 * j2 + 1][1]), a1);
+          b1 = ffma2(c.y, pack2(y[2 * j2 + 1][2], y[2 * j2 + 1][3]), b1);
+        }
+        acc[0] = lo2(a0) + lo2(a1);
+        acc[1] = hi2(a0) + hi2(a1);
+        acc[2] = lo2(b0) + lo2(b1);
+        acc[3] = hi2(b0) + hi2(b1);
+      } else if constexpr (VEC == 2) {
+        // packed path: {acc0,acc1} += {c,c} * {y0,y1}; two independent chains for ILP
+        const ulonglong2* mrow = reinterpret_cast<const ulonglong2*>(Mk + i * KP * 2);
+        unsigned long long a0 = 0ull, a1 = 0ull;
+#pragma unroll
+        for (int j2 = 0; j2 < KT / 2; ++j2) {
+          const ulonglong2 c = mrow[j2];             // {c_j, c_j}, {c_j+1, c_j+1}: warp-broadcast LDS.128
+          a0 = ffma2(c.x, pack2(y[2 * j2][0], y[2 * j2][1]), a0);
+          a1 = ffma2(c.y, pack2(y[2 * j2 + 1][0], y[2 * j2 + 1][1]), a1);
+        }
+        acc[0] = lo2(a0) + lo2(a1);
+        acc[1] = hi2(a0) + hi2(a1);
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+        const float4* mrow = reinterpret_cast<const float4*>(Mk + i * KP);
+#pragma unroll
+        for (int j4 = 0; j4 < KT / 4; ++j4) {
+          const float4 c = mrow[j4];                 // same address for the whole warp: broadcast
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            acc[v] = fmaf(c.x, y[4 * j4 + 0][v], acc[v]);
+            acc[v] = fmaf(c.y, y[4 * j4 + 1][v], acc[v]);
+            acc[v] = fmaf(c.z, y[4 * j4 + 2][v], acc[v]);
+            acc[v] = fmaf(c.w, y[4 * j4 + 3][v], acc[v]);
+          }
+        }
+      }
+      if constexpr (MODE == DM_FWD_POOL) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          acc[v] = fmaxf(acc[v], 0.f);
+          if (acc[v] > best[v]) { best[v] = acc[v]; barg[v] = i; }   // strict > : first index on ties
+        }
+      } else {
+        if constexpr (MODE == DM_FWD) {
+          if (p.flags & VQA_GC_RELU) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[v] = fmaxf(acc[v], 0.f);
+          }
+          if (p.drop_p > 0.f) {
+            // 16 random bits per element from one 32-bit counter hash per (row, VEC-column group)
+#pragma unroll
+            for (int v0 = 0; v0 < VEC; v0 += 2) {
+              const uint32_t r = hash32((unsigned long long)(((long long)b * K + i) * (p.out_dim / 2) + (colg + v0) / 2), p.seed, p.offset);
+              acc[v0] = (r & 0xFFFFu) >= p.drop_thresh16 ? acc[v0] * p.drop_scale : 0.f;
+              if (v0 + 1 < VEC) acc[v0 + 1 < VEC ? v0 + 1 : v0] = (r >> 16) >= p.drop_thresh16 ? acc[v0 + 1 < VEC ? v0 + 1 : v0] * p.drop_scale : 0.f;
+            }
+          }
+        }
+        float* dst = p.out + ((long long)b * K + i) * p.ldo + colg;
+        if constexpr (VEC == 4) *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        else if constexpr (VEC == 2) *reinterpret_cast<float2*>(dst) = make_float2(acc[0], acc[1]);
+        else dst[0] = acc[0];
+      }
+    }
+    if constexpr (MODE == DM_FWD_POOL) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const long long o = (long long)b * p.out_dim + colg + v;
+        p.pooled[o] = best[v];
+        p.argmax[o] = barg[v];
+        p.hq[o] = fmaxf(p.q[o], 0.f) * best[v];
+      }
+    }
+  }
+}
+
+// host: pick the compile-time K bucket and launch.  Returns 1 when the shape is not eligible (caller falls back to the
+// generic gather kernels): the tile width 32*VEC must divide D = out_dim / nk so that a tile belongs to one kernel.
+static int make_tile_map(CUtensorMap* tm, const float* ptr, long long ld, long long rows, int cols, int TW, int K);
+
+template <int MODE>
+static int dense_launch(const DenseParams& base, int B, cudaStream_t stream) {
+  DenseParams p = base;
+  const int K = p.K, D = p.out_dim / p.nk;
+  const int KT = K <= 36 ? 36 : (K <= 52 ? 52 : (K <= 64 ? 64 : (K <= 100 ? 100 : 128)));
+  const int VEC = (KT == 36 && D % 128 == 0 && (p.ldo % 4) == 0) ? 4 : (KT <= 64 ? 2 : 1);
+  const int TWD = 32 * VEC, dup = VEC >= 2 ? 2 : 1;
+  if (K > 128 || D % TWD != 0 || (p.ldin % 4) != 0 || (p.ldo % VEC) != 0) return 1;
+  p.D = D;
+  p.ntiles = p.out_dim / TWD;
+  const int tpk = D / TWD;                                    // tiles per kernel
+  const int mat_bytes = K * KT * 4 * dup;
+  p.tile_stride = (K * TWD * 4 + 127) & ~127;
+  const int slots = MODE == DM_BWD_POOLED ? 0 : DN_WARPS * p.tile_stride;
+  const int misc = (2 * ((K + 1) & ~1) + 4 * p.nk) * 4 + K * p.nb + 512;
+  int nkc = ((226 * 1024) / 2 - 1024 - slots - misc) / mat_bytes;   // coefficient matrices per CTA at 2 CTAs / SM
+  if (nkc > (p.nk + 1) / 2) nkc = (p.nk + 1) / 2;             // at least 2 slabs per image: finer load balance
+  if (nkc < 1) nkc = 1;
+  if ((size_t)nkc * mat_bytes + slots + misc > 226 * 1024) return 1;
+  p.nkc = nkc;
+  p.tiles_per_cta = nkc * tpk;
+  const int nslab = (p.ntiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  // dynamic smem: [coefficients | centres | gauss | idx8 | pad128 | per-warp tile slots | barriers]
+  int off = (nkc * K * KT * dup + 2 * ((K + 1) & ~1) + 4 * p.nk) * 4 + K * p.nb;
+  off = (off + 127) & ~127;
+  p.ring_off = off;
+  p.nstage = 1;
+  p.bar_off = off + slots;
+  const size_t smem = (size_t)p.bar_off + DN_WARPS * 8 + 128;
+  CUtensorMap tm;
+  if (MODE != DM_BWD_POOLED) {
+    if (int rc = make_tile_map(&tm, p.in, p.ldin, (long long)B * K, p.out_dim, TWD, K)) return rc;
+  } else {
+    memset(&tm, 0, sizeof(tm));
+  }
+  dim3 grid(nslab, B);
+#define VQA_DENSE_CASE(KT_, VEC_)                                                                                      \
+  {                                                                                                                    \
+    VQA_CUDA(cudaFuncSetAttribute(graphconv_dense_kernel<KT_, VEC_, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    graphconv_dense_kernel<KT_, VEC_, MODE><<<grid, DN_CTA, smem, stream>>>(tm, p);                                    \
+  }
+  if (KT == 36 && VEC == 4) VQA_DENSE_CASE(36, 4)
+  else if (KT == 36) VQA_DENSE_CASE(36, 2)
+  else if (KT == 52) VQA_DENSE_CASE(52, 2)
+  else if (KT == 64) VQA_DENSE_CASE(64, 2)
+  else if (KT == 100) VQA_DENSE_CASE(100, 1)
+  else VQA_DENSE_CASE(128, 1)
+#undef VQA_DENSE_CASE
+  VQA_LAUNCH_CHECK("graphconv_dense_kernel");
+  return VQA_OK;
+}
+
 // ------------------------------------------------------------------------------------------ forward
 template <bool POOL>
 __global__ void __launch_bounds__(GC_THREADS)
 graphconv_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const GcParams p, const GcSmem L) {
   extern __shared__ uint8_t sm_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sm_raw) + 127) & ~uintptr_t(127));
+  uint8_t* sm = sm_raw + ((128u - (smem_u32(sm_raw) & 127u)) & 127u);   // pointer arithmetic keeps the .shared address space (LDS/STS)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, K = p.K, nbp = p.nbp, TW = p.TW;
   const int t0 = blockIdx.x * p.tiles_per_cta;
@@ -270,7 +594,7 @@ __global__ void __launch_bounds__(GC_THREADS)
 graphconv_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmD, const GcParams p,
                      const GcSmem L) {
   extern __shared__ uint8_t sm_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sm_raw) + 127) & ~uintptr_t(127));
+  uint8_t* sm = sm_raw + ((128u - (smem_u32(sm_raw) & 127u)) & 127u);   // pointer arithmetic keeps the .shared address space (LDS/STS)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, K = p.K, nb = p.nb, nbp = p.nbp, TW = p.TW;
   const int t0 = blockIdx.x * p.tiles_per_cta;
@@ -347,8 +671,8 @@ graphconv_bwd_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
       if (POOLED) return make_float4(ar.x == i ? dp.x : 0.f, ar.y == i ? dp.y : 0.f, ar.z == i ? dp.z : 0.f, ar.w == i ? dp.w : 0.f);
       return *reinterpret_cast<const float4*>(dtile + i * TW + col);
     };
-    // (a) dY[j] = sum over incoming edges (i,m) of coef * dO[i]
-    for (int j = warp; j < K; j += GC_WARPS) {
+    // (a) dY[j] = sum over incoming edges (i,m) of coef * dO[i]   (skipped when the dense kernel already produced dY)
+    for (int j = warp; j < K && p.out != nullptr; j += GC_WARPS) {
       if (active) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const int n = rev_cnt[j];
@@ -545,6 +869,17 @@ static int gc_fwd_common(bool pool, const float* Y, long long ldy, const int* id
   VQA_CHECK_ARG(Y && idx && boxes && gauss, "%s: null pointer", who);
   VQA_CHECK_ARG(aligned16(Y) && (ldy & 3) == 0 && ldy >= out_dim, "%s: Y must be 16-byte aligned with ld %% 4 == 0", who);
   VQA_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "%s: dropout p must be in [0,1)", who);
+  if (K <= 128 && nb <= K && nk <= MAX_NK && out_dim % nk == 0) {   // preferred: dense-register kernel
+    DenseParams dp{};
+    dp.in = Y; dp.ldin = ldy; dp.idx = idx; dp.alpha = alpha; dp.boxes = boxes; dp.ldbox = ldbox; dp.gauss = gauss;
+    dp.out = out; dp.ldo = ldo; dp.q = q; dp.pooled = pooled; dp.argmax = argmax; dp.hq = hq;
+    dp.K = K; dp.nb = nb; dp.nk = nk; dp.out_dim = out_dim; dp.flags = flags;
+    dp.drop_p = drop_p; dp.drop_scale = 1.f / (1.f - drop_p); dp.drop_thresh16 = (unsigned)(drop_p * 65536.f + 0.5f);
+    dp.seed = seed; dp.offset = offset;
+    if (pool) dp.ldo = 2;
+    const int rc = pool ? dense_launch<DM_FWD_POOL>(dp, B, stream) : dense_launch<DM_FWD>(dp, B, stream);
+    if (rc <= 0) return rc;
+  }
   GcPlan pl;
   if (int rc = gc_plan(&pl, B, K, nb, nk, out_dim, false, pool, false, who)) return rc;
   CUtensorMap tm;
@@ -597,6 +932,16 @@ extern "C" int vqa_graphconv_bwd_f32(const float* dO, long long lddo, const floa
   VQA_CHECK_ARG(pooled ? (dpooled && argmax) : true, "%s: need either dO or (dpooled, argmax)", who);
   VQA_CHECK_ARG(aligned16(Y) && (ldy & 3) == 0 && aligned16(dY) && (lddy & 3) == 0, "%s: Y/dY alignment", who);
   VQA_CHECK_ARG(pooled ? aligned16(dpooled) : (aligned16(dO) && (lddo & 3) == 0), "%s: upstream gradient alignment", who);
+  bool dy_done = false;
+  if (K <= 128 && nb <= K && nk <= MAX_NK && out_dim % nk == 0) {   // dY = M^T dO on the dense-register kernel
+    DenseParams dp{};
+    dp.in = dO; dp.ldin = pooled ? 2 : lddo; dp.dpooled = dpooled; dp.argmax_in = argmax;
+    dp.idx = idx; dp.alpha = alpha; dp.boxes = boxes; dp.ldbox = ldbox; dp.gauss = gauss; dp.out = dY; dp.ldo = lddy;
+    dp.K = K; dp.nb = nb; dp.nk = nk; dp.out_dim = out_dim;
+    const int rc = pooled ? dense_launch<DM_BWD_POOLED>(dp, B, stream) : dense_launch<DM_BWD_DENSE>(dp, B, stream);
+    if (rc < 0) return rc;
+    dy_done = rc == 0;
+  }
   GcPlan pl;
   if (int rc = gc_plan(&pl, B, K, nb, nk, out_dim, true, false, pooled, who)) return rc;
   CUtensorMap tmY, tmD;
@@ -605,7 +950,7 @@ extern "C" int vqa_graphconv_bwd_f32(const float* dO, long long lddo, const floa
   else tmD = tmY;
   GcParams p{};
   p.Y = Y; p.ldy = ldy; p.dO = dO; p.lddo = lddo; p.dpooled = dpooled; p.argmax_in = argmax;
-  p.idx = idx; p.alpha = alpha; p.boxes = boxes; p.ldbox = ldbox; p.gauss = gauss; p.out = dY; p.ldo = lddy; p.P = P;
+  p.idx = idx; p.alpha = alpha; p.boxes = boxes; p.ldbox = ldbox; p.gauss = gauss; p.out = dy_done ? nullptr : dY; p.ldo = lddy; p.P = P;
   p.K = K; p.nb = nb; p.nbp = pl.nbp; p.nk = nk; p.out_dim = out_dim; p.D = pl.D; p.TW = pl.TW; p.tstride = pl.tstride;
   p.tiles_per_cta = pl.tiles_per_cta; p.ntiles = pl.ntiles; p.nkc = pl.nkc; p.nstage = pl.nstage;
   dim3 grid(pl.nslab, B);
