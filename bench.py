@@ -33,7 +33,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="vqa2_b512")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_strict", "tf32x3", "tf32"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
+                    help="fp32: split-bf16 3-pass tcgen05 GEMMs (fp32-grade, the parity mode); bf16: 1-pass bf16 tensor-core GEMMs")
     ap.add_argument("--gru-tf32", action="store_true", help="let cuDNN run the (unchanged) GRU in TF32, torch's default; off = fp32 like the parity tests")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=64, help="questions per CPU step (bounded sample of the workload)")
@@ -101,7 +102,7 @@ def config_dict(w, args, world):
     return {"workload": f"{w.name}: VQA2 conditioned-graph train step, per-GPU batch {w.batch}, K={w.n_obj} boxes x {w.feat_dim}-d, "
                         f"<= {w.max_qlen}-token questions, top-k={w.neighbourhood}, {w.n_kernels} Gaussian kernels, {w.out_dim} answers, dropout {w.dropout}",
             "global_batch": w.batch * world, "step": "zero_grad+forward+MultiLabelSoftMarginLoss+backward+allreduce+Adam",
-            "parallelism": f"dp{world}", "gru": "cuDNN tf32" if args.gru_tf32 else "cuDNN fp32", "gemm_precision": "tf32x3 (fp32-grade)" if args.precision != "tf32" else "tf32",
+            "parallelism": f"dp{world}", "gru": "cuDNN tf32" if args.gru_tf32 else "cuDNN fp32", "gemm_precision": "split-bf16 x3 passes (fp32-grade, rel err ~1e-5) + chunk-promoted 3xTF32 graph-learner forward" if args.precision == "fp32" else "bf16 x1 pass (graph-learner forward fp32-grade)",
             "l2_policy": "inputs larger than L2 (image batch 151 MB > 126 MB), 3 rotating batches"}
 
 
@@ -298,7 +299,7 @@ def run_b200(args, workload):
     line = {
         "metric": "train questions/sec (fwd+bwd)", "value": round(value, 1), "unit": "questions/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
         "config": config_dict(w, args, world),
         "e2e": {"value": round(e2e_value, 1), "unit": "questions/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e, 4), "last_loss": last_loss},

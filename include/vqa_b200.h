@@ -50,6 +50,22 @@ int vqa_gemm_f32(const float* A, long long lda, int a_mn_major, const float* B, 
                  long long ldrb, int group, const float* aux, long long ldaux, float aux_scale, int flags,
                  int precision, int split_k, int tile_n, vqa_stream_t stream);
 
+/* Split-bf16 operand planes: hi = bf16(x), lo = bf16(x - hi), each (rows, ldp) bf16 with ldp % 8 == 0.  lo may be
+ * NULL (plain bf16).  Producers of large activations write the planes from their own epilogue instead. */
+int vqa_split_bf16_f32(const float* x, long long ldx, void* hi, void* lo, long long ldp, long long rows, int cols,
+                       vqa_stream_t stream);
+
+/* C[M,N] = epi( sum_k A[m,k] * B[n,k] ) with A = A_hi + A_lo, B = B_hi + B_lo given as bf16 planes (kind::f16
+ * tcgen05.mma, fp32 TMEM accumulator).  passes = 3: lo*hi + hi*lo + hi*hi (fp32-grade, ~2^-17 per product);
+ * passes = 1: hi planes only (bf16 mode).  Same operand-major convention, epilogue and call sites as vqa_gemm_f32;
+ * the mask may also be given as the hi plane of a split tensor (aux_hi), and the result can be written as fp32 (C),
+ * as split planes (C_hi, C_lo; C_lo may be NULL), or both. */
+int vqa_gemm_bf16s(const void* A_hi, const void* A_lo, long long lda, int a_mn_major, const void* B_hi,
+                   const void* B_lo, long long ldb, int b_mn_major, float* C, long long ldc, void* C_hi, void* C_lo,
+                   long long ldcs, int M, int N, int Kc, const float* bias, const float* rowbcast, long long ldrb,
+                   int group, const float* aux, long long ldaux, const void* aux_hi, long long ldauxh,
+                   float aux_scale, int flags, int passes, int split_k, int tile_n, vqa_stream_t stream);
+
 /* y = x * keep / (1-p), keep ~ Bernoulli(1-p) from Philox4x32-10(seed; counter = (element/4, offset)).
  * Replaces nn.Dropout on the image tensor and the classifier hidden (sparse_graph_model.py:111,156). */
 int vqa_dropout_f32(const float* x, float* y, long long n, float p, unsigned long long seed,

@@ -103,6 +103,78 @@ def test_gemm_rejects_bad_arguments(kn):
         kn.gemm(torch.randn(8, 32), torch.randn(8, 32))   # CPU tensors: no fallback
 
 
+# --------------------------------------------------------------------------------------------- split-bf16 GEMM
+def test_split_planes_reconstruct_fp32(kn):
+    x = torch.randn(37, 2052, device=DEV) * 3.0
+    s = kn.split(x)
+    assert s.ld == 2056 and s.hi.dtype == torch.bfloat16
+    assert rel_err(s.float().cpu(), x.cpu()) < 2 ** -16            # hi + lo carries >= 16 mantissa bits
+    assert (s.hi[:, :2052].float() == x.bfloat16().float()).all()  # hi is exactly bf16(x), round to nearest
+    h = kn.split(x, with_lo=False)
+    assert h.lo is None and (h.hi[:, :2052] == s.hi[:, :2052]).all()
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,tile_n", GEMM_CASES)
+@pytest.mark.parametrize("passes,tol", [(3, 3e-5), (1, 8e-3)])
+def test_gemm_split_bf16_matches_fp64(kn, M, N, K, a_mn, b_mn, tile_n, passes, tol):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn(N, K, generator=g)
+    ref = a.double() @ b.double().t()
+    a_s = kn.split((a.t().contiguous() if a_mn else a).to(DEV))
+    b_s = kn.split((b.t().contiguous() if b_mn else b).to(DEV))
+    out = kn.gemm_s(a_s, b_s, a_mn=a_mn, b_mn=b_mn, passes=passes, tile_n=tile_n)
+    torch.cuda.synchronize()
+    assert out.shape == (M, N)
+    assert rel_err(out.cpu(), ref) < tol
+
+
+def test_gemm_split_bf16_epilogues(kn):
+    g = torch.Generator().manual_seed(5)
+    B, Kn, F, N = 5, 12, 40, 72
+    M = B * Kn
+    x = torch.randn(M, F, generator=g)
+    w = torch.randn(N, F, generator=g)
+    bias = torch.randn(N, generator=g)
+    rb = torch.randn(B, N, generator=g)
+    aux = torch.randn(M, N, generator=g)
+    xs, ws = kn.split(x.to(DEV)), kn.split(w.to(DEV))
+    ref = x.double() @ w.double().t() + rb.double().repeat_interleave(Kn, 0) + bias.double()
+    out = kn.gemm_s(xs, ws, bias=bias.to(DEV), rowbcast=rb.to(DEV), group=Kn, relu=True)
+    assert rel_err(out.cpu(), ref.clamp(min=0)) < 3e-5
+    ref2 = torch.where(aux > 0, 2.0 * (x.double() @ w.double().t()), torch.zeros((), dtype=torch.float64))
+    out2 = kn.gemm_s(xs, ws, aux=aux.to(DEV), aux_scale=2.0)                       # fp32 mask
+    assert rel_err(out2.cpu(), ref2) < 3e-5
+    out3 = kn.gemm_s(xs, ws, aux=kn.split(aux.to(DEV)), aux_scale=2.0)             # mask = hi plane of a split tensor
+    assert rel_err(out3.cpu(), ref2) < 3e-5
+    # split-plane output (with and without the fp32 copy) and writing into a column slice
+    os_ = kn.empty_split(M, N, DEV)
+    out4 = kn.gemm_s(xs, ws, out_split=os_)
+    assert rel_err(os_.float().cpu(), x.double() @ w.double().t()) < 3e-5 and rel_err(out4.cpu(), x.double() @ w.double().t()) < 3e-5
+    os2 = kn.empty_split(M, N, DEV)
+    r = kn.gemm_s(xs, ws, out_split=os2, want_f32=False, relu=True)
+    assert r is os2 and rel_err(os2.float().cpu(), (x.double() @ w.double().t()).clamp(min=0)) < 3e-5
+    big = torch.zeros(M, N + 24, device=DEV)
+    kn.gemm_s(xs, ws, out=big[:, 8:8 + N])
+    assert rel_err(big[:, 8:8 + N].cpu(), x.double() @ w.double().t()) < 3e-5
+    assert big[:, :8].abs().max() == 0 and big[:, 8 + N:].abs().max() == 0
+    # column sub-view of a wider operand (question half of the graph-learner weight)
+    wide = torch.randn(N, 64 + F, generator=g)
+    wide_s = kn.split(wide.to(DEV))
+    out5 = kn.gemm_s(xs, wide_s.cols_slice(64, 64 + F))
+    assert rel_err(out5.cpu(), x.double() @ wide[:, 64:].double().t()) < 3e-5
+
+
+@pytest.mark.parametrize("split", [2, 5, 16])
+def test_gemm_split_bf16_split_k(kn, split):
+    g = torch.Generator().manual_seed(9)
+    Kc, M, N = 1000, 96, 200
+    a = torch.randn(Kc, M, generator=g)
+    b = torch.randn(Kc, N, generator=g)
+    out = kn.gemm_s(kn.split(a.to(DEV)), kn.split(b.to(DEV)), a_mn=True, b_mn=True, split_k=split)
+    assert rel_err(out.cpu(), a.double().t() @ b.double()) < 3e-5
+
+
 # --------------------------------------------------------------------------------------------- small kernels
 def test_dropout_statistics_and_determinism(kn):
     x = torch.ones(1 << 20, device=DEV)

@@ -1,0 +1,432 @@
+// Dense projections on the bf16 tensor-core path with fp32-grade results: "split-bf16" tcgen05 GEMM (sm_100a).
+//
+//   C[M,N] = epilogue( sum_k A[m,k] * B[n,k] ),   A = A_hi + A_lo,  B = B_hi + B_lo   (bf16 planes in HBM)
+//
+// Every fp32 operand x is stored as two bf16 planes hi = bf16(x), lo = bf16(x - hi) (16+ mantissa bits, produced by
+// vqa_split_bf16_f32 or directly by the producing kernel's epilogue).  PASSES = 3 issues lo*hi + hi*lo + hi*hi into
+// one fp32 TMEM accumulator (relative error ~2^-17 per product: well inside the 1e-3 parity budget, where single-pass
+// TF32 measured 2.9e-3 is not); PASSES = 1 uses the hi planes only (plain bf16 tensor-core GEMM, stated tolerance).
+// Versus the TF32x3 kernel (gemm_tcgen05.cu) this halves the tensor-pipe time per pass (kind::f16, K = 16 per
+// instruction), needs no in-kernel operand transform (no generic-proxy smem traffic at all: TMA -> smem -> UMMA) and
+// moves the same 4 bytes per operand element.
+//
+// Replaces the same reference call sites as gemm_tcgen05.cu: the per-kernel conv Linears (layers.py:140-142, ONE
+// projection), the classifier (sparse_graph_model.py:154-157), the graph-learner backward, and every dX / dW product.
+//
+// Structure: one 128 x BN output tile per CTA, 6 warps: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA
+// issuer, warps 2-5 = epilogue (TMEM -> registers -> global; bias / row-broadcast / ReLU / mask / split-plane output).
+// Operands are K-major (contraction contiguous) or MN-major (dW = dY^T X: contraction strided); both arrive by TMA
+// with the 128-byte swizzle in the canonical UMMA layouts.
+#include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+#include <mutex>
+#include <cstring>
+
+#include "../../include/vqa_b200.h"
+
+namespace vqa {
+namespace sb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                  // bf16 elements per k-block: one 128-byte swizzle row
+constexpr int A_TILE = BM * 128;        // bytes per plane
+constexpr int THREADS = 192;
+constexpr int SMEM_BUDGET = 232448 - 1024 - 256;
+
+struct Params {
+  float* C; long long ldc;
+  __nv_bfloat16* Chi; __nv_bfloat16* Clo; long long ldcs;      // optional split-plane copy of the output
+  int M, N, Kc, a_mn, b_mn;
+  const float* bias;
+  const float* rowb; long long ldrb; int group;
+  const float* aux; long long ldaux;                            // mask source, fp32 ...
+  const __nv_bfloat16* auxh; long long ldauxh;                  // ... or the hi plane of a split tensor
+  float aux_scale;
+  int flags, kb_per_split, num_kb;
+};
+
+template <int BN, int PASSES>
+struct Cfg {
+  static constexpr int PLANES = PASSES == 3 ? 2 : 1;
+  static constexpr int B_TILE = BN * 128;
+  static constexpr int PLANE = A_TILE + B_TILE;               // [A | B] of one plane
+  static constexpr int STAGE = PLANE * PLANES;
+  static constexpr int S_ = SMEM_BUDGET / STAGE;
+  static constexpr int S = S_ > 8 ? 8 : S_;
+  static constexpr int SMEM = S * STAGE + 1024 + 256;
+};
+
+// UMMA shared-memory descriptor, 16-bit operands, 128-byte swizzle.
+//   K-major : rows of 128 B (64 k), 8-row swizzle atoms 1024 B apart (SBO); LBO unused.
+//   MN-major: rows of 128 B (64 mn) indexed by k, 8-k atoms 1024 B apart (SBO), 64-element MN chunks 8192 B apart
+//             (LBO = one [64 k x 64 mn] TMA box).
+__device__ __forceinline__ uint64_t umma_desc16(uint32_t saddr, int mn_major) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(mn_major ? (8192 >> 4) : 1) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;                                            // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+// epilogue for 32 consecutive columns [cb, cb+32) of one output row
+struct Epi {
+  const Params& p;
+  float* crow; __nv_bfloat16* hrow; __nv_bfloat16* lrow; const float* rb; const float* ax; const __nv_bfloat16* axh;
+  bool vec_ok, relu, atomic;
+  __device__ __forceinline__ Epi(const Params& p_, int row) : p(p_) {
+    relu = p.flags & VQA_GEMM_RELU; atomic = p.flags & VQA_GEMM_ATOMIC_ADD;
+    crow = p.C ? p.C + (long long)row * p.ldc : nullptr;
+    hrow = p.Chi ? p.Chi + (long long)row * p.ldcs : nullptr;
+    lrow = p.Clo ? p.Clo + (long long)row * p.ldcs : nullptr;
+    rb = p.rowb ? p.rowb + (long long)(row / p.group) * p.ldrb : nullptr;
+    ax = p.aux ? p.aux + (long long)row * p.ldaux : nullptr;
+    axh = p.auxh ? p.auxh + (long long)row * p.ldauxh : nullptr;
+    vec_ok = ((p.N & 7) == 0) &&
+             (!p.C || (((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0))) &&
+             (!p.Chi || (((p.ldcs & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.Chi) & 15) == 0) && (!p.Clo || (reinterpret_cast<uintptr_t>(p.Clo) & 15) == 0))) &&
+             (!ax || (((p.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0))) &&
+             (!axh || (((p.ldauxh & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.auxh) & 15) == 0))) &&
+             (!rb || (((p.ldrb & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.rowb) & 15) == 0))) &&
+             (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
+  }
+  __device__ __forceinline__ float one(float v, int col) const {
+    if (rb) v += rb[col];
+    if (p.bias) v += p.bias[col];
+    if (relu) v = fmaxf(v, 0.f);
+    if (ax) v = ax[col] > 0.f ? v * p.aux_scale : 0.f;
+    if (axh) v = __bfloat162float(axh[col]) > 0.f ? v * p.aux_scale : 0.f;
+    return v;
+  }
+  __device__ __forceinline__ void store32(int cb, const float* r) const {
+    if (vec_ok && !atomic) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const int col = cb + j;
+        if (col >= p.N) break;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = r[j + e];
+        if (rb) {
+          const float4 a0 = *reinterpret_cast<const float4*>(rb + col), a1 = *reinterpret_cast<const float4*>(rb + col + 4);
+          v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+        }
+        if (p.bias) {
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.bias + col)), a1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+          v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+        }
+        if (relu) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+        }
+        if (ax) {
+          const float4 a0 = *reinterpret_cast<const float4*>(ax + col), a1 = *reinterpret_cast<const float4*>(ax + col + 4);
+          const float m[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = m[e] > 0.f ? v[e] * p.aux_scale : 0.f;
+        }
+        if (axh) {
+          const uint4 a = *reinterpret_cast<const uint4*>(axh + col);
+          const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {     // bf16 > 0  <=>  sign clear and magnitude bits non-zero
+            const uint32_t lo16 = w[e] & 0xFFFFu, hi16 = w[e] >> 16;
+            v[2 * e] = (lo16 != 0 && lo16 < 0x8000u) ? v[2 * e] * p.aux_scale : 0.f;
+            v[2 * e + 1] = (hi16 != 0 && hi16 < 0x8000u) ? v[2 * e + 1] * p.aux_scale : 0.f;
+          }
+        }
+        if (crow) {
+          *reinterpret_cast<float4*>(crow + col) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(crow + col + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        if (hrow) {
+          float h[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) h[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
+          *reinterpret_cast<uint4*>(hrow + col) = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+          if (lrow)
+            *reinterpret_cast<uint4*>(lrow + col) = make_uint4(pack_bf16(v[0] - h[0], v[1] - h[1]), pack_bf16(v[2] - h[2], v[3] - h[3]),
+                                                               pack_bf16(v[4] - h[4], v[5] - h[5]), pack_bf16(v[6] - h[6], v[7] - h[7]));
+        }
+      }
+    } else {
+#pragma unroll 4
+      for (int j = 0; j < 32; ++j) {
+        const int col = cb + j;
+        if (col >= p.N) break;
+        const float v = one(r[j], col);
+        if (crow) { if (atomic) atomicAdd(crow + col, v); else crow[col] = v; }
+        if (hrow) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(v);
+          hrow[col] = h;
+          if (lrow) lrow[col] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
+      }
+    }
+  }
+};
+
+struct Maps { CUtensorMap a_hi, a_lo, b_hi, b_lo; };
+
+template <int BN, int PASSES>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_bf16s_kernel(const __grid_constant__ Maps tm, const Params p) {
+  using C = Cfg<BN, PASSES>;
+  constexpr int S = C::S;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * C::STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + S;
+  uint64_t* acc_full = bars + 2 * S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_stop = min(p.num_kb, kb_begin + p.kb_per_split);
+  const int nkb = kb_stop - kb_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm.a_hi); tma_prefetch_desc(&tm.b_hi);
+    if (PASSES == 3) { tma_prefetch_desc(&tm.a_lo); tma_prefetch_desc(&tm.b_lo); }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      mbar_init(acc_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % S, ph = (i / S) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], C::STAGE);
+        const int k0 = (kb_begin + i) * BK;
+#pragma unroll
+        for (int pl = 0; pl < C::PLANES; ++pl) {
+          uint8_t* a_dst = smem + s * C::STAGE + pl * C::PLANE;
+          uint8_t* b_dst = a_dst + A_TILE;
+          const CUtensorMap* ma = pl ? &tm.a_lo : &tm.a_hi;
+          const CUtensorMap* mb = pl ? &tm.b_lo : &tm.b_hi;
+          if (!p.a_mn) {
+            tma_load_2d(a_dst, ma, &full[s], k0, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d(a_dst + c * 8192, ma, &full[s], m0 + c * 64, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(b_dst, mb, &full[s], k0, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(b_dst + c * 8192, mb, &full[s], n0 + c * 64, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one thread)
+    // instruction descriptor: D = f32, A = B = bf16, majors, N >> 3, M >> 4
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t a_step = p.a_mn ? 2048 : 32, b_step = p.b_mn ? 2048 : 32;   // bytes per K = 16
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % S, ph = (i / S) & 1;
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_hi = smem_u32(smem + s * C::STAGE), b_hi = a_hi + A_TILE;
+        const uint32_t a_lo = a_hi + C::PLANE, b_lo = a_lo + A_TILE;
+#pragma unroll
+        for (int ks = 0; ks < BK / 16; ++ks) {
+          const uint64_t dah = umma_desc16(a_hi + ks * a_step, p.a_mn), dbh = umma_desc16(b_hi + ks * b_step, p.b_mn);
+          const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
+          if (PASSES == 3) {
+            const uint64_t dal = umma_desc16(a_lo + ks * a_step, p.a_mn), dbl = umma_desc16(b_lo + ks * b_step, p.b_mn);
+            tc_mma<1>(tmem_base, dal, dbh, idesc, acc);   // small terms first
+            tc_mma<1>(tmem_base, dah, dbl, idesc, 1u);
+            tc_mma<1>(tmem_base, dah, dbh, idesc, 1u);
+          } else {
+            tc_mma<1>(tmem_base, dah, dbh, idesc, acc);
+          }
+        }
+        tc_commit(&empty[s]);                       // smem slot reusable once these MMAs retire
+        if (i == nkb - 1) tc_commit(acc_full);      // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------ warps 2-5: epilogue
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    const Epi epi(p, row_ok ? row : 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= p.N) break;            // warp-uniform
+      uint32_t r[32];
+      tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tc_wait_ld();
+      if (row_ok) epi.store32(n0 + c0, reinterpret_cast<const float*>(r));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(f);
+  });
+  return fn;
+}
+
+// plane stored either (rows = MN, cols = K contiguous) [k-major] or (rows = K, cols = MN contiguous) [mn-major]
+static int make_map(CUtensorMap* tm, const void* ptr, long long ld, int mn_extent, int k_extent, int mn_major, int tile_mn) {
+  auto enc = get_encode();
+  if (!enc) return vqa_fail(VQA_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2], strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2], estr[2] = {1, 1};
+  if (!mn_major) { dims[0] = k_extent; dims[1] = mn_extent; box[0] = BK; box[1] = tile_mn; }
+  else           { dims[0] = mn_extent; dims[1] = k_extent; box[0] = 64; box[1] = BK; }
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return vqa_fail(VQA_ERR_CUDA, "cuTensorMapEncodeTiled(bf16 plane) failed with CUresult %d (ld=%lld mn=%d k=%d)", (int)r, ld, mn_extent, k_extent);
+  return VQA_OK;
+}
+
+template <int BN, int PASSES>
+static int launch(const Maps& tm, const Params& p, int splits, cudaStream_t st) {
+  using C = Cfg<BN, PASSES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VQA_CUDA(cudaFuncSetAttribute(gemm_bf16s_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    attr_set = true;
+  }
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, splits);
+  gemm_bf16s_kernel<BN, PASSES><<<grid, THREADS, C::SMEM, st>>>(tm, p);
+  VQA_LAUNCH_CHECK("gemm_bf16s_kernel");
+  return VQA_OK;
+}
+
+// ------------------------------------------------------------------------------------------ fp32 -> (hi, lo) planes
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ hi,
+                                                   __nv_bfloat16* __restrict__ lo, long long ldp, long long rows, int cols, int vec) {
+  const int groups = (cols + 7) >> 3;
+  const long long total = rows * groups;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const long long r = g / groups;
+    const int c = (int)(g - r * groups) << 3;
+    const float* src = x + r * ldx + c;
+    float v[8];
+    if (vec && c + 8 <= cols) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = c + e < cols ? src[e] : 0.f;
+    }
+    float h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
+    *reinterpret_cast<uint4*>(hi + r * ldp + c) = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+    if (lo)
+      *reinterpret_cast<uint4*>(lo + r * ldp + c) = make_uint4(pack_bf16(v[0] - h[0], v[1] - h[1]), pack_bf16(v[2] - h[2], v[3] - h[3]),
+                                                               pack_bf16(v[4] - h[4], v[5] - h[5]), pack_bf16(v[6] - h[6], v[7] - h[7]));
+  }
+}
+
+}  // namespace sb
+}  // namespace vqa
+
+using namespace vqa;
+
+extern "C" int vqa_split_bf16_f32(const float* x, long long ldx, void* hi, void* lo, long long ldp, long long rows, int cols,
+                                  cudaStream_t stream) {
+  VQA_CHECK_ARG(x && hi && rows > 0 && cols > 0, "vqa_split_bf16_f32: bad arguments");
+  VQA_CHECK_ARG((ldp & 7) == 0 && ldp >= ((cols + 7) & ~7) && aligned16(hi) && (!lo || aligned16(lo)),
+                "vqa_split_bf16_f32: planes need 16-byte aligned rows with ld %% 8 == 0 and ld >= cols rounded up to 8 (ldp=%lld cols=%d)", ldp, cols);
+  const int vec = aligned16(x) && (ldx & 3) == 0;
+  const long long groups = rows * ((cols + 7) >> 3);
+  long long blocks = (groups + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  sb::split_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), ldp, rows, cols, vec);
+  VQA_LAUNCH_CHECK("split_kernel");
+  return VQA_OK;
+}
+
+extern "C" int vqa_gemm_bf16s(const void* A_hi, const void* A_lo, long long lda, int a_mn_major, const void* B_hi,
+                              const void* B_lo, long long ldb, int b_mn_major, float* C, long long ldc, void* C_hi, void* C_lo,
+                              long long ldcs, int M, int N, int Kc, const float* bias, const float* rowbcast, long long ldrb,
+                              int group, const float* aux, long long ldaux, const void* aux_hi, long long ldauxh,
+                              float aux_scale, int flags, int passes, int split_k, int tile_n, cudaStream_t stream) {
+  const char* who = "vqa_gemm_bf16s";
+  VQA_CHECK_ARG(A_hi && B_hi && (C || C_hi), "%s: null operand", who);
+  VQA_CHECK_ARG(passes == 1 || passes == 3, "%s: passes must be 1 (bf16) or 3 (split-bf16, fp32-grade), got %d", who, passes);
+  VQA_CHECK_ARG(passes == 1 || (A_lo && B_lo), "%s: 3-pass mode needs the lo planes", who);
+  VQA_CHECK_ARG(M > 0 && N > 0 && Kc > 0, "%s: empty problem M=%d N=%d K=%d", who, M, N, Kc);
+  VQA_CHECK_ARG(aligned16(A_hi) && aligned16(B_hi) && (!A_lo || aligned16(A_lo)) && (!B_lo || aligned16(B_lo)), "%s: planes must be 16-byte aligned for TMA", who);
+  VQA_CHECK_ARG((lda & 7) == 0 && (ldb & 7) == 0, "%s: plane leading dimensions must be multiples of 8 bf16 (TMA 16-byte strides), got lda=%lld ldb=%lld", who, lda, ldb);
+  VQA_CHECK_ARG(lda >= (a_mn_major ? M : Kc) && ldb >= (b_mn_major ? N : Kc) && (!C || ldc >= N) && (!C_hi || ldcs >= N), "%s: leading dimension smaller than the row length", who);
+  VQA_CHECK_ARG(!rowbcast || group > 0, "%s: rowbcast needs group > 0", who);
+  VQA_CHECK_ARG(!(aux && aux_hi), "%s: give the mask either as fp32 or as a bf16 hi plane, not both", who);
+  const int num_kb = (Kc + sb::BK - 1) / sb::BK;
+  int splits = split_k < 1 ? 1 : split_k;
+  if (splits > num_kb) splits = num_kb;
+  int per = (num_kb + splits - 1) / splits;
+  splits = (num_kb + per - 1) / per;   // no empty split
+  if (splits > 1) {
+    VQA_CHECK_ARG(C && !C_hi && !bias && !rowbcast && !aux && !aux_hi && !(flags & VQA_GEMM_RELU), "%s: split-K supports the plain fp32 epilogue only", who);
+    flags |= VQA_GEMM_ATOMIC_ADD;      // caller zero-fills C
+  }
+  int bn = tile_n;
+  if (bn == 0) bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  VQA_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "%s: tile_n must be 64, 128 or 256", who);
+
+  sb::Maps tm;
+  memset(&tm, 0, sizeof(tm));
+  int rc = sb::make_map(&tm.a_hi, A_hi, lda, M, Kc, a_mn_major, sb::BM);
+  if (!rc) rc = sb::make_map(&tm.b_hi, B_hi, ldb, N, Kc, b_mn_major, bn);
+  if (!rc && passes == 3) rc = sb::make_map(&tm.a_lo, A_lo, lda, M, Kc, a_mn_major, sb::BM);
+  if (!rc && passes == 3) rc = sb::make_map(&tm.b_lo, B_lo, ldb, N, Kc, b_mn_major, bn);
+  if (rc) return rc;
+  sb::Params p{C, ldc, reinterpret_cast<__nv_bfloat16*>(C_hi), reinterpret_cast<__nv_bfloat16*>(C_lo), ldcs, M, N, Kc,
+               a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, bias, rowbcast, ldrb, group, aux, ldaux,
+               reinterpret_cast<const __nv_bfloat16*>(aux_hi), ldauxh, aux_scale, flags, per, num_kb};
+#define VQA_DISPATCH(BN_) (passes == 3 ? sb::launch<BN_, 3>(tm, p, splits, stream) : sb::launch<BN_, 1>(tm, p, splits, stream))
+  if (bn == 256) return VQA_DISPATCH(256);
+  if (bn == 128) return VQA_DISPATCH(128);
+  return VQA_DISPATCH(64);
+#undef VQA_DISPATCH
+}

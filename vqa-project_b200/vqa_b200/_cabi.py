@@ -27,6 +27,9 @@ _u64 = C.c_ulonglong
 # name -> argument types (all return int unless noted); mirrors include/vqa_b200.h one-to-one
 SIGNATURES = {
     "vqa_gemm_f32": [_p, _ll, _i, _p, _ll, _i, _p, _ll, _i, _i, _i, _p, _p, _ll, _i, _p, _ll, _f, _i, _i, _i, _i, _p],
+    "vqa_split_bf16_f32": [_p, _ll, _p, _p, _ll, _ll, _i, _p],
+    "vqa_gemm_bf16s": [_p, _p, _ll, _i, _p, _p, _ll, _i, _p, _ll, _p, _p, _ll, _i, _i, _i, _p, _p, _ll, _i, _p, _ll, _p, _ll,
+                       _f, _i, _i, _i, _i, _p],
     "vqa_dropout_f32": [_p, _p, _ll, _f, _u64, _u64, _p],
     "vqa_weight_norm_fwd_f32": [_p, _p, _p, _i, _i, _p],
     "vqa_weight_norm_bwd_f32": [_p, _p, _p, _p, _p, _i, _i, _p],

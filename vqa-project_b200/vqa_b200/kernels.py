@@ -102,6 +102,92 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     return out
 
 
+# ------------------------------------------------------------------------------------------- split-bf16 GEMM
+class SplitT:
+    """An fp32 matrix stored as two bf16 planes (hi, lo) of shape (rows, ld), ld % 8 == 0; lo is None in bf16 mode.
+    ``shape`` is the logical (rows, cols)."""
+    __slots__ = ("hi", "lo", "rows", "cols", "ld")
+
+    def __init__(self, hi, lo, rows, cols, ld):
+        self.hi, self.lo, self.rows, self.cols, self.ld = hi, lo, rows, cols, ld
+
+    @property
+    def shape(self):
+        return (self.rows, self.cols)
+
+    def float(self) -> torch.Tensor:
+        x = self.hi[:, :self.cols].float()
+        return x + self.lo[:, :self.cols].float() if self.lo is not None else x
+
+    def rows_slice(self, r0: int, r1: int) -> "SplitT":
+        return SplitT(self.hi[r0:r1], None if self.lo is None else self.lo[r0:r1], r1 - r0, self.cols, self.ld)
+
+    def cols_slice(self, c0: int, c1: int) -> "SplitT":
+        if c0 % 8:
+            raise RuntimeError("SplitT.cols_slice: start column must be a multiple of 8 (16-byte TMA alignment)")
+        return SplitT(self.hi[:, c0:], None if self.lo is None else self.lo[:, c0:], self.rows, c1 - c0, self.ld)
+
+
+def empty_split(rows: int, cols: int, device, with_lo: bool = True) -> SplitT:
+    ld = (cols + 7) // 8 * 8
+    buf = torch.empty((2 if with_lo else 1, rows, ld), device=device, dtype=torch.bfloat16)
+    return SplitT(buf[0], buf[1] if with_lo else None, rows, cols, ld)
+
+
+def split(x: torch.Tensor, with_lo: bool = True) -> SplitT:
+    """fp32 (rows, cols) -> bf16 planes hi = bf16(x), lo = bf16(x - hi)."""
+    x, ldx = _rows_view(_chk(x, "split x"), "split x")
+    rows, cols = x.shape
+    out = empty_split(rows, cols, x.device, with_lo)
+    _call("vqa_split_bf16_f32", x.data_ptr(), ldx, out.hi.data_ptr(), _ptr(out.lo), out.ld, rows, cols, _stream())
+    return out
+
+
+def gemm_s(a: SplitT, b: SplitT, *, a_mn: bool = False, b_mn: bool = False, out: Optional[torch.Tensor] = None,
+           out_split: Optional[SplitT] = None, want_f32: bool = True, bias: Optional[torch.Tensor] = None,
+           rowbcast: Optional[torch.Tensor] = None, group: int = 1, aux=None, aux_scale: float = 1.0, relu: bool = False,
+           passes: int = 3, split_k: int = 1, tile_n: int = 0):
+    """C[M,N] = epi(A . B^T) on the split-bf16 tcgen05 GEMM.  ``a`` is (M,K) [a_mn=False] or (K,M) [a_mn=True]; same
+    for ``b`` with N.  ``aux`` (mask source) may be an fp32 tensor or a SplitT.  Returns ``out`` (fp32) or, when
+    ``want_f32`` is False, ``out_split``."""
+    M, Ka = (a.cols, a.rows) if a_mn else (a.rows, a.cols)
+    N, Kb = (b.cols, b.rows) if b_mn else (b.rows, b.cols)
+    if Ka != Kb:
+        raise RuntimeError(f"gemm_s: contraction mismatch {Ka} vs {Kb}")
+    if passes == 3 and (a.lo is None or b.lo is None):
+        raise RuntimeError("gemm_s: 3-pass mode needs operands split with with_lo=True")
+    dev = a.hi.device
+    ldc = 0
+    if want_f32:
+        if out is None:
+            out = torch.empty((M, N), device=dev, dtype=torch.float32)
+            if split_k > 1:
+                out.zero_()
+        elif out.shape != (M, N):
+            raise RuntimeError(f"gemm_s: out has shape {tuple(out.shape)}, expected {(M, N)}")
+        out, ldc = _rows_view(_chk(out, "gemm_s out"), "gemm_s out")
+    else:
+        out = None
+        if out_split is None:
+            raise RuntimeError("gemm_s: want_f32=False needs out_split")
+    if out_split is not None and out_split.shape != (M, N):
+        raise RuntimeError(f"gemm_s: out_split has shape {out_split.shape}, expected {(M, N)}")
+    ldrb = ldaux = ldauxh = 0
+    aux_f = aux_h = None
+    if rowbcast is not None:
+        rowbcast, ldrb = _rows_view(_chk(rowbcast, "gemm_s rowbcast"), "gemm_s rowbcast")
+    if isinstance(aux, SplitT):
+        aux_h, ldauxh = aux.hi, aux.ld
+    elif aux is not None:
+        aux_f, ldaux = _rows_view(_chk(aux, "gemm_s aux"), "gemm_s aux")
+    _call("vqa_gemm_bf16s", a.hi.data_ptr(), _ptr(a.lo) if passes == 3 else None, a.ld, int(a_mn),
+          b.hi.data_ptr(), _ptr(b.lo) if passes == 3 else None, b.ld, int(b_mn), _ptr(out), ldc,
+          None if out_split is None else out_split.hi.data_ptr(), None if out_split is None else _ptr(out_split.lo),
+          0 if out_split is None else out_split.ld, M, N, Ka, _ptr(bias), _ptr(rowbcast), ldrb, group,
+          _ptr(aux_f), ldaux, _ptr(aux_h), ldauxh, float(aux_scale), GEMM_RELU if relu else 0, passes, split_k, tile_n, _stream())
+    return out if want_f32 else out_split
+
+
 # ------------------------------------------------------------------------------------------- elementwise
 def dropout(x: torch.Tensor, p: float, seed: int, offset: int) -> torch.Tensor:
     x = _chk(x, "dropout x").contiguous()

@@ -20,21 +20,25 @@ import torch
 from . import kernels as kn
 from ._cabi import PREC_TF32, PREC_TF32X3, PREC_TF32X3_HP
 
-# GEMM precision policy.  "fp32" (default): 3-pass split TF32 everywhere (error ~1e-5 at K~2000, from the tensor
-# core's truncating accumulator) and the chunk-promoted variant (fp32 round-to-nearest promotion every K=128, error
-# ~1e-6 = cuBLAS-fp32 grade) for the graph-learner FORWARD chain, whose output is exponentiated by the neighbourhood
-# softmax (an absolute error e in the adjacency is a relative error e in alpha).  "fp32_strict": promoted everywhere.
-# "tf32": single pass everywhere (does not meet the 1e-3 parity budget; speed reference only).
-_PRECISION_NAMES = {"fp32": (PREC_TF32X3, PREC_TF32X3_HP), "tf32x3": (PREC_TF32X3, PREC_TF32X3_HP),
-                    "fp32_strict": (PREC_TF32X3_HP, PREC_TF32X3_HP), "tf32": (PREC_TF32, PREC_TF32)}
+# GEMM precision policy (fp32 tensors stay fp32 at the module boundary; see csrc/gemm_bf16s.cu, csrc/gemm_tcgen05.cu).
+#   "fp32" (default): every dense product runs on the split-bf16 tcgen05 GEMM with 3 passes (operands carried as
+#            hi/lo bf16 planes, ~2^-17 per product, measured 8e-6 at K=2052), except the graph-learner FORWARD chain,
+#            whose output is exponentiated by the neighbourhood softmax (an absolute error e in the adjacency is a
+#            relative error e in alpha): that chain uses the chunk-promoted 3xTF32 kernel (1.2e-6, cuBLAS-fp32 grade).
+#   "bf16":  one pass on the hi planes (plain bf16 tensor-core GEMM, fp32 accumulate); the graph-learner forward chain
+#            stays fp32-grade so the neighbourhood selection does not drift.  Stated tolerance: logits 2e-2, grads 5e-2.
 _PRECISION_NAME = "fp32"
-_PRECISION, _PRECISION_GL = _PRECISION_NAMES["fp32"]
+_PASSES = 3
 
 
 def set_precision(name: str) -> None:
-    global _PRECISION, _PRECISION_GL, _PRECISION_NAME
-    _PRECISION, _PRECISION_GL = _PRECISION_NAMES[name]
-    _PRECISION_NAME = name
+    global _PRECISION_NAME, _PASSES
+    if name in ("fp32", "tf32x3", "fp32_strict"):
+        _PRECISION_NAME, _PASSES = "fp32", 3
+    elif name == "bf16":
+        _PRECISION_NAME, _PASSES = "bf16", 1
+    else:
+        raise ValueError(f"unknown precision {name!r}: use 'fp32' or 'bf16'")
 
 
 def get_precision() -> str:
@@ -42,18 +46,27 @@ def get_precision() -> str:
 
 
 def _gemm(a, b, **kw):
-    return kn.gemm(a, b, precision=_PRECISION, **kw)
+    """fp32-in/fp32-out product on the 3xTF32 kernel (layer-level API)."""
+    return kn.gemm(a, b, precision=PREC_TF32X3, **kw)
 
 
 def _gemm_gl(a, b, **kw):
     """GEMMs on the path image/question -> adjacency (feeds exp): chunk-promoted accumulation."""
-    return kn.gemm(a, b, precision=_PRECISION_GL, **kw)
+    return kn.gemm(a, b, precision=PREC_TF32X3_HP, **kw)
+
+
+def _split(x):
+    return kn.split(x, with_lo=_PASSES == 3)
+
+
+def _gemm_s(a, b, **kw):
+    return kn.gemm_s(a, b, passes=_PASSES, **kw)
 
 
 def _split_for(out_rows: int, out_cols: int, contraction: int) -> int:
     """Split-K factor for dW = dY^T X products whose output has too few tiles to fill 148 SMs."""
     tiles = ((out_rows + 127) // 128) * ((out_cols + 255) // 256)
-    kblocks = (contraction + 31) // 32
+    kblocks = (contraction + 63) // 64
     s = max(1, min(148 // max(tiles, 1), kblocks // 8))
     return s
 
@@ -114,81 +127,98 @@ class ConditionedGraphFn(torch.autograd.Function):
         W2 = kn.weight_norm_fwd(v2, g2)
         Wo1 = kn.weight_norm_fwd(vo1, go1)
         Wo2 = kn.weight_norm_fwd(vo2, go2)
+        Wc1 = flat_weight(conv_ws[:nk])
+        Wc2 = flat_weight(conv_ws[nk:])
+        W1q = W1[:, F:].contiguous()
+        W1qs, W2s, Wo1s, Wo2s, Wc1s, Wc2s = (_split(w) for w in (W1q, W2, Wo1, Wo2, Wc1, Wc2))
+        Xs = _split(X2)
+        qs = _split(qenc)
 
         # graph learner: [X || q] W1^T = X W1[:, :F]^T + (q W1[:, F:]^T) broadcast over the K nodes  (no concat/repeat)
         qt = _gemm_gl(qenc, W1[:, F:])
         h1 = _gemm_gl(X2, W1[:, :F], bias=b1, rowbcast=qt, group=K, relu=True)
         h2 = _gemm_gl(h1, W2, bias=b2, relu=True)
+        h1s = _split(h1)
         C = h2.shape[1]
         adj, idx, alpha = kn.adjacency_topk_fwd(h2.view(B, K, C), nb)
 
         # graph convolution 1 (project first, then fused Gaussian-weight/gather/aggregate + ReLU + dropout)
-        Wc1 = flat_weight(conv_ws[:nk])
-        Wc2 = flat_weight(conv_ws[nk:])
         gs1 = pack_gauss(mr1, pr1, mt1, pt1)
         gs2 = pack_gauss(mr2, pr2, mt2, pt2)
-        Y1 = _gemm(X2, Wc1)
+        Y1 = _gemm_s(Xs, Wc1s)
         if drop:
             seed, off = next_philox(dev)
             G1 = kn.graphconv_fwd(Y1, idx, alpha, image, gs1, B, K, relu=True, dropout_p=p_drop, seed=seed, offset=off)
         else:
             G1 = kn.graphconv_fwd(Y1, idx, alpha, image, gs1, B, K, relu=True)
+        G1s = _split(G1)
         # graph convolution 2 with max-pool over nodes + question gate fused (sparse_graph_model.py:146-151)
-        Y2 = _gemm(G1, Wc2)
+        Y2 = _gemm_s(G1s, Wc2s)
         pooled, argmax, hq = kn.graphconv_pool_fwd(Y2, idx, image, gs2, qenc, B, K)
 
         # classifier
-        o1 = _gemm(hq, Wo1, bias=bo1, relu=True)
+        hqs = _split(hq)
+        o1 = _gemm_s(hqs, Wo1s, bias=bo1, relu=True)
         if drop:
             seed, off = next_philox(dev)
             o1 = kn.dropout(o1, p_drop, seed, off)
-        logits = _gemm(o1, Wo2, bias=bo2)
+        o1s = _split(o1)
+        logits = _gemm_s(o1s, Wo2s, bias=bo2)
 
         ctx.cfg = dict(B=B, K=K, F=F, H=H, nk=nk, nb=nb, scale=scale)
-        ctx.save_for_backward(image, X2, qenc, v1, g1, v2, g2, vo1, go1, vo2, go2, W1, W2, Wo1, Wo2, Wc1, Wc2, gs1, gs2,
-                              h1, h2, idx, alpha, Y1, G1, Y2, pooled, argmax, hq, o1)
+        ctx.splits = (Xs, qs, h1s, G1s, hqs, o1s, W1qs, W2s, Wo1s, Wo2s, Wc1s, Wc2s)
+        ctx.save_for_backward(image, qenc, v1, g1, v2, g2, vo1, go1, vo2, go2, gs1, gs2, h2, idx, alpha, Y1, Y2, pooled, argmax)
         ctx.mark_non_differentiable(argmax)
         return logits, adj, argmax
 
     @staticmethod
     def backward(ctx, dlogits, dadj, _dargmax):
-        (image, X2, qenc, v1, g1, v2, g2, vo1, go1, vo2, go2, W1, W2, Wo1, Wo2, Wc1, Wc2, gs1, gs2,
-         h1, h2, idx, alpha, Y1, G1, Y2, pooled, argmax, hq, o1) = ctx.saved_tensors
+        (image, qenc, v1, g1, v2, g2, vo1, go1, vo2, go2, gs1, gs2, h2, idx, alpha, Y1, Y2, pooled, argmax) = ctx.saved_tensors
+        Xs, qs, h1s, G1s, hqs, o1s, W1qs, W2s, Wo1s, Wo2s, Wc1s, Wc2s = ctx.splits
         c = ctx.cfg
         B, K, F, H, nk, scale = c["B"], c["K"], c["F"], c["H"], c["nk"], c["scale"]
         M = B * K
+        dev = image.device
+        with_lo = _PASSES == 3
         dlogits = dlogits.contiguous()
 
         # classifier
+        dls = _split(dlogits)
         dbo2 = kn.colsum(dlogits)
-        dWo2 = _gemm(dlogits, o1, a_mn=True, b_mn=True)
-        do1 = _gemm(dlogits, Wo2, b_mn=True, aux=o1, aux_scale=scale)       # ReLU + dropout mask from the stored output
+        dWo2 = _gemm_s(dls, o1s, a_mn=True, b_mn=True)
+        do1s = kn.empty_split(o1s.rows, o1s.cols, dev, with_lo)
+        do1 = _gemm_s(dls, Wo2s, b_mn=True, aux=o1s, aux_scale=scale, out_split=do1s)   # ReLU + dropout mask from the stored output
         dbo1 = kn.colsum(do1)
-        dWo1 = _gemm(do1, hq, a_mn=True, b_mn=True)
-        dhq = _gemm(do1, Wo1, b_mn=True)
+        dWo1 = _gemm_s(do1s, hqs, a_mn=True, b_mn=True)
+        dhq = _gemm_s(do1s, Wo1s, b_mn=True)
         dpooled, dq = kn.gate_bwd(dhq, qenc, pooled)
 
         # graph convolution 2: max-pool scatter by argmax is done inside the kernel
         dY2, _, dgs2 = kn.graphconv_bwd(Y2, idx, None, image, gs2, B, K, dpooled=dpooled, argmax=argmax)
-        dWc2 = _gemm(dY2, G1, a_mn=True, b_mn=True, split_k=_split_for(Wc2.shape[0], Wc2.shape[1], M))
-        dG1 = _gemm(dY2, Wc2, b_mn=True, aux=G1, aux_scale=scale)
+        dY2s = _split(dY2)
+        dWc2 = _gemm_s(dY2s, G1s, a_mn=True, b_mn=True, split_k=_split_for(Wc2s.rows, Wc2s.cols, M))
+        dG1 = _gemm_s(dY2s, Wc2s, b_mn=True, aux=G1s, aux_scale=scale)
         # graph convolution 1
         dY1, dalpha, dgs1 = kn.graphconv_bwd(Y1, idx, alpha, image, gs1, B, K, dO=dG1)
-        dWc1 = _gemm(dY1, X2, a_mn=True, b_mn=True, split_k=_split_for(Wc1.shape[0], Wc1.shape[1], M))
+        dY1s = _split(dY1)
+        dWc1 = _gemm_s(dY1s, Xs, a_mn=True, b_mn=True, split_k=_split_for(Wc1s.rows, Wc1s.cols, M))
 
         # graph learner
         Cdim = h2.shape[1]
         dh2 = kn.adjacency_topk_bwd(h2.view(B, K, Cdim), idx, alpha, dalpha, dadj).view(M, Cdim)
+        dh2s = _split(dh2)
         db2 = kn.colsum(dh2)
-        dW2 = _gemm(dh2, h1, a_mn=True, b_mn=True, split_k=_split_for(Cdim, Cdim, M))
-        dh1 = _gemm(dh2, W2, b_mn=True, aux=h1, aux_scale=1.0)
+        dW2 = _gemm_s(dh2s, h1s, a_mn=True, b_mn=True, split_k=_split_for(Cdim, Cdim, M))
+        dh1s = kn.empty_split(M, Cdim, dev, with_lo)
+        dh1 = _gemm_s(dh2s, W2s, b_mn=True, aux=h1s, aux_scale=1.0, out_split=dh1s)
         db1 = kn.colsum(dh1)
         s1 = _split_for(Cdim, F, M)
-        dW1 = torch.zeros_like(W1) if s1 > 1 else torch.empty_like(W1)
-        _gemm(dh1, X2, a_mn=True, b_mn=True, out=dW1[:, :F], split_k=s1)
+        dW1 = torch.zeros((Cdim, F + H), device=dev, dtype=torch.float32) if s1 > 1 else torch.empty((Cdim, F + H), device=dev, dtype=torch.float32)
+        _gemm_s(dh1s, Xs, a_mn=True, b_mn=True, out=dW1[:, :F], split_k=s1)
         dqt = kn.segment_sum(dh1, K)
-        _gemm(dqt, qenc, a_mn=True, b_mn=True, out=dW1[:, F:])
-        dq_gl = _gemm(dqt, W1[:, F:], b_mn=True)
+        dqts = _split(dqt)
+        _gemm_s(dqts, qs, a_mn=True, b_mn=True, out=dW1[:, F:])
+        dq_gl = _gemm_s(dqts, W1qs, b_mn=True)
         dq = dq + dq_gl
 
         dv1, dg1 = kn.weight_norm_bwd(dW1, v1, g1)
@@ -196,8 +226,8 @@ class ConditionedGraphFn(torch.autograd.Function):
         dvo1, dgo1 = kn.weight_norm_bwd(dWo1, vo1, go1)
         dvo2, dgo2 = kn.weight_norm_bwd(dWo2, vo2, go2)
 
-        d1 = Wc1.shape[0] // nk
-        d2 = Wc2.shape[0] // nk
+        d1 = Wc1s.rows // nk
+        d2 = Wc2s.rows // nk
         conv_grads = [dWc1[i * d1:(i + 1) * d1] for i in range(nk)] + [dWc2[i * d2:(i + 1) * d2] for i in range(nk)]
         gsh = (nk, 1)
         return (None, None, dq, dv1, dg1, db1, dv2, dg2, db2,
