@@ -35,8 +35,8 @@ def parse():
     ap.add_argument("--workload", default="vqa2_b512")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
                     help="fp32: split-bf16 3-pass tcgen05 GEMMs (fp32-grade, the parity mode); bf16: 1-pass bf16 tensor-core GEMMs")
-    ap.add_argument("--gru-tf32", action="store_true", help="let cuDNN run the (unchanged) GRU in TF32, torch's default; off = fp32 like the parity tests")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--cpu-sample", type=int, default=64, help="questions per CPU step (bounded sample of the workload)")
     return ap.parse_args()
 
@@ -101,35 +101,47 @@ def run_reference(args, workload):
 def config_dict(w, args, world):
     return {"workload": f"{w.name}: VQA2 conditioned-graph train step, per-GPU batch {w.batch}, K={w.n_obj} boxes x {w.feat_dim}-d, "
                         f"<= {w.max_qlen}-token questions, top-k={w.neighbourhood}, {w.n_kernels} Gaussian kernels, {w.out_dim} answers, dropout {w.dropout}",
-            "global_batch": w.batch * world, "step": "zero_grad+forward+MultiLabelSoftMarginLoss+backward+allreduce+Adam",
-            "parallelism": f"dp{world}", "gru": "cuDNN tf32" if args.gru_tf32 else "cuDNN fp32", "gemm_precision": "split-bf16 x3 passes (fp32-grade, rel err ~1e-5) + chunk-promoted 3xTF32 graph-learner forward" if args.precision == "fp32" else "bf16 x1 pass (graph-learner forward fp32-grade)",
+            "global_batch": w.batch * world, "step": "zero_grad+forward+MultiLabelSoftMarginLoss+backward+allreduce+Adam, " + ("eager launches" if args.no_graph else "one CUDA-graph replay per step (vqa_b200.engine.TrainStep)"),
+            "parallelism": f"dp{world}", "gru": "padded masked recurrence on split-bf16 x3 tcgen05 GEMMs (fp32-grade)", "gemm_precision": "split-bf16 x3 passes (fp32-grade, rel err ~1e-5) + chunk-promoted 3xTF32 graph-learner forward" if args.precision == "fp32" else "bf16 x1 pass (graph-learner forward fp32-grade)",
             "l2_policy": "inputs larger than L2 (image batch 151 MB > 126 MB), 3 rotating batches"}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region through NVML (the library nvidia-smi itself
+    uses; no subprocess, so sampling does not perturb the launching thread)."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.err = index, [], set(), False, None, None
 
     def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if "Active" in v and "Not" not in v:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self.stop_flag:
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for n, bit in self.REASONS.items():
+                    if mask & bit:
                         self.reasons.add(n)
-            except Exception:
-                pass
-            time.sleep(0.1)
+                time.sleep(0.02)
+        except Exception as e:   # keep the bench alive; the JSON line records that sampling failed
+            self.err = repr(e)
 
     def summary(self):
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        out = {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s),
+               "source": "nvml"}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -137,6 +149,7 @@ def run_b200(args, workload):
     import torch.distributed as dist
     from vqa_b200 import kernels as kn, ops
     from vqa_b200.ddp import GradReducer, broadcast_parameters
+    from vqa_b200.engine import TrainStep
     from vqa_b200.synthetic import make_batch, make_wemb
     import sparse_graph_model as M
 
@@ -150,35 +163,32 @@ def run_b200(args, workload):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ops.set_precision(args.precision)
-    torch.backends.cudnn.allow_tf32 = bool(args.gru_tf32)
     w = workload
 
     torch.manual_seed(1000)
     model = M.Model(pretrained_wemb=make_wemb(w), **w.model_kwargs()).to(dev)
+    model.max_question_len = w.max_qlen
     broadcast_parameters(model)
     model.train()
     criterion = torch.nn.MultiLabelSoftMarginLoss()
     reducer = GradReducer(model.parameters())
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=not args.no_graph)
     torch.manual_seed(1234 + rank)       # rank-offset dropout streams
+    step = TrainStep(model, opt, criterion, reducer=reducer, use_graph=not args.no_graph, seed=1234 + rank)
 
     # host batches (pinned) and device-resident copies; rank-offset seeds = different data per rank
     NB = 3
+    keys = ("question", "image", "K", "qlen", "target")
     host = []
     for i in range(NB):
         b = make_batch(w, seed=1000 + 17 * rank + i)
-        host.append({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()})
-    resident = [{k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in b.items()} for b in host]
-    h2d_bytes = sum(v.numel() * v.element_size() for k, v in host[0].items() if torch.is_tensor(v))
+        b["qlen"] = torch.tensor([int(x) for x in b["qlen"]], dtype=torch.int32)
+        host.append({k: b[k].pin_memory() for k in keys})
+    resident = [{k: v.to(dev, non_blocking=True) for k, v in b.items()} for b in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
 
-    def step(b):
-        reducer.zero_grad()
-        logits, _, _ = model(b["question"], b["image"], b["K"], b["qlen"])
-        loss = criterion(logits, b["target"])
-        loss.backward()
-        reducer.finish()
-        opt.step()
-        return loss
+    def run(b):
+        return step(b["question"], b["image"], b["K"], b["qlen"], b["target"])
 
     def barrier():
         if world > 1:
@@ -193,57 +203,40 @@ def run_b200(args, workload):
         return ms
 
     # ---- device-resident throughput ------------------------------------------------------------
-    for i in range(args.warmup):
-        step(resident[i % NB])
-    GC, ADJ, GEMM = "vqa_graphconv_fwd_f32", "vqa_adjacency_topk_fwd_f32", "vqa_gemm_f32"
-    kn.enable_timing(GC, ADJ, "vqa_graphconv_bwd_f32", "vqa_graphconv_pool_fwd_f32", "vqa_adjacency_topk_bwd_f32")
+    for i in range(max(args.warmup, 3)):
+        run(resident[i % NB])
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
-    launches0 = kn.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        loss = step(resident[i % NB])
+        loss = run(resident[i % NB])
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = (kn.LAUNCHES - launches0) // max(args.steps, 1)
+    launches = step.launches_per_step
     sampler.stop_flag = True
-    timers = {k: [a.elapsed_time(b) for a, b in v] for k, v in kn.TIMERS.items()}
-    kn.enable_timing()
     ms_step = ms_total / args.steps
     value = w.batch * world / (ms_step * 1e-3)
+    final_loss = float(loss.detach())
 
     # ---- end to end through the public API: pinned host -> device every step, loss read back ---------------
-    copy_stream = torch.cuda.Stream()
-    slots = [dict(), dict()]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
-
-    def prefetch(i, slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])
-            hb = host[i % NB]
-            slots[slot] = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in hb.items()}
-            ready[slot].record(copy_stream)
-
     def e2e_loop(n):
-        for s in (0, 1):
-            consumed[s].record()
-        prefetch(0, 0)
         last = None
         for i in range(n):
+            hb = host[i % NB]
+            if i == 0:
+                step.prefetch(hb["question"], hb["image"], hb["K"], hb["qlen"], hb["target"])
+            loss = run(hb)                                  # waits for this batch's H2D, replays the step
             if i + 1 < n:
-                prefetch(i + 1, (i + 1) % 2)          # next step's H2D overlaps this step's compute
-            torch.cuda.current_stream().wait_event(ready[i % 2])
-            loss = step(slots[i % 2])
-            consumed[i % 2].record()
-            last = loss.item()                         # D2H read of the step's result, every step
+                nb_ = host[(i + 1) % NB]                    # next step's H2D overlaps this step's compute
+                step.prefetch(nb_["question"], nb_["image"], nb_["K"], nb_["qlen"], nb_["target"])
+            last = loss.item()                             # D2H read of the step's result, every step
         return last
 
-    e2e_loop(max(2, args.warmup // 2))
+    e2e_loop(max(3, args.warmup))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -252,6 +245,22 @@ def run_b200(args, workload):
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     e2e_value = w.batch * world / (ms_e2e * 1e-3)
+
+    # ---- per-kernel CUDA-event times: an eager pass over the same step (individual launches cannot be bracketed inside a
+    # graph replay), same inputs, same stream ------------------------------------------------------------------
+    GC, ADJ = "vqa_graphconv_fwd_f32", "vqa_adjacency_topk_fwd_f32"
+    timers = {}
+    if rank == 0:
+        eager = TrainStep(model, opt, criterion, reducer=reducer, use_graph=False, seed=99)
+        for i in range(3):
+            eager(*(resident[i % NB][k] for k in keys))
+        kn.enable_timing(GC, ADJ, "vqa_graphconv_bwd_f32", "vqa_graphconv_pool_fwd_f32", "vqa_adjacency_topk_bwd_f32", "vqa_gemm_bf16s")
+        for i in range(6):
+            eager(*(resident[i % NB][k] for k in keys))
+        torch.cuda.synchronize()
+        timers = {k: [a.elapsed_time(b) for a, b in v] for k, v in kn.TIMERS.items()}
+        kn.enable_timing()
+    barrier()
 
     if rank != 0:
         if world > 1:
@@ -305,7 +314,7 @@ def run_b200(args, workload):
                 "ms_per_step": round(ms_e2e, 4), "last_loss": last_loss},
         "gpu_launches": int(launches),
         "roofline": roof, "roofline_other_kernels": extra, "cpu_baseline": cpu,
-        "clocks": sampler.summary(), "final_loss": float(loss.detach()),
+        "clocks": sampler.summary(), "final_loss": final_loss,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

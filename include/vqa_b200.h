@@ -20,7 +20,7 @@ extern "C" {
 
 typedef struct CUstream_st* vqa_stream_t; /* cudaStream_t */
 
-#define VQA_ABI_VERSION 1
+#define VQA_ABI_VERSION 2
 
 /* GEMM precision modes */
 #define VQA_PREC_TF32X3 0 /* 3-pass split TF32 on tcgen05: fp32-grade results (parity mode)      */
@@ -30,6 +30,7 @@ typedef struct CUstream_st* vqa_stream_t; /* cudaStream_t */
 /* GEMM epilogue flags */
 #define VQA_GEMM_RELU 1
 #define VQA_GEMM_ATOMIC_ADD 4 /* set internally for split-K: C must be zero-filled by the caller */
+#define VQA_GEMM_ACCUMULATE 8 /* C += A.B^T with fp32 atomics into a caller-initialised C (plain epilogue, any split_k) */
 
 /* graph-conv flags */
 #define VQA_GC_RELU 1
@@ -67,9 +68,11 @@ int vqa_gemm_bf16s(const void* A_hi, const void* A_lo, long long lda, int a_mn_m
                    float aux_scale, int flags, int passes, int split_k, int tile_n, vqa_stream_t stream);
 
 /* y = x * keep / (1-p), keep ~ Bernoulli(1-p) from Philox4x32-10(seed; counter = (element/4, offset)).
- * Replaces nn.Dropout on the image tensor and the classifier hidden (sparse_graph_model.py:111,156). */
+ * step_ptr (optional, device): *step_ptr * 16 is added to offset at run time, so a CUDA-graph replay that bumps the
+ * counter draws fresh masks.  Replaces nn.Dropout on the image tensor and the classifier hidden
+ * (sparse_graph_model.py:111,156). */
 int vqa_dropout_f32(const float* x, float* y, long long n, float p, unsigned long long seed,
-                    unsigned long long offset, vqa_stream_t stream);
+                    unsigned long long offset, const unsigned long long* step_ptr, vqa_stream_t stream);
 
 /* Old-style weight norm (dim=0): w[r,:] = v[r,:] * (g[r] / ||v[r,:]||).  torch._weight_norm at layers.py:171-172,
  * sparse_graph_model.py:88-89.  bwd: given dw returns dv, dg. */
@@ -105,7 +108,7 @@ int vqa_adjacency_topk_bwd_f32(const float* h, const int* idx, const float* alph
 int vqa_graphconv_fwd_f32(const float* Y, long long ldy, const int* idx, const float* alpha, const float* boxes,
                           long long ldbox, const float* gauss, float* out, long long ldo, int B, int K, int nb,
                           int nk, int out_dim, int flags, float dropout_p, unsigned long long seed,
-                          unsigned long long offset, vqa_stream_t stream);
+                          unsigned long long offset, const unsigned long long* step_ptr, vqa_stream_t stream);
 /* Second layer with the pooling tail fused: relu, max over the K nodes (first index on ties), gate with relu(q):
  * pooled (B,out), argmax (B,out) int64, hq = relu(q) * pooled.  sparse_graph_model.py:146-151. */
 int vqa_graphconv_pool_fwd_f32(const float* Y, long long ldy, const int* idx, const float* boxes, long long ldbox,
@@ -130,6 +133,28 @@ int vqa_graphconv_edge_bwd_f32(const float* P, const int* idx, const float* alph
  * get_gaussian_weights, layers.py:100-125 (layer-level API). */
 int vqa_gaussian_weights_f32(const float* pseudo, const float* gauss, float* w, long long n, int nk,
                              vqa_stream_t stream);
+
+/* ---- question encoder (sparse_graph_model.py:117-121: nn.Embedding + pack_padded_sequence + nn.GRU, final state) ----
+ * The recurrence runs over padded time-major steps; a sequence past its length keeps its state, which equals the
+ * packed-sequence result.  The matrix products (x W_ih^T for all steps, h W_hh^T per step, and the backward
+ * products) are vqa_gemm_bf16s calls; these entry points are the gather/scatter and the pointwise cell. */
+/* E[(t*B + b), :] = W[question[b,t], :] written as split planes (rows time-major), t < T. */
+int vqa_embed_gather_split(const long long* question, long long ldq, const float* W, long long vocab, int emb, void* hi,
+                           void* lo, long long ldp, int B, int T, vqa_stream_t stream);
+/* dW[question[b,t], :] += dE[(t*B + b), :] for t < len[b]  (fp32 atomics; dW pre-zeroed / accumulated by the caller). */
+int vqa_embed_scatter_add_f32(const float* dE, long long ldd, const long long* question, long long ldq, const int* len,
+                              float* dW, long long vocab, int emb, int B, int T, vqa_stream_t stream);
+/* One GRU step, torch gate order (r,z,n).  gi = x_t W_ih^T + b_ih (B,3H); gh = h_{t-1} W_hh^T (B,3H) WITHOUT bias
+ * (b_hh is added by this kernel) or NULL at t = 0; h_t = t < len[b] ? cell : h_{t-1}, written as fp32 and split planes; gates (B,4H)
+ * = r | z | n | gh_n saved for backward. */
+int vqa_gru_cell_fwd_f32(const float* gi, long long ldgi, const float* gh, const float* b_hh, const float* h_prev,
+                         const int* len, int t, float* h_out, void* h_hi, void* h_lo, long long ldp, float* gates, int B,
+                         int H, vqa_stream_t stream);
+/* Backward of one step: dh (B,H) -> dgi, dgh (B,3H; fp32 and split planes, ld = ldp) and dh_part (B,H), the direct
+ * part of dL/dh_{t-1}; the caller adds dgh W_hh. */
+int vqa_gru_cell_bwd_f32(const float* dh, const float* gates, const float* h_prev, const int* len, int t, float* dgi,
+                         float* dgh, void* dgi_hi, void* dgi_lo, void* dgh_hi, void* dgh_lo, long long ldp, float* dh_part,
+                         int B, int H, vqa_stream_t stream);
 
 /* Gate/pool backward: dpooled = pooled > 0 ? dhq * relu(q) : 0 ;  dq = q > 0 ? dhq * pooled : 0.
  * sparse_graph_model.py:150-151 (autograd of max + relu*mul). */

@@ -37,7 +37,7 @@ def test_argument_errors_are_reported_without_a_gpu():
         _cabi.call("vqa_gemm_f32", None, 4, 0, None, 4, 0, None, 4, 1, 1, 1, None, None, 0, 1, None, 0, 1.0, 0, 0, 1, 0, None)
     assert "null operand" in str(e.value)
     with pytest.raises(_cabi.VqaKernelError):
-        _cabi.call("vqa_dropout_f32", None, None, 10, 0.5, 1, 1, None)
+        _cabi.call("vqa_dropout_f32", None, None, 10, 0.5, 1, 1, None, None)
 
 
 def test_no_cpu_fallback():

@@ -175,6 +175,48 @@ def test_gemm_split_bf16_split_k(kn, split):
     assert rel_err(out.cpu(), a.double().t() @ b.double()) < 3e-5
 
 
+def test_gemm_split_bf16_accumulate_and_auto_tile(kn):
+    g = torch.Generator().manual_seed(11)
+    M, N, Kc = 512, 1024, 3072            # the GRU backward product: few tiles -> BN = 64 tile, split-K, accumulate into C
+    a = torch.randn(M, Kc, generator=g)
+    b = torch.randn(Kc, N, generator=g)
+    c0 = torch.randn(M, N, generator=g)
+    out = c0.to(DEV).clone()
+    kn.gemm_s(kn.split(a.to(DEV)), kn.split(b.to(DEV)), b_mn=True, out=out, accumulate=True, split_k=4)
+    assert rel_err(out.cpu(), c0.double() + a.double() @ b.double()) < 3e-5
+    out1 = c0.to(DEV).clone()
+    kn.gemm_s(kn.split(a.to(DEV)), kn.split(b.to(DEV)), b_mn=True, out=out1, accumulate=True)
+    assert rel_err(out1.cpu(), c0.double() + a.double() @ b.double()) < 3e-5
+
+
+# --------------------------------------------------------------------------------------------- question encoder
+@pytest.mark.parametrize("B,T,H,V,E", [(9, 7, 64, 50, 300), (33, 14, 128, 200, 300), (4, 3, 32, 11, 24)])
+def test_question_encoder_matches_packed_gru(B, T, H, V, E):
+    """ops.QuestionEncoderFn (padded, masked recurrence on our kernels) vs nn.Embedding + pack_padded_sequence + nn.GRU
+    in fp64 on the CPU (the reference's construction, sparse_graph_model.py:117-121), forward and every gradient."""
+    from torch.nn.utils.rnn import pack_padded_sequence
+    from vqa_b200 import ops
+    g = torch.Generator().manual_seed(B * 100 + T)
+    lens = torch.randint(1, T + 1, (B,), generator=g)
+    lens[0] = T
+    q = torch.zeros(B, T + 5, dtype=torch.int64)
+    for b in range(B):
+        q[b, :lens[b]] = torch.randint(1, V, (int(lens[b]),), generator=g)
+    emb = torch.nn.Embedding(V, E).double()
+    gru = torch.nn.GRU(E, H).double()
+    R = torch.randn(B, H, generator=g).double()
+    packed = pack_padded_sequence(emb(q), lens, batch_first=True, enforce_sorted=False)
+    _, hid = gru(packed)
+    (hid[0] * R).sum().backward()
+    params = [emb.weight, gru.weight_ih_l0, gru.weight_hh_l0, gru.bias_ih_l0, gru.bias_hh_l0]
+    dev_params = [p.detach().float().to(DEV).requires_grad_(True) for p in params]
+    out = ops.QuestionEncoderFn.apply(q.to(DEV), lens.to(torch.int32).to(DEV), int(lens.max()), *dev_params)
+    (out * R.float().to(DEV)).sum().backward()
+    assert rel_err(out.detach().cpu(), hid[0].detach()) < 2e-5
+    for name, p, d in zip(["wembed", "w_ih", "w_hh", "b_ih", "b_hh"], params, dev_params):
+        assert rel_err(d.grad.cpu(), p.grad) < 1e-4, name
+
+
 # --------------------------------------------------------------------------------------------- small kernels
 def test_dropout_statistics_and_determinism(kn):
     x = torch.ones(1 << 20, device=DEV)

@@ -13,8 +13,9 @@ namespace vqa {
 // ------------------------------------------------------------------------------------------ dropout
 __global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
                                                      float p, float scale, unsigned long long seed,
-                                                     unsigned long long offset, int vec) {
+                                                     unsigned long long offset, const unsigned long long* __restrict__ step_ptr, int vec) {
   const Philox rng(seed);
+  if (step_ptr) offset += *step_ptr * 16ull;     // device-side step counter: CUDA-graph replays draw fresh masks
   const long long ngroups = (n + 3) >> 2;
   for (long long gidx = blockIdx.x * (long long)blockDim.x + threadIdx.x; gidx < ngroups;
        gidx += (long long)gridDim.x * blockDim.x) {
@@ -110,13 +111,13 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__
 using namespace vqa;
 
 extern "C" int vqa_dropout_f32(const float* x, float* y, long long n, float p, unsigned long long seed,
-                               unsigned long long offset, cudaStream_t stream) {
+                               unsigned long long offset, const unsigned long long* step_ptr, cudaStream_t stream) {
   VQA_CHECK_ARG(x && y && n >= 0, "vqa_dropout_f32: bad arguments");
   VQA_CHECK_ARG(p >= 0.f && p < 1.f, "vqa_dropout_f32: p must be in [0,1), got %f", p);
   if (n == 0) return VQA_OK;
   const long long groups = (n + 3) / 4;
   const int blocks = (int)min((long long)kNumSMs * 16, (groups + 255) / 256);
-  dropout_kernel<<<blocks, 256, 0, stream>>>(x, y, n, p, 1.f / (1.f - p), seed, offset, aligned16(x) && aligned16(y));
+  dropout_kernel<<<blocks, 256, 0, stream>>>(x, y, n, p, 1.f / (1.f - p), seed, offset, step_ptr, aligned16(x) && aligned16(y));
   VQA_LAUNCH_CHECK("dropout_kernel");
   return VQA_OK;
 }

@@ -54,7 +54,8 @@ struct Cfg {
   static constexpr int PLANE = A_TILE + B_TILE;               // [A | B] of one plane
   static constexpr int STAGE = PLANE * PLANES;
   static constexpr int S_ = SMEM_BUDGET / STAGE;
-  static constexpr int S = S_ > 8 ? 8 : S_;
+  // BN = 64 is the small-problem tile (few CTAs, latency-bound): 2 x 48 KB stages so that 2 CTAs are resident per SM
+  static constexpr int S = BN == 64 ? (PLANES == 2 ? 2 : 4) : (S_ > 8 ? 8 : S_);
   static constexpr int SMEM = S * STAGE + 1024 + 256;
 };
 
@@ -155,6 +156,13 @@ struct Epi {
             *reinterpret_cast<uint4*>(lrow + col) = make_uint4(pack_bf16(v[0] - h[0], v[1] - h[1]), pack_bf16(v[2] - h[2], v[3] - h[3]),
                                                                pack_bf16(v[4] - h[4], v[5] - h[5]), pack_bf16(v[6] - h[6], v[7] - h[7]));
         }
+      }
+    } else if (atomic && crow && !hrow && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.N & 3) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {           // split-K / accumulate: 16-byte vector reductions (red.global.add.v4.f32)
+        const int col = cb + j;
+        if (col >= p.N) break;
+        atomicAdd(reinterpret_cast<float4*>(crow + col), make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]));
       }
     } else {
 #pragma unroll 4
@@ -406,12 +414,18 @@ extern "C" int vqa_gemm_bf16s(const void* A_hi, const void* A_lo, long long lda,
   if (splits > num_kb) splits = num_kb;
   int per = (num_kb + splits - 1) / splits;
   splits = (num_kb + per - 1) / per;   // no empty split
-  if (splits > 1) {
-    VQA_CHECK_ARG(C && !C_hi && !bias && !rowbcast && !aux && !aux_hi && !(flags & VQA_GEMM_RELU), "%s: split-K supports the plain fp32 epilogue only", who);
-    flags |= VQA_GEMM_ATOMIC_ADD;      // caller zero-fills C
+  if (splits > 1 || (flags & VQA_GEMM_ACCUMULATE)) {
+    VQA_CHECK_ARG(C && !C_hi && !bias && !rowbcast && !aux && !aux_hi && !(flags & VQA_GEMM_RELU), "%s: split-K / accumulate support the plain fp32 epilogue only", who);
+    flags |= VQA_GEMM_ATOMIC_ADD;      // caller zero-fills (split-K) or pre-loads (accumulate) C
   }
   int bn = tile_n;
-  if (bn == 0) bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  if (bn == 0) {                       // widest tile that still gives the 148 SMs enough CTAs
+    const long long mt = (M + sb::BM - 1) / sb::BM;
+    auto ctas = [&](int w) { return mt * ((N + w - 1) / w) * splits; };
+    bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+    if (bn == 256 && ctas(256) < 120) bn = 128;
+    if (bn == 128 && ctas(128) < 120) bn = 64;
+  }
   VQA_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "%s: tile_n must be 64, 128 or 256", who);
 
   sb::Maps tm;

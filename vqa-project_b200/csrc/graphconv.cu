@@ -37,6 +37,7 @@ struct GcParams {
   int K, nb, nbp, nk, out_dim, D, TW, tstride, tiles_per_cta, ntiles, nkc, nstage, flags;   // tstride: floats per staged tile
   float drop_p, drop_scale;
   unsigned long long seed, offset;
+  const unsigned long long* step_ptr;
 };
 
 struct GcSmem {   // byte offsets into dynamic smem (host-computed, identical on both sides)
@@ -177,6 +178,7 @@ struct DenseParams {
   float drop_p, drop_scale;
   unsigned int drop_thresh16;                // keep iff 16-bit uniform >= thresh
   unsigned long long seed, offset;
+  const unsigned long long* step_ptr;        // optional device-side step counter added to offset (CUDA-graph replays)
 };
 
 template <int KT, int VEC, int MODE>
@@ -193,6 +195,7 @@ graphconv_dense_kernel(const __grid_constant__ CUtensorMap tmIn, const DensePara
   const int b = blockIdx.y, K = p.K, nb = p.nb, nk = p.nk;
   const int t0 = blockIdx.x * p.tiles_per_cta;
   const int nt = min(p.tiles_per_cta, p.ntiles - t0);
+  const unsigned long long rng_offset = p.offset + (p.step_ptr ? *p.step_ptr * 16ull : 0ull);
   const int k_lo = (t0 * TWD) / p.D;
   const int nkc = ((t0 + nt) * TWD - 1) / p.D - k_lo + 1;
   // Input tiles: every warp owns one shared-memory landing slot.  Lane 0 issues the TMA load of the warp's NEXT tile as
@@ -363,7 +366,7 @@ graphconv_dense_kernel(const __grid_constant__ CUtensorMap tmIn, const DensePara
             // 16 random bits per element from one 32-bit counter hash per (row, VEC-column group)
 #pragma unroll
             for (int v0 = 0; v0 < VEC; v0 += 2) {
-              const uint32_t r = hash32((unsigned long long)(((long long)b * K + i) * (p.out_dim / 2) + (colg + v0) / 2), p.seed, p.offset);
+              const uint32_t r = hash32((unsigned long long)(((long long)b * K + i) * (p.out_dim / 2) + (colg + v0) / 2), p.seed, rng_offset);
               acc[v0] = (r & 0xFFFFu) >= p.drop_thresh16 ? acc[v0] * p.drop_scale : 0.f;
               if (v0 + 1 < VEC) acc[v0 + 1 < VEC ? v0 + 1 : v0] = (r >> 16) >= p.drop_thresh16 ? acc[v0 + 1 < VEC ? v0 + 1 : v0] * p.drop_scale : 0.f;
             }
@@ -526,7 +529,7 @@ graphconv_fwd_kernel(const __grid_constant__ CUtensorMap tmY, const GcParams p, 
           const long long row = (long long)b * K + i;
           if (p.drop_p > 0.f) {
             const Philox rng(p.seed);
-            const uint4 r = rng((unsigned long long)((row * p.out_dim + colg) >> 2), p.offset);
+            const uint4 r = rng((unsigned long long)((row * p.out_dim + colg) >> 2), p.offset + (p.step_ptr ? *p.step_ptr * 16ull : 0ull));
             acc.x = u32_to_unit(r.x) >= p.drop_p ? acc.x * p.drop_scale : 0.f;
             acc.y = u32_to_unit(r.y) >= p.drop_p ? acc.y * p.drop_scale : 0.f;
             acc.z = u32_to_unit(r.z) >= p.drop_p ? acc.z * p.drop_scale : 0.f;
@@ -864,7 +867,7 @@ static int gc_plan(GcPlan* pl, int B, int K, int nb, int nk, int out_dim, bool b
 static int gc_fwd_common(bool pool, const float* Y, long long ldy, const int* idx, const float* alpha, const float* boxes,
                          long long ldbox, const float* gauss, float* out, long long ldo, const float* q, float* pooled,
                          long long* argmax, float* hq, int B, int K, int nb, int nk, int out_dim, int flags, float drop_p,
-                         unsigned long long seed, unsigned long long offset, cudaStream_t stream) {
+                         unsigned long long seed, unsigned long long offset, const unsigned long long* step_ptr, cudaStream_t stream) {
   const char* who = pool ? "vqa_graphconv_pool_fwd_f32" : "vqa_graphconv_fwd_f32";
   VQA_CHECK_ARG(Y && idx && boxes && gauss, "%s: null pointer", who);
   VQA_CHECK_ARG(aligned16(Y) && (ldy & 3) == 0 && ldy >= out_dim, "%s: Y must be 16-byte aligned with ld %% 4 == 0", who);
@@ -875,7 +878,7 @@ static int gc_fwd_common(bool pool, const float* Y, long long ldy, const int* id
     dp.out = out; dp.ldo = ldo; dp.q = q; dp.pooled = pooled; dp.argmax = argmax; dp.hq = hq;
     dp.K = K; dp.nb = nb; dp.nk = nk; dp.out_dim = out_dim; dp.flags = flags;
     dp.drop_p = drop_p; dp.drop_scale = 1.f / (1.f - drop_p); dp.drop_thresh16 = (unsigned)(drop_p * 65536.f + 0.5f);
-    dp.seed = seed; dp.offset = offset;
+    dp.seed = seed; dp.offset = offset; dp.step_ptr = step_ptr;
     if (pool) dp.ldo = 2;
     const int rc = pool ? dense_launch<DM_FWD_POOL>(dp, B, stream) : dense_launch<DM_FWD>(dp, B, stream);
     if (rc <= 0) return rc;
@@ -889,7 +892,7 @@ static int gc_fwd_common(bool pool, const float* Y, long long ldy, const int* id
   p.out = out; p.ldo = ldo; p.q = q; p.pooled = pooled; p.argmax = argmax; p.hq = hq;
   p.K = K; p.nb = nb; p.nbp = pl.nbp; p.nk = nk; p.out_dim = out_dim; p.D = pl.D; p.TW = pl.TW; p.tstride = pl.tstride;
   p.tiles_per_cta = pl.tiles_per_cta; p.ntiles = pl.ntiles; p.nkc = pl.nkc; p.nstage = pl.nstage; p.flags = flags;
-  p.drop_p = drop_p; p.drop_scale = 1.f / (1.f - drop_p); p.seed = seed; p.offset = offset;
+  p.drop_p = drop_p; p.drop_scale = 1.f / (1.f - drop_p); p.seed = seed; p.offset = offset; p.step_ptr = step_ptr;
   dim3 grid(pl.nslab, B);
   if (pool) {
     VQA_CUDA(cudaFuncSetAttribute(graphconv_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem));
@@ -908,10 +911,10 @@ using namespace vqa;
 extern "C" int vqa_graphconv_fwd_f32(const float* Y, long long ldy, const int* idx, const float* alpha, const float* boxes,
                                      long long ldbox, const float* gauss, float* out, long long ldo, int B, int K, int nb,
                                      int nk, int out_dim, int flags, float dropout_p, unsigned long long seed,
-                                     unsigned long long offset, cudaStream_t stream) {
+                                     unsigned long long offset, const unsigned long long* step_ptr, cudaStream_t stream) {
   VQA_CHECK_ARG(out && aligned16(out) && (ldo & 3) == 0 && ldo >= out_dim, "vqa_graphconv_fwd_f32: out must be 16-byte aligned with ld %% 4 == 0");
   return gc_fwd_common(false, Y, ldy, idx, alpha, boxes, ldbox, gauss, out, ldo, nullptr, nullptr, nullptr, nullptr, B, K,
-                       nb, nk, out_dim, flags, dropout_p, seed, offset, stream);
+                       nb, nk, out_dim, flags, dropout_p, seed, offset, step_ptr, stream);
 }
 
 extern "C" int vqa_graphconv_pool_fwd_f32(const float* Y, long long ldy, const int* idx, const float* boxes, long long ldbox,
@@ -919,7 +922,7 @@ extern "C" int vqa_graphconv_pool_fwd_f32(const float* Y, long long ldy, const i
                                           int B, int K, int nb, int nk, int out_dim, cudaStream_t stream) {
   VQA_CHECK_ARG(q && pooled && argmax && hq, "vqa_graphconv_pool_fwd_f32: null pointer");
   return gc_fwd_common(true, Y, ldy, idx, nullptr, boxes, ldbox, gauss, nullptr, 0, q, pooled, argmax, hq, B, K, nb, nk,
-                       out_dim, VQA_GC_RELU, 0.f, 0, 0, stream);
+                       out_dim, VQA_GC_RELU, 0.f, 0, 0, nullptr, stream);
 }
 
 extern "C" int vqa_graphconv_bwd_f32(const float* dO, long long lddo, const float* dpooled, const long long* argmax,

@@ -5,12 +5,11 @@ Keeps the reference's constructor signature, attribute names, ``state_dict`` key
 (reference sparse_graph_model.py:28-159), so ``run.py`` / ``run_imageclef.py`` / ``run_mimic.py`` /
 ``plot.py`` import it unchanged when ``vqa-project_b200/`` precedes the reference on ``sys.path``.
 
-What differs is underneath: the embedding + GRU stay torch modules (cuDNN), everything after the question
-encoding is ONE autograd node (``vqa_b200.ops.ConditionedGraphFn``) made of hand-written sm_100a kernels.
+What differs is underneath: the question encoder (embedding + GRU) is one autograd node (``ops.QuestionEncoderFn``) and everything
+after it is ONE more (``vqa_b200.ops.ConditionedGraphFn``) made of hand-written sm_100a kernels.
 """
 import torch
 import torch.nn as nn
-from torch.nn.utils.rnn import pack_padded_sequence
 
 from layers import NeighbourhoodGraphConvolution as GraphConvolution
 from layers import GraphLearner, WeightNormLinear
@@ -49,10 +48,22 @@ class Model(nn.Module):
         self.out_2 = WeightNormLinear(out_dim, out_dim)
 
     def encode_question(self, question, qlen):
-        emb = self.wembed(question)
-        packed = pack_padded_sequence(emb, qlen, batch_first=True, enforce_sorted=False)
-        _, hid = self.q_gru(packed)
-        return hid[0]
+        """Embedding + GRU final state (reference :117-121) through ``ops.QuestionEncoderFn``.  ``qlen`` is the
+        reference's list of lengths (ints or 0-d tensors), or -- for CUDA-graph capture, where nothing may depend on
+        host data -- a CUDA int32 tensor (B,), in which case the number of steps is ``self.max_question_len`` (set it
+        to the dataset's maximum, 14 for VQA2) or the question width."""
+        if torch.is_tensor(qlen) and qlen.is_cuda:
+            qlen_dev = qlen.to(torch.int32)
+            steps = int(getattr(self, "max_question_len", 0) or question.shape[1])
+        else:
+            lens = [int(x) for x in qlen]
+            steps = max(lens)
+            if min(lens) < 1:
+                raise ValueError("question lengths must be >= 1 (pack_padded_sequence rejects empty sequences)")
+            qlen_dev = torch.tensor(lens, dtype=torch.int32).to(question.device, non_blocking=True)
+        g = self.q_gru
+        return ops.QuestionEncoderFn.apply(question, qlen_dev, steps, self.wembed.weight, g.weight_ih_l0, g.weight_hh_l0,
+                                           g.bias_ih_l0, g.bias_hh_l0)
 
     def forward(self, question, image, K, qlen):
         """question (B,T) int64, image (B,K,F) float32 whose last 4 columns are xyxy boxes, K (B,1) (all equal),

@@ -11,11 +11,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqa_sm100.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 PREC_TF32X3 = 0
 PREC_TF32 = 1
 PREC_TF32X3_HP = 2
 GEMM_RELU = 1
+GEMM_ACCUMULATE = 8
 GC_RELU = 1
 
 _p = C.c_void_p
@@ -30,7 +31,7 @@ SIGNATURES = {
     "vqa_split_bf16_f32": [_p, _ll, _p, _p, _ll, _ll, _i, _p],
     "vqa_gemm_bf16s": [_p, _p, _ll, _i, _p, _p, _ll, _i, _p, _ll, _p, _p, _ll, _i, _i, _i, _p, _p, _ll, _i, _p, _ll, _p, _ll,
                        _f, _i, _i, _i, _i, _p],
-    "vqa_dropout_f32": [_p, _p, _ll, _f, _u64, _u64, _p],
+    "vqa_dropout_f32": [_p, _p, _ll, _f, _u64, _u64, _p, _p],
     "vqa_weight_norm_fwd_f32": [_p, _p, _p, _i, _i, _p],
     "vqa_weight_norm_bwd_f32": [_p, _p, _p, _p, _p, _i, _i, _p],
     "vqa_colsum_f32": [_p, _ll, _p, _p, _ll, _i, _p],
@@ -38,12 +39,16 @@ SIGNATURES = {
     "vqa_adjacency_topk_fwd_f32": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     "vqa_topk_softmax_f32": [_p, _p, _p, _i, _i, _i, _p],
     "vqa_adjacency_topk_bwd_f32": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
-    "vqa_graphconv_fwd_f32": [_p, _ll, _p, _p, _p, _ll, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _f, _u64, _u64, _p],
+    "vqa_graphconv_fwd_f32": [_p, _ll, _p, _p, _p, _ll, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _f, _u64, _u64, _p, _p],
     "vqa_graphconv_pool_fwd_f32": [_p, _ll, _p, _p, _ll, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "vqa_graphconv_bwd_f32": [_p, _ll, _p, _p, _p, _ll, _p, _p, _p, _ll, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _p],
     "vqa_graphconv_edge_blocks": [_i, _i, _i],
     "vqa_graphconv_edge_bwd_f32": [_p, _p, _p, _p, _ll, _p, _p, _p, _i, _i, _i, _i, _p],
     "vqa_gaussian_weights_f32": [_p, _p, _p, _ll, _i, _p],
+    "vqa_embed_gather_split": [_p, _ll, _p, _ll, _i, _p, _p, _ll, _i, _i, _p],
+    "vqa_embed_scatter_add_f32": [_p, _ll, _p, _ll, _p, _p, _ll, _i, _i, _i, _p],
+    "vqa_gru_cell_fwd_f32": [_p, _ll, _p, _p, _p, _p, _i, _p, _p, _p, _ll, _p, _i, _i, _p],
+    "vqa_gru_cell_bwd_f32": [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _ll, _p, _i, _i, _p],
     "vqa_gate_bwd_f32": [_p, _p, _p, _p, _p, _ll, _p],
 }
 EXPORTS = ["vqa_last_error", "vqa_abi_version"] + list(SIGNATURES)

@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import PREC_TF32, PREC_TF32X3, PREC_TF32X3_HP, GEMM_RELU, GC_RELU
+from ._cabi import PREC_TF32, PREC_TF32X3, PREC_TF32X3_HP, GEMM_RELU, GEMM_ACCUMULATE, GC_RELU
 
 LAUNCHES = 0
 _LAUNCH_COST = {"vqa_colsum_f32": 2}
@@ -146,8 +146,8 @@ def split(x: torch.Tensor, with_lo: bool = True) -> SplitT:
 def gemm_s(a: SplitT, b: SplitT, *, a_mn: bool = False, b_mn: bool = False, out: Optional[torch.Tensor] = None,
            out_split: Optional[SplitT] = None, want_f32: bool = True, bias: Optional[torch.Tensor] = None,
            rowbcast: Optional[torch.Tensor] = None, group: int = 1, aux=None, aux_scale: float = 1.0, relu: bool = False,
-           passes: int = 3, split_k: int = 1, tile_n: int = 0):
-    """C[M,N] = epi(A . B^T) on the split-bf16 tcgen05 GEMM.  ``a`` is (M,K) [a_mn=False] or (K,M) [a_mn=True]; same
+           passes: int = 3, split_k: int = 1, tile_n: int = 0, accumulate: bool = False):
+    """C[M,N] = epi(A . B^T) on the split-bf16 tcgen05 GEMM (``accumulate``: ``out += A . B^T`` with fp32 atomics).  ``a`` is (M,K) [a_mn=False] or (K,M) [a_mn=True]; same
     for ``b`` with N.  ``aux`` (mask source) may be an fp32 tensor or a SplitT.  Returns ``out`` (fp32) or, when
     ``want_f32`` is False, ``out_split``."""
     M, Ka = (a.cols, a.rows) if a_mn else (a.rows, a.cols)
@@ -160,6 +160,8 @@ def gemm_s(a: SplitT, b: SplitT, *, a_mn: bool = False, b_mn: bool = False, out:
     ldc = 0
     if want_f32:
         if out is None:
+            if accumulate:
+                raise RuntimeError("gemm_s: accumulate=True needs an initialised out")
             out = torch.empty((M, N), device=dev, dtype=torch.float32)
             if split_k > 1:
                 out.zero_()
@@ -184,15 +186,17 @@ def gemm_s(a: SplitT, b: SplitT, *, a_mn: bool = False, b_mn: bool = False, out:
           b.hi.data_ptr(), _ptr(b.lo) if passes == 3 else None, b.ld, int(b_mn), _ptr(out), ldc,
           None if out_split is None else out_split.hi.data_ptr(), None if out_split is None else _ptr(out_split.lo),
           0 if out_split is None else out_split.ld, M, N, Ka, _ptr(bias), _ptr(rowbcast), ldrb, group,
-          _ptr(aux_f), ldaux, _ptr(aux_h), ldauxh, float(aux_scale), GEMM_RELU if relu else 0, passes, split_k, tile_n, _stream())
+          _ptr(aux_f), ldaux, _ptr(aux_h), ldauxh, float(aux_scale), (GEMM_RELU if relu else 0) | (GEMM_ACCUMULATE if accumulate else 0),
+          passes, split_k, tile_n, _stream())
     return out if want_f32 else out_split
 
 
 # ------------------------------------------------------------------------------------------- elementwise
-def dropout(x: torch.Tensor, p: float, seed: int, offset: int) -> torch.Tensor:
+def dropout(x: torch.Tensor, p: float, seed: int, offset: int, step: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``step``: optional CUDA int64 scalar tensor; 16 * its run-time value is added to ``offset`` (graph replays)."""
     x = _chk(x, "dropout x").contiguous()
     y = torch.empty_like(x)
-    _call("vqa_dropout_f32", x.data_ptr(), y.data_ptr(), x.numel(), float(p), seed, offset, _stream())
+    _call("vqa_dropout_f32", x.data_ptr(), y.data_ptr(), x.numel(), float(p), seed, offset, _ptr(step), _stream())
     return y
 
 
@@ -282,7 +286,7 @@ def _boxes_view(image: torch.Tensor):
     return image.data_ptr() + (image.shape[2] - 4) * 4, image.stride(1)
 
 
-def graphconv_fwd(Y, idx, alpha, image, gauss, B, K, relu=True, dropout_p=0.0, seed=0, offset=0):
+def graphconv_fwd(Y, idx, alpha, image, gauss, B, K, relu=True, dropout_p=0.0, seed=0, offset=0, step=None):
     Y, ldy = _rows_view(_chk(Y, "graphconv Y"), "graphconv Y")
     nb = idx.shape[-1]
     nk = gauss.numel() // 4
@@ -290,7 +294,7 @@ def graphconv_fwd(Y, idx, alpha, image, gauss, B, K, relu=True, dropout_p=0.0, s
     bptr, ldbox = _boxes_view(image)
     out = torch.empty((B * K, out_dim), device=Y.device, dtype=torch.float32)
     _call("vqa_graphconv_fwd_f32", Y.data_ptr(), ldy, idx.data_ptr(), _ptr(alpha), bptr, ldbox, gauss.data_ptr(),
-          out.data_ptr(), out_dim, B, K, nb, nk, out_dim, GC_RELU if relu else 0, float(dropout_p), seed, offset, _stream())
+          out.data_ptr(), out_dim, B, K, nb, nk, out_dim, GC_RELU if relu else 0, float(dropout_p), seed, offset, _ptr(step), _stream())
     return out
 
 
@@ -340,3 +344,40 @@ def gaussian_weights(pseudo: torch.Tensor, gauss: torch.Tensor) -> torch.Tensor:
     w = torch.empty((pseudo.shape[0], nk), device=pseudo.device, dtype=torch.float32)
     _call("vqa_gaussian_weights_f32", pseudo.data_ptr(), gauss.data_ptr(), w.data_ptr(), pseudo.shape[0], nk, _stream())
     return w
+
+
+# ------------------------------------------------------------------------------------------- question encoder
+def embed_gather_split(question: torch.Tensor, wemb: torch.Tensor, T: int, with_lo: bool = True) -> SplitT:
+    """question (B, >=T) int64, wemb (V, E) fp32 -> split planes of the time-major embeddings (T*B, E)."""
+    if question.dtype != torch.int64 or not question.is_cuda or question.stride(1) != 1:
+        raise RuntimeError("embed_gather_split: question must be a CUDA int64 tensor with contiguous rows (no CPU fallback)")
+    wemb = _chk(wemb, "embedding weight").contiguous()
+    B = question.shape[0]
+    if T > question.shape[1]:
+        raise RuntimeError(f"embed_gather_split: T={T} exceeds the question width {question.shape[1]}")
+    out = empty_split(T * B, wemb.shape[1], wemb.device, with_lo)
+    _call("vqa_embed_gather_split", question.data_ptr(), question.stride(0), wemb.data_ptr(), wemb.shape[0], wemb.shape[1],
+          out.hi.data_ptr(), _ptr(out.lo), out.ld, B, T, _stream())
+    return out
+
+
+def embed_scatter_add(dE: torch.Tensor, question: torch.Tensor, qlen: torch.Tensor, dW: torch.Tensor, T: int) -> torch.Tensor:
+    dE, ldd = _rows_view(_chk(dE, "dE"), "dE")
+    _chk(dW, "dW")
+    _chk(qlen, "qlen", torch.int32)
+    _call("vqa_embed_scatter_add_f32", dE.data_ptr(), ldd, question.data_ptr(), question.stride(0), qlen.data_ptr(), dW.data_ptr(),
+          dW.shape[0], dW.shape[1], question.shape[0], T, _stream())
+    return dW
+
+
+def gru_cell_fwd(gi, gh, b_hh, h_prev, qlen, t, h_out, h_split: SplitT, gates):
+    gi, ldgi = _rows_view(_chk(gi, "gi"), "gi")
+    B, H = h_out.shape
+    _call("vqa_gru_cell_fwd_f32", gi.data_ptr(), ldgi, _ptr(gh), b_hh.data_ptr(), _ptr(h_prev), qlen.data_ptr(), t, h_out.data_ptr(),
+          h_split.hi.data_ptr(), _ptr(h_split.lo), h_split.ld, gates.data_ptr(), B, H, _stream())
+
+
+def gru_cell_bwd(dh, gates, h_prev, qlen, t, dgi, dgh, dgi_s: SplitT, dgh_s: SplitT, dh_part):
+    B, H = dh.shape
+    _call("vqa_gru_cell_bwd_f32", dh.data_ptr(), gates.data_ptr(), _ptr(h_prev), qlen.data_ptr(), t, dgi.data_ptr(), dgh.data_ptr(),
+          dgi_s.hi.data_ptr(), _ptr(dgi_s.lo), dgh_s.hi.data_ptr(), _ptr(dgh_s.lo), dgi_s.ld, dh_part.data_ptr(), B, H, _stream())

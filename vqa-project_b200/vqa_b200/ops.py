@@ -71,13 +71,30 @@ def _split_for(out_rows: int, out_cols: int, contraction: int) -> int:
     return s
 
 
+_GRAPH_RNG = None   # (seed, device int64 step counter) while a CUDA-graph-safe RNG is installed (engine.TrainStep)
+_GRAPH_RNG_SITE = 0
+
+
+def set_graph_rng(seed=None, step: "torch.Tensor | None" = None) -> None:
+    """Install (or remove, with no arguments) a graph-safe dropout RNG: masks are a function of (seed, call site,
+    *step) with ``step`` read on the device at run time, so replays of a captured step differ once ``step`` is bumped."""
+    global _GRAPH_RNG, _GRAPH_RNG_SITE
+    _GRAPH_RNG = None if seed is None else (int(seed) & 0xFFFFFFFFFFFFFFFF, step)
+    _GRAPH_RNG_SITE = 0
+
+
 def next_philox(device: torch.device):
-    """(seed, offset) for one fused-dropout call, drawn from (and advancing) torch's CUDA generator state,
-    so ``torch.manual_seed`` controls the masks exactly as it does for nn.Dropout."""
+    """(seed, offset, step tensor or None) for one fused-dropout call.  Eager mode: drawn from (and advancing) torch's
+    CUDA generator state, so ``torch.manual_seed`` controls the masks exactly as it does for nn.Dropout.  Graph mode
+    (``set_graph_rng``): per-call-site offsets plus the device-side step counter."""
+    global _GRAPH_RNG_SITE
+    if _GRAPH_RNG is not None:
+        _GRAPH_RNG_SITE = _GRAPH_RNG_SITE % 15 + 1
+        return _GRAPH_RNG[0], _GRAPH_RNG_SITE, _GRAPH_RNG[1]
     gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
     off = gen.get_offset()
     gen.set_offset(off + 4)
-    return gen.initial_seed() & 0xFFFFFFFFFFFFFFFF, off // 4 + 1
+    return gen.initial_seed() & 0xFFFFFFFFFFFFFFFF, off // 4 + 1, None
 
 
 def pack_gauss(mean_rho, precision_rho, mean_theta, precision_theta) -> torch.Tensor:
@@ -116,8 +133,8 @@ class ConditionedGraphFn(torch.autograd.Function):
         # dropout on the WHOLE image tensor incl. box columns (sparse_graph_model.py:111); box centres are taken
         # from the un-dropped image inside the graph-conv kernels (:106-108 precede :111)
         if drop:
-            seed, off = next_philox(dev)
-            X = kn.dropout(image, p_drop, seed, off)
+            seed, off, step = next_philox(dev)
+            X = kn.dropout(image, p_drop, seed, off, step)
         else:
             X = image
         X2 = X.view(B * K, F)
@@ -147,8 +164,8 @@ class ConditionedGraphFn(torch.autograd.Function):
         gs2 = pack_gauss(mr2, pr2, mt2, pt2)
         Y1 = _gemm_s(Xs, Wc1s)
         if drop:
-            seed, off = next_philox(dev)
-            G1 = kn.graphconv_fwd(Y1, idx, alpha, image, gs1, B, K, relu=True, dropout_p=p_drop, seed=seed, offset=off)
+            seed, off, step = next_philox(dev)
+            G1 = kn.graphconv_fwd(Y1, idx, alpha, image, gs1, B, K, relu=True, dropout_p=p_drop, seed=seed, offset=off, step=step)
         else:
             G1 = kn.graphconv_fwd(Y1, idx, alpha, image, gs1, B, K, relu=True)
         G1s = _split(G1)
@@ -160,8 +177,8 @@ class ConditionedGraphFn(torch.autograd.Function):
         hqs = _split(hq)
         o1 = _gemm_s(hqs, Wo1s, bias=bo1, relu=True)
         if drop:
-            seed, off = next_philox(dev)
-            o1 = kn.dropout(o1, p_drop, seed, off)
+            seed, off, step = next_philox(dev)
+            o1 = kn.dropout(o1, p_drop, seed, off, step)
         o1s = _split(o1)
         logits = _gemm_s(o1s, Wo2s, bias=bo2)
 
@@ -234,6 +251,72 @@ class ConditionedGraphFn(torch.autograd.Function):
                 dgs1[0:nk].view(gsh), dgs1[nk:2 * nk].view(gsh), dgs1[2 * nk:3 * nk].view(gsh), dgs1[3 * nk:].view(gsh),
                 dgs2[0:nk].view(gsh), dgs2[nk:2 * nk].view(gsh), dgs2[2 * nk:3 * nk].view(gsh), dgs2[3 * nk:].view(gsh),
                 dvo1, dgo1, dbo1, dvo2, dgo2, dbo2, *conv_grads)
+
+
+class QuestionEncoderFn(torch.autograd.Function):
+    """(question tokens, lengths, embedding + GRU parameters) -> final GRU state per question (B, H).
+
+    Restates nn.Embedding + pack_padded_sequence + nn.GRU + ``hid[0]`` (reference sparse_graph_model.py:117-121) as a
+    padded, length-masked recurrence whose matrix products run on the split-bf16 tcgen05 GEMM (always 3 passes: the
+    recurrence compounds errors over T steps).  No host-side packing, no data-dependent shapes."""
+
+    @staticmethod
+    def forward(ctx, question, qlen, T, wemb, w_ih, w_hh, b_ih, b_hh):
+        B = question.shape[0]
+        H = w_hh.shape[1]
+        dev = wemb.device
+        Es = kn.embed_gather_split(question, wemb, T)
+        Wihs, Whhs = kn.split(w_ih), kn.split(w_hh)
+        b_ih = b_ih.contiguous()
+        b_hh = b_hh.contiguous()
+        GI = kn.gemm_s(Es, Wihs, bias=b_ih)                                   # (T*B, 3H), all steps at once
+        Hall = torch.empty((T + 1, B, H), device=dev, dtype=torch.float32)     # Hall[t+1] = h_t, Hall[0] = 0
+        Hs = kn.empty_split((T + 1) * B, H, dev)
+        Hall[0].zero_(); Hs.hi[:B].zero_(); Hs.lo[:B].zero_()
+        gates = torch.empty((T, B, 4 * H), device=dev, dtype=torch.float32)
+        fsplit = max(1, min(4, 384 // max(1, ((B + 127) // 128) * ((3 * H + 63) // 64))))   # ~384 CTAs for the per-step product
+        for t in range(T):
+            GH = kn.gemm_s(Hs.rows_slice(t * B, (t + 1) * B), Whhs, split_k=fsplit) if t > 0 else None
+            kn.gru_cell_fwd(GI[t * B:(t + 1) * B], GH, b_hh, Hall[t] if t > 0 else None, qlen, t, Hall[t + 1],
+                            Hs.rows_slice((t + 1) * B, (t + 2) * B), gates[t])
+        ctx.T = T
+        ctx.splits = (Es, Wihs, Whhs, Hs)
+        ctx.save_for_backward(question, qlen, wemb, Hall, gates)
+        return Hall[T]
+
+    @staticmethod
+    def backward(ctx, dq):
+        question, qlen, wemb, Hall, gates = ctx.saved_tensors
+        Es, Wihs, Whhs, Hs = ctx.splits
+        T = ctx.T
+        _, B, H = Hall.shape
+        dev = wemb.device
+        dh = dq.contiguous()
+        dGI = torch.empty((T * B, 3 * H), device=dev, dtype=torch.float32)
+        dGH = torch.empty((T * B, 3 * H), device=dev, dtype=torch.float32)
+        dGIs = kn.empty_split(T * B, 3 * H, dev)
+        dGHs = kn.empty_split(T * B, 3 * H, dev)
+        ksplit = max(1, min(8, 256 // max(1, ((B + 127) // 128) * ((H + 63) // 64))))   # ~256 CTAs for the per-step product
+        for t in reversed(range(T)):
+            r0, r1 = t * B, (t + 1) * B
+            dh_part = torch.empty((B, H), device=dev, dtype=torch.float32)
+            kn.gru_cell_bwd(dh, gates[t], Hall[t] if t > 0 else None, qlen, t, dGI[r0:r1], dGH[r0:r1],
+                            dGIs.rows_slice(r0, r1), dGHs.rows_slice(r0, r1), dh_part)
+            if t > 0:   # dL/dh_{t-1} = direct part + dgh . W_hh  (split-K accumulating into the direct part)
+                kn.gemm_s(dGHs.rows_slice(r0, r1), Whhs, b_mn=True, out=dh_part, accumulate=True, split_k=ksplit)
+            dh = dh_part
+        db_ih = kn.colsum(dGI)
+        db_hh = kn.colsum(dGH)
+        TB = T * B
+        s_ih = _split_for(3 * H, Es.cols, TB)
+        dW_ih = kn.gemm_s(dGIs, Es, a_mn=True, b_mn=True, split_k=s_ih)
+        dW_hh = kn.gemm_s(dGHs, Hs.rows_slice(0, TB), a_mn=True, b_mn=True, split_k=_split_for(3 * H, H, TB))
+        dwemb = None
+        if ctx.needs_input_grad[3]:
+            dE = kn.gemm_s(dGIs, Wihs, b_mn=True)                             # (T*B, E)
+            dwemb = torch.zeros_like(wemb)
+            kn.embed_scatter_add(dE, question, qlen, dwemb, T)
+        return None, None, None, dwemb, dW_ih, dW_hh, db_ih, db_hh
 
 
 # ------------------------------------------------------------------------------------------- layer-level operators
