@@ -116,7 +116,8 @@ int vqa_graphconv_pool_fwd_f32(const float* Y, long long ldy, const int* idx, co
                                int B, int K, int nb, int nk, int out_dim, vqa_stream_t stream);
 /* Backward data path of the aggregate.  Upstream gradient is either dense dO (B,K,out) (already ReLU/dropout
  * masked) or, for the pooled layer, dpooled (B,out) + argmax (scatter by argmax is done on the fly).
- * Writes dY (B,K,out) and the per-edge, per-kernel dot products P (B,K,nb,nk) = <dO[i,chunk k], Y[idx,chunk k]>. */
+ * Writes dY (B,K,out) (skipped when dY is NULL) and the per-edge, per-kernel dot products
+ * P (B,K,nb,nk) = <dO[i,chunk k], Y[idx,chunk k]>. */
 int vqa_graphconv_bwd_f32(const float* dO, long long lddo, const float* dpooled, const long long* argmax,
                           const float* Y, long long ldy, const int* idx, const float* alpha, const float* boxes,
                           long long ldbox, const float* gauss, float* dY, long long lddy, float* P, int B, int K,
@@ -128,6 +129,22 @@ int vqa_graphconv_edge_blocks(int B, int K, int nb);
 int vqa_graphconv_edge_bwd_f32(const float* P, const int* idx, const float* alpha, const float* boxes,
                                long long ldbox, const float* gauss, float* dalpha, float* dgauss_partial, int B,
                                int K, int nb, int nk, vqa_stream_t stream);
+
+/* ---- tensor-core graph convolution on split-bf16 planes (graphconv_mma.cu).  Same maths and reference call sites as
+ * vqa_graphconv_fwd_f32 / _pool_fwd_f32 / the dY part of _bwd_f32; Y and the results are (hi, lo) bf16 planes (lo may
+ * be NULL: bf16 mode), so the projections before and after exchange planes with no fp32 round trip.  Requires
+ * (out_dim / nk) % 128 == 0 and K <= 128; returns VQA_ERR_UNSUPPORTED otherwise (callers use the fp32 kernels). */
+int vqa_graphconv_mma_fwd(const void* Y_hi, const void* Y_lo, long long ldy, const int* idx, const float* alpha,
+                          const float* boxes, long long ldbox, const float* gauss, void* out_hi, void* out_lo, long long ldo,
+                          int B, int K, int nb, int nk, int out_dim, int flags, float dropout_p, unsigned long long seed,
+                          unsigned long long offset, const unsigned long long* step_ptr, vqa_stream_t stream);
+int vqa_graphconv_mma_pool_fwd(const void* Y_hi, const void* Y_lo, long long ldy, const int* idx, const float* boxes,
+                               long long ldbox, const float* gauss, const float* q, float* pooled, long long* argmax,
+                               float* hq, int B, int K, int nb, int nk, int out_dim, vqa_stream_t stream);
+/* dY[b,j, chunk k] = sum_{(i,m): idx[i,m]=j} w[i,m,k] alpha[i,m] dO[b,i, chunk k]  (the transposed aggregate) */
+int vqa_graphconv_mma_bwd_data(const void* dO_hi, const void* dO_lo, long long lddo, const int* idx, const float* alpha,
+                               const float* boxes, long long ldbox, const float* gauss, void* dY_hi, void* dY_lo,
+                               long long lddy, int B, int K, int nb, int nk, int out_dim, vqa_stream_t stream);
 
 /* Gaussian patch weights for explicit pseudo-coordinates (n,2) -> (n,nk): NeighbourhoodGraphConvolution.
  * get_gaussian_weights, layers.py:100-125 (layer-level API). */

@@ -422,6 +422,79 @@ def test_graphconv_bwd(kn, B, K, nb, nk, out_dim, mode):
         assert dalpha is None
 
 
+# ---- tensor-core aggregate on split planes (graphconv_mma.cu) -----------------------------------------------------
+MMA_CASES = [(4, 36, 16, 8, 2048), (3, 36, 16, 8, 1024), (2, 51, 19, 4, 512), (2, 100, 32, 8, 1024), (3, 12, 5, 2, 256), (2, 7, 7, 1, 128)]
+
+
+@pytest.mark.parametrize("B,K,nb,nk,out_dim", MMA_CASES)
+@pytest.mark.parametrize("use_alpha", [True, False])
+def test_graphconv_mma_fwd(kn, B, K, nb, nk, out_dim, use_alpha):
+    image, Y, idx, alpha, gp = _gc_inputs(B, K, nb, nk, out_dim, seed=K + nb)
+    ref = torch.relu(_gc_reference(Y, idx, alpha if use_alpha else None, image, gp, "gc", nk))
+    Ys = kn.split(Y.float().view(B * K, -1).to(DEV))
+    out = kn.graphconv_fwd_s(Ys, idx.int().to(DEV), alpha.float().to(DEV) if use_alpha else None, image.float().to(DEV),
+                             _pack_gauss(gp, "gc"), B, K, relu=True)
+    assert out.shape == (B * K, out_dim)
+    assert rel_err(out.float().view(B, K, -1).cpu(), ref) < 3e-5
+    # bf16 mode: hi planes only
+    out1 = kn.graphconv_fwd_s(kn.split(Y.float().view(B * K, -1).to(DEV), with_lo=False), idx.int().to(DEV),
+                              alpha.float().to(DEV) if use_alpha else None, image.float().to(DEV), _pack_gauss(gp, "gc"), B, K)
+    assert out1.lo is None and rel_err(out1.float().view(B, K, -1).cpu(), ref) < 2e-2
+
+
+def test_graphconv_mma_fused_dropout(kn):
+    B, K, nb, nk, out_dim = 6, 36, 16, 8, 2048
+    image, Y, idx, alpha, gp = _gc_inputs(B, K, nb, nk, out_dim, seed=11)
+    args = (kn.split(Y.float().view(B * K, -1).to(DEV)), idx.int().to(DEV), alpha.float().to(DEV), image.float().to(DEV), _pack_gauss(gp, "gc"), B, K)
+    base = kn.graphconv_fwd_s(*args, relu=True).float()
+    dropped = kn.graphconv_fwd_s(*args, relu=True, dropout_p=0.5, seed=42, offset=3).float()
+    kept = dropped != 0
+    assert torch.allclose(dropped[kept], 2.0 * base[kept], rtol=1e-4, atol=1e-6)
+    pos = base > 0
+    assert abs((kept & pos).sum().item() / pos.sum().item() - 0.5) < 0.01
+    assert torch.equal(dropped, kn.graphconv_fwd_s(*args, relu=True, dropout_p=0.5, seed=42, offset=3).float())
+    other = kn.graphconv_fwd_s(*args, relu=True, dropout_p=0.5, seed=42, offset=4).float()
+    assert not torch.equal(dropped, other)
+    step = torch.tensor(5, dtype=torch.int64, device=DEV)          # device-side step counter shifts the stream
+    s5 = kn.graphconv_fwd_s(*args, relu=True, dropout_p=0.5, seed=42, offset=3, step=step).float()
+    assert not torch.equal(dropped, s5)
+    # masks of neighbouring rows / columns are uncorrelated
+    m = kept[:, :-1] & pos[:, :-1] & pos[:, 1:]
+    agree = ((kept[:, :-1] == kept[:, 1:]) & pos[:, :-1] & pos[:, 1:]).sum().item() / max(1, (pos[:, :-1] & pos[:, 1:]).sum().item())
+    assert abs(agree - 0.5) < 0.01
+
+
+@pytest.mark.parametrize("B,K,nb,nk,out_dim", MMA_CASES)
+def test_graphconv_mma_pool_fwd(kn, B, K, nb, nk, out_dim):
+    image, Y, idx, alpha, gp = _gc_inputs(B, K, nb, nk, out_dim, seed=2 * K + nb)
+    g2 = torch.relu(_gc_reference(Y, idx, None, image, gp, "gc", nk))
+    pooled_ref, arg_ref = g2.max(1)
+    q = torch.randn(B, out_dim, dtype=torch.float64)
+    pooled, arg, hq = kn.graphconv_pool_fwd_s(kn.split(Y.float().view(B * K, -1).to(DEV)), idx.int().to(DEV), image.float().to(DEV),
+                                              _pack_gauss(gp, "gc"), q.float().to(DEV), B, K)
+    assert rel_err(pooled.cpu(), pooled_ref) < 3e-5
+    assert rel_err(hq.cpu(), torch.relu(q) * pooled_ref) < 3e-5
+    assert arg.dtype == torch.int64
+    top2 = g2.topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 1e-3 * top2[:, 0].abs().clamp(min=1e-3)
+    assert torch.equal(arg.cpu()[safe], arg_ref[safe])
+    zero_cols = pooled_ref == 0
+    assert (arg.cpu()[zero_cols] == 0).all()
+
+
+@pytest.mark.parametrize("B,K,nb,nk,out_dim", MMA_CASES)
+@pytest.mark.parametrize("use_alpha", [True, False])
+def test_graphconv_mma_bwd_data(kn, B, K, nb, nk, out_dim, use_alpha):
+    image, Y, idx, alpha, gp = _gc_inputs(B, K, nb, nk, out_dim, seed=3 * K + nb)
+    Yr = Y.clone().requires_grad_(True)
+    out = _gc_reference(Yr, idx, alpha if use_alpha else None, image, gp, "gc", nk)
+    dO = torch.randn(B, K, out_dim, generator=torch.Generator().manual_seed(1), dtype=torch.float64)
+    (dY_ref,) = torch.autograd.grad((out * dO).sum(), [Yr])
+    dY = kn.graphconv_bwd_data_s(kn.split(dO.float().view(B * K, -1).to(DEV)), idx.int().to(DEV), alpha.float().to(DEV) if use_alpha else None,
+                                 image.float().to(DEV), _pack_gauss(gp, "gc"), B, K)
+    assert rel_err(dY.float().view(B, K, -1).cpu(), dY_ref) < 3e-5
+
+
 def test_gaussian_weights_match_reference_golden(kn):
     g = load_golden("tiny")
     p = golden_params(g)

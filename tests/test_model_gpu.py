@@ -86,6 +86,47 @@ def test_model_forward_backward_matches_reference(name):
     assert worst[1] < 5e-4
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_model_tensor_core_aggregate_path_matches_oracle(precision):
+    """'medium' is the smallest shape on which both graph convolutions run the tcgen05 aggregate (graphconv_mma.cu); the
+    golden workloads above take the CUDA-core fallback.  Checker: the oracle (pinned to the reference by
+    test_oracle_golden.py) run on the CPU with the same weights and inputs.  bf16 mode: stated tolerance."""
+    import sparse_graph_model as M
+    from vqa_b200 import kernels as kn, ops
+    w = WORKLOADS["medium"]
+    assert kn.mma_eligible(w.n_obj, 2 * w.hid_dim, w.n_kernels) and kn.mma_eligible(w.n_obj, w.hid_dim, w.n_kernels)
+    torch.manual_seed(1000)
+    model = M.Model(pretrained_wemb=make_wemb(w), **w.model_kwargs())
+    with torch.no_grad():
+        for gc in (model.graph_convolution_1, model.graph_convolution_2):
+            gc.precision_rho.clamp_(min=0.05); gc.precision_theta.clamp_(min=0.05)
+    params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV).train()
+    b = make_batch(w, seed=7)
+    ops.set_precision(precision)
+    try:
+        logits, adj, arg = model(b["question"].to(DEV), b["image"].to(DEV), b["K"].to(DEV), b["qlen"])
+        loss = torch.nn.MultiLabelSoftMarginLoss()(logits, b["target"].to(DEV))
+        loss.backward()
+    finally:
+        ops.set_precision("fp32")
+    ref_loss, ref_grads, (ref_logits, ref_adj, _) = O.train_step_grads(params, b["question"], b["image"], [int(x) for x in b["qlen"]],
+                                                                        b["target"], w.neighbourhood, w.n_kernels)
+    # bf16 mode, stated tolerance: logits 2e-2, weight gradients 5e-2, Gaussian-kernel parameter gradients (sums of
+    # cancelling per-edge terms) 2e-1 -- max-norm relative
+    tol_out, tol_grad, tol_gauss = (TIGHT, 5e-4, 5e-4) if precision == "fp32" else (2e-2, 5e-2, 2e-1)
+    assert rel_err(adj.detach().cpu(), ref_adj) < TIGHT          # graph-learner forward is fp32-grade in both modes
+    assert rel_err(logits.detach().cpu(), ref_logits) < tol_out
+    worst = ("", 0.0)
+    for k, v in model.named_parameters():
+        e = rel_err(v.grad.cpu(), ref_grads[k])
+        gaussian = ".mean_" in k or ".precision_" in k
+        assert e < (tol_gauss if gaussian else tol_grad), (k, e)
+        if e > worst[1] and not gaussian:
+            worst = (k, e)
+    print(f"medium/{precision}: logits rel err {rel_err(logits.detach().cpu(), ref_logits):.2e}, worst weight-gradient rel err {worst[1]:.2e} ({worst[0]})")
+
+
 def test_eval_mode_and_no_grad_match_train_mode_without_dropout():
     g = load_golden("tiny")
     _, model = _build("tiny", g)

@@ -931,12 +931,12 @@ extern "C" int vqa_graphconv_bwd_f32(const float* dO, long long lddo, const floa
                                      int nb, int nk, int out_dim, cudaStream_t stream) {
   const char* who = "vqa_graphconv_bwd_f32";
   const bool pooled = dO == nullptr;
-  VQA_CHECK_ARG(Y && idx && boxes && gauss && dY && P, "%s: null pointer", who);
+  VQA_CHECK_ARG(Y && idx && boxes && gauss && P, "%s: null pointer", who);
   VQA_CHECK_ARG(pooled ? (dpooled && argmax) : true, "%s: need either dO or (dpooled, argmax)", who);
-  VQA_CHECK_ARG(aligned16(Y) && (ldy & 3) == 0 && aligned16(dY) && (lddy & 3) == 0, "%s: Y/dY alignment", who);
+  VQA_CHECK_ARG(aligned16(Y) && (ldy & 3) == 0 && (!dY || (aligned16(dY) && (lddy & 3) == 0)), "%s: Y/dY alignment", who);
   VQA_CHECK_ARG(pooled ? aligned16(dpooled) : (aligned16(dO) && (lddo & 3) == 0), "%s: upstream gradient alignment", who);
-  bool dy_done = false;
-  if (K <= 128 && nb <= K && nk <= MAX_NK && out_dim % nk == 0) {   // dY = M^T dO on the dense-register kernel
+  bool dy_done = dY == nullptr;            // dY == NULL: the caller computes dY elsewhere (tensor-core path); only P is wanted
+  if (!dy_done && K <= 128 && nb <= K && nk <= MAX_NK && out_dim % nk == 0) {   // dY = M^T dO on the dense-register kernel
     DenseParams dp{};
     dp.in = dO; dp.ldin = pooled ? 2 : lddo; dp.dpooled = dpooled; dp.argmax_in = argmax;
     dp.idx = idx; dp.alpha = alpha; dp.boxes = boxes; dp.ldbox = ldbox; dp.gauss = gauss; dp.out = dY; dp.ldo = lddy;

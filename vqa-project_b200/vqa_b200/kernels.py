@@ -313,14 +313,14 @@ def graphconv_pool_fwd(Y, idx, image, gauss, q, B, K):
     return pooled, argmax, hq
 
 
-def graphconv_bwd(Y, idx, alpha, image, gauss, B, K, dO=None, dpooled=None, argmax=None):
-    """-> dY (B*K,out), dalpha (B,K,nb) or None, dgauss (4*nk,)"""
+def graphconv_bwd(Y, idx, alpha, image, gauss, B, K, dO=None, dpooled=None, argmax=None, want_dY=True):
+    """-> dY (B*K,out) (None when ``want_dY`` is False), dalpha (B,K,nb) or None, dgauss (4*nk,)"""
     Y, ldy = _rows_view(_chk(Y, "graphconv Y"), "graphconv Y")
     nb = idx.shape[-1]
     nk = gauss.numel() // 4
     out_dim = Y.shape[1]
     bptr, ldbox = _boxes_view(image)
-    dY = torch.empty((B * K, out_dim), device=Y.device, dtype=torch.float32)
+    dY = torch.empty((B * K, out_dim), device=Y.device, dtype=torch.float32) if want_dY else None
     P = torch.empty((B, K, nb, nk), device=Y.device, dtype=torch.float32)
     lddo = 0
     if dO is not None:
@@ -328,7 +328,7 @@ def graphconv_bwd(Y, idx, alpha, image, gauss, B, K, dO=None, dpooled=None, argm
     else:
         dpooled = _chk(dpooled, "dpooled").contiguous()
     _call("vqa_graphconv_bwd_f32", _ptr(dO), lddo, _ptr(dpooled), _ptr(argmax), Y.data_ptr(), ldy, idx.data_ptr(),
-          _ptr(alpha), bptr, ldbox, gauss.data_ptr(), dY.data_ptr(), out_dim, P.data_ptr(), B, K, nb, nk, out_dim, _stream())
+          _ptr(alpha), bptr, ldbox, gauss.data_ptr(), _ptr(dY), out_dim, P.data_ptr(), B, K, nb, nk, out_dim, _stream())
     nblk = _cabi.load().vqa_graphconv_edge_blocks(B, K, nb)
     partial = torch.empty((nblk, 4 * nk), device=Y.device, dtype=torch.float32)
     dalpha = torch.empty((B, K, nb), device=Y.device, dtype=torch.float32) if alpha is not None else None
@@ -336,6 +336,45 @@ def graphconv_bwd(Y, idx, alpha, image, gauss, B, K, dO=None, dpooled=None, argm
           _ptr(dalpha), partial.data_ptr(), B, K, nb, nk, _stream())
     dgauss = colsum(partial)
     return dY, dalpha, dgauss
+
+
+# ---- tensor-core variants on split planes -------------------------------------------------------------------------
+def mma_eligible(K: int, out_dim: int, nk: int) -> bool:
+    return K <= 128 and out_dim % nk == 0 and (out_dim // nk) % 128 == 0
+
+
+def graphconv_fwd_s(Ys: SplitT, idx, alpha, image, gauss, B, K, relu=True, dropout_p=0.0, seed=0, offset=0, step=None) -> SplitT:
+    """Layer-1 style aggregate on planes: Ys (B*K, out) -> relu/dropout(aggregate) as planes."""
+    nb, nk, out_dim = idx.shape[-1], gauss.numel() // 4, Ys.cols
+    bptr, ldbox = _boxes_view(image)
+    out = empty_split(B * K, out_dim, Ys.hi.device, Ys.lo is not None)
+    _call("vqa_graphconv_mma_fwd", Ys.hi.data_ptr(), _ptr(Ys.lo), Ys.ld, idx.data_ptr(), _ptr(alpha), bptr, ldbox, gauss.data_ptr(),
+          out.hi.data_ptr(), _ptr(out.lo), out.ld, B, K, nb, nk, out_dim, GC_RELU if relu else 0, float(dropout_p), seed, offset,
+          _ptr(step), _stream())
+    return out
+
+
+def graphconv_pool_fwd_s(Ys: SplitT, idx, image, gauss, q, B, K):
+    nb, nk, out_dim = idx.shape[-1], gauss.numel() // 4, Ys.cols
+    bptr, ldbox = _boxes_view(image)
+    q = _chk(q, "q").contiguous()
+    dev = Ys.hi.device
+    pooled = torch.empty((B, out_dim), device=dev, dtype=torch.float32)
+    argmax = torch.empty((B, out_dim), device=dev, dtype=torch.int64)
+    hq = torch.empty((B, out_dim), device=dev, dtype=torch.float32)
+    _call("vqa_graphconv_mma_pool_fwd", Ys.hi.data_ptr(), _ptr(Ys.lo), Ys.ld, idx.data_ptr(), bptr, ldbox, gauss.data_ptr(), q.data_ptr(),
+          pooled.data_ptr(), argmax.data_ptr(), hq.data_ptr(), B, K, nb, nk, out_dim, _stream())
+    return pooled, argmax, hq
+
+
+def graphconv_bwd_data_s(dOs: SplitT, idx, alpha, image, gauss, B, K) -> SplitT:
+    """dY = M^T dO on planes."""
+    nb, nk, out_dim = idx.shape[-1], gauss.numel() // 4, dOs.cols
+    bptr, ldbox = _boxes_view(image)
+    out = empty_split(B * K, out_dim, dOs.hi.device, dOs.lo is not None)
+    _call("vqa_graphconv_mma_bwd_data", dOs.hi.data_ptr(), _ptr(dOs.lo), dOs.ld, idx.data_ptr(), _ptr(alpha), bptr, ldbox, gauss.data_ptr(),
+          out.hi.data_ptr(), _ptr(out.lo), out.ld, B, K, nb, nk, out_dim, _stream())
+    return out
 
 
 def gaussian_weights(pseudo: torch.Tensor, gauss: torch.Tensor) -> torch.Tensor:

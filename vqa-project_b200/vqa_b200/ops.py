@@ -162,16 +162,31 @@ class ConditionedGraphFn(torch.autograd.Function):
         # graph convolution 1 (project first, then fused Gaussian-weight/gather/aggregate + ReLU + dropout)
         gs1 = pack_gauss(mr1, pr1, mt1, pt1)
         gs2 = pack_gauss(mr2, pr2, mt2, pt2)
-        Y1 = _gemm_s(Xs, Wc1s)
-        if drop:
-            seed, off, step = next_philox(dev)
-            G1 = kn.graphconv_fwd(Y1, idx, alpha, image, gs1, B, K, relu=True, dropout_p=p_drop, seed=seed, offset=off, step=step)
+        mma1 = kn.mma_eligible(K, Wc1s.rows, nk)      # tensor-core aggregate needs (out/nk) % 128 == 0; else CUDA-core kernels
+        mma2 = kn.mma_eligible(K, Wc2s.rows, nk)
+        with_lo = _PASSES == 3
+        gseed, goff, gstep = next_philox(dev) if drop else (0, 0, None)
+        if mma1:
+            Y1s = kn.empty_split(B * K, Wc1s.rows, dev, with_lo)
+            Y1 = _gemm_s(Xs, Wc1s, out_split=Y1s)                      # fp32 copy kept for the P kernel of the backward
+            G1s = kn.graphconv_fwd_s(Y1s, idx, alpha, image, gs1, B, K, relu=True, dropout_p=p_drop if drop else 0.0,
+                                     seed=gseed, offset=goff, step=gstep)
+            del Y1s
         else:
-            G1 = kn.graphconv_fwd(Y1, idx, alpha, image, gs1, B, K, relu=True)
-        G1s = _split(G1)
+            Y1 = _gemm_s(Xs, Wc1s)
+            G1 = kn.graphconv_fwd(Y1, idx, alpha, image, gs1, B, K, relu=True, dropout_p=p_drop if drop else 0.0,
+                                  seed=gseed, offset=goff, step=gstep)
+            G1s = _split(G1)
+            del G1
         # graph convolution 2 with max-pool over nodes + question gate fused (sparse_graph_model.py:146-151)
-        Y2 = _gemm_s(G1s, Wc2s)
-        pooled, argmax, hq = kn.graphconv_pool_fwd(Y2, idx, image, gs2, qenc, B, K)
+        if mma2:
+            Y2s = kn.empty_split(B * K, Wc2s.rows, dev, with_lo)
+            Y2 = _gemm_s(G1s, Wc2s, out_split=Y2s)
+            pooled, argmax, hq = kn.graphconv_pool_fwd_s(Y2s, idx, image, gs2, qenc, B, K)
+            del Y2s
+        else:
+            Y2 = _gemm_s(G1s, Wc2s)
+            pooled, argmax, hq = kn.graphconv_pool_fwd(Y2, idx, image, gs2, qenc, B, K)
 
         # classifier
         hqs = _split(hq)
@@ -182,7 +197,7 @@ class ConditionedGraphFn(torch.autograd.Function):
         o1s = _split(o1)
         logits = _gemm_s(o1s, Wo2s, bias=bo2)
 
-        ctx.cfg = dict(B=B, K=K, F=F, H=H, nk=nk, nb=nb, scale=scale)
+        ctx.cfg = dict(B=B, K=K, F=F, H=H, nk=nk, nb=nb, scale=scale, mma1=mma1)
         ctx.splits = (Xs, qs, h1s, G1s, hqs, o1s, W1qs, W2s, Wo1s, Wo2s, Wc1s, Wc2s)
         ctx.save_for_backward(image, qenc, v1, g1, v2, g2, vo1, go1, vo2, go2, gs1, gs2, h2, idx, alpha, Y1, Y2, pooled, argmax)
         ctx.mark_non_differentiable(argmax)
@@ -214,10 +229,16 @@ class ConditionedGraphFn(torch.autograd.Function):
         dY2, _, dgs2 = kn.graphconv_bwd(Y2, idx, None, image, gs2, B, K, dpooled=dpooled, argmax=argmax)
         dY2s = _split(dY2)
         dWc2 = _gemm_s(dY2s, G1s, a_mn=True, b_mn=True, split_k=_split_for(Wc2s.rows, Wc2s.cols, M))
-        dG1 = _gemm_s(dY2s, Wc2s, b_mn=True, aux=G1s, aux_scale=scale)
         # graph convolution 1
-        dY1, dalpha, dgs1 = kn.graphconv_bwd(Y1, idx, alpha, image, gs1, B, K, dO=dG1)
-        dY1s = _split(dY1)
+        if c["mma1"]:
+            dG1s = kn.empty_split(M, G1s.cols, dev, with_lo)
+            dG1 = _gemm_s(dY2s, Wc2s, b_mn=True, aux=G1s, aux_scale=scale, out_split=dG1s)
+            dY1s = kn.graphconv_bwd_data_s(dG1s, idx, alpha, image, gs1, B, K)          # dY = M^T dO on the tensor cores
+            _, dalpha, dgs1 = kn.graphconv_bwd(Y1, idx, alpha, image, gs1, B, K, dO=dG1, want_dY=False)
+        else:
+            dG1 = _gemm_s(dY2s, Wc2s, b_mn=True, aux=G1s, aux_scale=scale)
+            dY1, dalpha, dgs1 = kn.graphconv_bwd(Y1, idx, alpha, image, gs1, B, K, dO=dG1)
+            dY1s = _split(dY1)
         dWc1 = _gemm_s(dY1s, Xs, a_mn=True, b_mn=True, split_k=_split_for(Wc1s.rows, Wc1s.cols, M))
 
         # graph learner

@@ -53,6 +53,9 @@ WORKLOADS = {
                      neighbourhood=5, max_qlen=6, q_width=10, dropout=0.0),
     "small": Workload("small", 8, 36, 132, hid_dim=128, emb_dim=32, out_dim=200, vocab=300,
                       n_kernels=8, neighbourhood=16, max_qlen=14, q_width=20, dropout=0.0),
+    # smallest shape whose graph convolutions take the tensor-core aggregate path ((2*hid/nk) % 128 == 0 and (hid/nk) % 128 == 0)
+    "medium": Workload("medium", 6, 36, 68, hid_dim=512, emb_dim=32, out_dim=120, vocab=200,
+                       n_kernels=4, neighbourhood=16, max_qlen=9, q_width=12, dropout=0.0),
 }
 
 
