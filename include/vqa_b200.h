@@ -117,7 +117,7 @@ int vqa_graphconv_pool_fwd_f32(const float* Y, long long ldy, const int* idx, co
 /* Backward data path of the aggregate.  Upstream gradient is either dense dO (B,K,out) (already ReLU/dropout
  * masked) or, for the pooled layer, dpooled (B,out) + argmax (scatter by argmax is done on the fly).
  * Writes dY (B,K,out) (skipped when dY is NULL) and the per-edge, per-kernel dot products
- * P (B,K,nb,nk) = <dO[i,chunk k], Y[idx,chunk k]>. */
+ * P (B,K,nb,nk) = <dO[i,chunk k], Y[idx,chunk k]> (skipped when P is NULL; Y may then be NULL too). */
 int vqa_graphconv_bwd_f32(const float* dO, long long lddo, const float* dpooled, const long long* argmax,
                           const float* Y, long long ldy, const int* idx, const float* alpha, const float* boxes,
                           long long ldbox, const float* gauss, float* dY, long long lddy, float* P, int B, int K,
@@ -145,6 +145,18 @@ int vqa_graphconv_mma_pool_fwd(const void* Y_hi, const void* Y_lo, long long ldy
 int vqa_graphconv_mma_bwd_data(const void* dO_hi, const void* dO_lo, long long lddo, const int* idx, const float* alpha,
                                const float* boxes, long long ldbox, const float* gauss, void* dY_hi, void* dY_lo,
                                long long lddy, int B, int K, int nb, int nk, int out_dim, vqa_stream_t stream);
+
+/* Edge part of the backward on the tensor cores: P[i,m,k] = <dO[i,chunk k], Y[idx[i,m],chunk k]> per image as
+ * dO_k Y_k^T, then dalpha (B,K,nb) (NULL when alpha is NULL) and the per-image partial sums of the Gaussian-parameter
+ * gradients dgauss_partial (B, 4*nk) (reduce over B with vqa_colsum_f32).  Upstream: dO planes, or (dpooled, argmax)
+ * with dO_hi == NULL for the pooled layer.  p_scratch: (B,K,nb,nk) floats, needed only when K*nb*nk*4 B > 48 KB
+ * (the selected products then round-trip through L2 instead of shared memory).  Requires (out_dim / nk) % 64 == 0.
+ * SURVEY.md 9.2. */
+int vqa_graphconv_mma_bwd_edges(const void* dO_hi, const void* dO_lo, long long lddo, const float* dpooled,
+                                const long long* argmax, const void* Y_hi, const void* Y_lo, long long ldy, const int* idx,
+                                const float* alpha, const float* boxes, long long ldbox, const float* gauss, float* dalpha,
+                                float* dgauss_partial, float* p_scratch, int B, int K, int nb, int nk, int out_dim,
+                                vqa_stream_t stream);
 
 /* Gaussian patch weights for explicit pseudo-coordinates (n,2) -> (n,nk): NeighbourhoodGraphConvolution.
  * get_gaussian_weights, layers.py:100-125 (layer-level API). */

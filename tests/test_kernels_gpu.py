@@ -423,7 +423,7 @@ def test_graphconv_bwd(kn, B, K, nb, nk, out_dim, mode):
 
 
 # ---- tensor-core aggregate on split planes (graphconv_mma.cu) -----------------------------------------------------
-MMA_CASES = [(4, 36, 16, 8, 2048), (3, 36, 16, 8, 1024), (2, 51, 19, 4, 512), (2, 100, 32, 8, 1024), (3, 12, 5, 2, 256), (2, 7, 7, 1, 128)]
+MMA_CASES = [(4, 36, 16, 8, 2048), (3, 36, 16, 8, 1024), (2, 51, 19, 4, 512), (2, 100, 32, 8, 1024), (3, 12, 5, 2, 256), (2, 7, 7, 2, 256)]
 
 
 @pytest.mark.parametrize("B,K,nb,nk,out_dim", MMA_CASES)
@@ -493,6 +493,35 @@ def test_graphconv_mma_bwd_data(kn, B, K, nb, nk, out_dim, use_alpha):
     dY = kn.graphconv_bwd_data_s(kn.split(dO.float().view(B * K, -1).to(DEV)), idx.int().to(DEV), alpha.float().to(DEV) if use_alpha else None,
                                  image.float().to(DEV), _pack_gauss(gp, "gc"), B, K)
     assert rel_err(dY.float().view(B, K, -1).cpu(), dY_ref) < 3e-5
+
+
+@pytest.mark.parametrize("B,K,nb,nk,out_dim", MMA_CASES)
+@pytest.mark.parametrize("mode", ["dense_alpha", "dense", "pooled"])
+def test_graphconv_mma_bwd_edges(kn, B, K, nb, nk, out_dim, mode):
+    image, Y, idx, alpha, gp = _gc_inputs(B, K, nb, nk, out_dim, seed=3 * K + nb)
+    ar = alpha.clone().requires_grad_(True)
+    gpr = {k: v.clone().requires_grad_(True) for k, v in gp.items()}
+    use_alpha = mode == "dense_alpha"
+    out = _gc_reference(Y, idx, ar if use_alpha else None, image, gpr, "gc", nk)
+    g = torch.Generator().manual_seed(1)
+    Ys = kn.split(Y.float().view(B * K, -1).to(DEV))
+    common = (Ys, idx.int().to(DEV), alpha.float().to(DEV) if use_alpha else None, image.float().to(DEV), _pack_gauss(gp, "gc"), B, K)
+    if mode == "pooled":
+        arg = torch.randint(0, K, (B, out_dim), generator=g)
+        dpooled = torch.randn(B, out_dim, generator=g, dtype=torch.float64)
+        dO = torch.zeros(B, K, out_dim, dtype=torch.float64).scatter_(1, arg.unsqueeze(1), dpooled.unsqueeze(1))
+        dalpha, dgauss = kn.graphconv_bwd_edges_s(*common, dpooled=dpooled.float().to(DEV), argmax=arg.to(DEV))
+    else:
+        dO = torch.randn(B, K, out_dim, generator=g, dtype=torch.float64)
+        dalpha, dgauss = kn.graphconv_bwd_edges_s(*common, dOs=kn.split(dO.float().view(B * K, -1).to(DEV)))
+    wanted = [gpr[f"gc.{k}"] for k in ("mean_rho", "precision_rho", "mean_theta", "precision_theta")] + ([ar] if use_alpha else [])
+    grads = torch.autograd.grad((out * dO).sum(), wanted)
+    dg_ref = torch.cat([x.reshape(-1) for x in grads[:4]])
+    assert rel_err(dgauss.cpu(), dg_ref) < 2e-4
+    if use_alpha:
+        assert rel_err(dalpha.cpu(), grads[4]) < 3e-5
+    else:
+        assert dalpha is None
 
 
 def test_gaussian_weights_match_reference_golden(kn):

@@ -28,3 +28,8 @@ timeit("mma fwd L1 relu (bf16 planes)", lambda: kn.graphconv_fwd_s(kn.SplitT(Y1s
 timeit("mma pool fwd L2", lambda: kn.graphconv_pool_fwd_s(Y2s, idx, img, gauss, q, B, K), M * 1024 * 4 + M * nb * 4 + M * 16 + 4 * B * 1024 * 4)
 timeit("mma bwd data L1", lambda: kn.graphconv_bwd_data_s(Y1s, idx, alpha, img, gauss, B, K), b1)
 timeit("mma bwd data L2", lambda: kn.graphconv_bwd_data_s(Y2s, idx, None, img, gauss, B, K), 2 * M * 1024 * 4 + M * nb * 4 + M * 16)
+dO1s = kn.split(torch.randn(M, 2048, device=dev))
+timeit("mma bwd edges L1 (P + edge finish)", lambda: kn.graphconv_bwd_edges_s(Y1s, idx, alpha, img, gauss, B, K, dOs=dO1s), 2 * M * 2048 * 4 + 3 * M * nb * 4)
+pooled, arg, hq = kn.graphconv_pool_fwd_s(Y2s, idx, img, gauss, q, B, K)
+dp = torch.randn(B, 1024, device=dev)
+timeit("mma bwd edges L2 (pooled upstream)", lambda: kn.graphconv_bwd_edges_s(Y2s, idx, None, img, gauss, B, K, dpooled=dp, argmax=arg), M * 1024 * 4 + M * nb * 4)

@@ -401,7 +401,7 @@ static int dense_launch(const DenseParams& base, int B, cudaStream_t stream) {
   const int KT = K <= 36 ? 36 : (K <= 52 ? 52 : (K <= 64 ? 64 : (K <= 100 ? 100 : 128)));
   const int VEC = (KT == 36 && D % 128 == 0 && (p.ldo % 4) == 0) ? 4 : (KT <= 64 ? 2 : 1);
   const int TWD = 32 * VEC, dup = VEC >= 2 ? 2 : 1;
-  if (K > 128 || D % TWD != 0 || (p.ldin % 4) != 0 || (p.ldo % VEC) != 0) return 1;
+  if (K > 128 || D % TWD != 0 || (MODE != DM_BWD_POOLED && (p.ldin % 4) != 0) || (p.ldo % VEC) != 0) return 1;
   p.D = D;
   p.ntiles = p.out_dim / TWD;
   const int tpk = D / TWD;                                    // tiles per kernel
@@ -931,9 +931,9 @@ extern "C" int vqa_graphconv_bwd_f32(const float* dO, long long lddo, const floa
                                      int nb, int nk, int out_dim, cudaStream_t stream) {
   const char* who = "vqa_graphconv_bwd_f32";
   const bool pooled = dO == nullptr;
-  VQA_CHECK_ARG(Y && idx && boxes && gauss && P, "%s: null pointer", who);
+  VQA_CHECK_ARG(idx && boxes && gauss && (P || dY) && (Y || !P), "%s: null pointer", who);
   VQA_CHECK_ARG(pooled ? (dpooled && argmax) : true, "%s: need either dO or (dpooled, argmax)", who);
-  VQA_CHECK_ARG(aligned16(Y) && (ldy & 3) == 0 && (!dY || (aligned16(dY) && (lddy & 3) == 0)), "%s: Y/dY alignment", who);
+  VQA_CHECK_ARG((!Y || (aligned16(Y) && (ldy & 3) == 0)) && (!dY || (aligned16(dY) && (lddy & 3) == 0)), "%s: Y/dY alignment", who);
   VQA_CHECK_ARG(pooled ? aligned16(dpooled) : (aligned16(dO) && (lddo & 3) == 0), "%s: upstream gradient alignment", who);
   bool dy_done = dY == nullptr;            // dY == NULL: the caller computes dY elsewhere (tensor-core path); only P is wanted
   if (!dy_done && K <= 128 && nb <= K && nk <= MAX_NK && out_dim % nk == 0) {   // dY = M^T dO on the dense-register kernel
@@ -944,6 +944,10 @@ extern "C" int vqa_graphconv_bwd_f32(const float* dO, long long lddo, const floa
     const int rc = pooled ? dense_launch<DM_BWD_POOLED>(dp, B, stream) : dense_launch<DM_BWD_DENSE>(dp, B, stream);
     if (rc < 0) return rc;
     dy_done = rc == 0;
+  }
+  if (!P) {   // data path only: the edge products are computed elsewhere (tensor-core path)
+    if (dy_done) return VQA_OK;
+    return vqa_fail(VQA_ERR_UNSUPPORTED, "%s: dY-only mode needs a shape the dense kernel supports", who);
   }
   GcPlan pl;
   if (int rc = gc_plan(&pl, B, K, nb, nk, out_dim, true, false, pooled, who)) return rc;

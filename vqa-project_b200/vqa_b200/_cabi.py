@@ -45,6 +45,7 @@ SIGNATURES = {
     "vqa_graphconv_mma_fwd": [_p, _p, _ll, _p, _p, _p, _ll, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _f, _u64, _u64, _p, _p],
     "vqa_graphconv_mma_pool_fwd": [_p, _p, _ll, _p, _p, _ll, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "vqa_graphconv_mma_bwd_data": [_p, _p, _ll, _p, _p, _p, _ll, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _p],
+    "vqa_graphconv_mma_bwd_edges": [_p, _p, _ll, _p, _p, _p, _p, _ll, _p, _p, _p, _ll, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "vqa_graphconv_edge_blocks": [_i, _i, _i],
     "vqa_graphconv_edge_bwd_f32": [_p, _p, _p, _p, _ll, _p, _p, _p, _i, _i, _i, _i, _p],
     "vqa_gaussian_weights_f32": [_p, _p, _p, _ll, _i, _p],

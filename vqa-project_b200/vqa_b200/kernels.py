@@ -313,25 +313,31 @@ def graphconv_pool_fwd(Y, idx, image, gauss, q, B, K):
     return pooled, argmax, hq
 
 
-def graphconv_bwd(Y, idx, alpha, image, gauss, B, K, dO=None, dpooled=None, argmax=None, want_dY=True):
-    """-> dY (B*K,out) (None when ``want_dY`` is False), dalpha (B,K,nb) or None, dgauss (4*nk,)"""
-    Y, ldy = _rows_view(_chk(Y, "graphconv Y"), "graphconv Y")
+def graphconv_bwd(Y, idx, alpha, image, gauss, B, K, dO=None, dpooled=None, argmax=None, want_dY=True, want_edges=True, out_dim=None):
+    """-> dY (B*K,out) (None when ``want_dY`` is False), dalpha (B,K,nb) or None, dgauss (4*nk,) (None when ``want_edges``
+    is False; ``Y`` may then be None and ``out_dim`` must be given)."""
     nb = idx.shape[-1]
     nk = gauss.numel() // 4
-    out_dim = Y.shape[1]
+    ldy = 0
+    if Y is not None:
+        Y, ldy = _rows_view(_chk(Y, "graphconv Y"), "graphconv Y")
+        out_dim = Y.shape[1]
+    dev = idx.device
     bptr, ldbox = _boxes_view(image)
-    dY = torch.empty((B * K, out_dim), device=Y.device, dtype=torch.float32) if want_dY else None
-    P = torch.empty((B, K, nb, nk), device=Y.device, dtype=torch.float32)
+    dY = torch.empty((B * K, out_dim), device=dev, dtype=torch.float32) if want_dY else None
+    P = torch.empty((B, K, nb, nk), device=dev, dtype=torch.float32) if want_edges else None
     lddo = 0
     if dO is not None:
         dO, lddo = _rows_view(_chk(dO, "graphconv dO"), "graphconv dO")
     else:
         dpooled = _chk(dpooled, "dpooled").contiguous()
-    _call("vqa_graphconv_bwd_f32", _ptr(dO), lddo, _ptr(dpooled), _ptr(argmax), Y.data_ptr(), ldy, idx.data_ptr(),
-          _ptr(alpha), bptr, ldbox, gauss.data_ptr(), _ptr(dY), out_dim, P.data_ptr(), B, K, nb, nk, out_dim, _stream())
+    _call("vqa_graphconv_bwd_f32", _ptr(dO), lddo, _ptr(dpooled), _ptr(argmax), _ptr(Y), ldy, idx.data_ptr(),
+          _ptr(alpha), bptr, ldbox, gauss.data_ptr(), _ptr(dY), out_dim, _ptr(P), B, K, nb, nk, out_dim, _stream())
+    if not want_edges:
+        return dY, None, None
     nblk = _cabi.load().vqa_graphconv_edge_blocks(B, K, nb)
-    partial = torch.empty((nblk, 4 * nk), device=Y.device, dtype=torch.float32)
-    dalpha = torch.empty((B, K, nb), device=Y.device, dtype=torch.float32) if alpha is not None else None
+    partial = torch.empty((nblk, 4 * nk), device=dev, dtype=torch.float32)
+    dalpha = torch.empty((B, K, nb), device=dev, dtype=torch.float32) if alpha is not None else None
     _call("vqa_graphconv_edge_bwd_f32", P.data_ptr(), idx.data_ptr(), _ptr(alpha), bptr, ldbox, gauss.data_ptr(),
           _ptr(dalpha), partial.data_ptr(), B, K, nb, nk, _stream())
     dgauss = colsum(partial)
@@ -375,6 +381,22 @@ def graphconv_bwd_data_s(dOs: SplitT, idx, alpha, image, gauss, B, K) -> SplitT:
     _call("vqa_graphconv_mma_bwd_data", dOs.hi.data_ptr(), _ptr(dOs.lo), dOs.ld, idx.data_ptr(), _ptr(alpha), bptr, ldbox, gauss.data_ptr(),
           out.hi.data_ptr(), _ptr(out.lo), out.ld, B, K, nb, nk, out_dim, _stream())
     return out
+
+
+def graphconv_bwd_edges_s(Ys: SplitT, idx, alpha, image, gauss, B, K, dOs: Optional[SplitT] = None, dpooled=None, argmax=None):
+    """Edge part of the backward on planes -> (dalpha (B,K,nb) or None, dgauss (4*nk,))."""
+    nb, nk, out_dim = idx.shape[-1], gauss.numel() // 4, Ys.cols
+    bptr, ldbox = _boxes_view(image)
+    dev = Ys.hi.device
+    dalpha = torch.empty((B, K, nb), device=dev, dtype=torch.float32) if alpha is not None else None
+    partial = torch.empty((B, 4 * nk), device=dev, dtype=torch.float32)
+    if dOs is None:
+        dpooled = _chk(dpooled, "dpooled").contiguous()
+    scratch = torch.empty((B, K, nb, nk), device=dev, dtype=torch.float32) if K * nb * nk * 4 > 48 * 1024 else None
+    _call("vqa_graphconv_mma_bwd_edges", None if dOs is None else dOs.hi.data_ptr(), None if dOs is None else _ptr(dOs.lo),
+          0 if dOs is None else dOs.ld, _ptr(dpooled), _ptr(argmax), Ys.hi.data_ptr(), _ptr(Ys.lo), Ys.ld, idx.data_ptr(), _ptr(alpha),
+          bptr, ldbox, gauss.data_ptr(), _ptr(dalpha), partial.data_ptr(), _ptr(scratch), B, K, nb, nk, out_dim, _stream())
+    return dalpha, colsum(partial)
 
 
 def gaussian_weights(pseudo: torch.Tensor, gauss: torch.Tensor) -> torch.Tensor:
