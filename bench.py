@@ -33,7 +33,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="vqa2_b512")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_strict", "bf16"],
                     help="fp32: split-bf16 3-pass tcgen05 GEMMs (fp32-grade, the parity mode); bf16: 1-pass bf16 tensor-core GEMMs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying the captured CUDA graph")
@@ -102,7 +102,8 @@ def config_dict(w, args, world):
     return {"workload": f"{w.name}: VQA2 conditioned-graph train step, per-GPU batch {w.batch}, K={w.n_obj} boxes x {w.feat_dim}-d, "
                         f"<= {w.max_qlen}-token questions, top-k={w.neighbourhood}, {w.n_kernels} Gaussian kernels, {w.out_dim} answers, dropout {w.dropout}",
             "global_batch": w.batch * world, "step": "zero_grad+forward+MultiLabelSoftMarginLoss+backward+allreduce+Adam, " + ("eager launches" if args.no_graph else "one CUDA-graph replay per step (vqa_b200.engine.TrainStep)"),
-            "parallelism": f"dp{world}", "gru": "padded masked recurrence on split-bf16 x3 tcgen05 GEMMs (fp32-grade)", "gemm_precision": "split-bf16 x3 passes (fp32-grade, rel err ~1e-5) + chunk-promoted 3xTF32 graph-learner forward" if args.precision == "fp32" else "bf16 x1 pass (graph-learner forward fp32-grade)",
+            "parallelism": f"dp{world}", "gru": "padded masked recurrence on split-bf16 x3 tcgen05 GEMMs (fp32-grade)", "gemm_precision": {"fp32": "split-bf16 x3 passes (fp32-grade, rel err ~1e-5)", "fp32_strict": "split-bf16 x3 passes + chunk-promoted 3xTF32 graph-learner forward",
+                                   "bf16": "bf16 x1 pass (graph-learner forward x3 passes)"}[args.precision],
             "l2_policy": "inputs larger than L2 (image batch 151 MB > 126 MB), 3 rotating batches"}
 
 
@@ -308,7 +309,7 @@ def run_b200(args, workload):
     line = {
         "metric": "train questions/sec (fwd+bwd)", "value": round(value, 1), "unit": "questions/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": config_dict(w, args, world),
         "e2e": {"value": round(e2e_value, 1), "unit": "questions/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e, 4), "last_loss": last_loss},

@@ -56,6 +56,12 @@ int vqa_gemm_f32(const float* A, long long lda, int a_mn_major, const float* B, 
 int vqa_split_bf16_f32(const float* x, long long ldx, void* hi, void* lo, long long ldp, long long rows, int cols,
                        vqa_stream_t stream);
 
+/* Inverted dropout fused with the split: planes of dropout(x); same RNG family and step_ptr convention as
+ * vqa_dropout_f32 (counter = (row * ceil(cols/4) + col/4, offset)).  sparse_graph_model.py:111 feeding the projections. */
+int vqa_dropout_split_f32(const float* x, long long ldx, void* hi, void* lo, long long ldp, long long rows, int cols, float p,
+                          unsigned long long seed, unsigned long long offset, const unsigned long long* step_ptr,
+                          vqa_stream_t stream);
+
 /* C[M,N] = epi( sum_k A[m,k] * B[n,k] ) with A = A_hi + A_lo, B = B_hi + B_lo given as bf16 planes (kind::f16
  * tcgen05.mma, fp32 TMEM accumulator).  passes = 3: lo*hi + hi*lo + hi*hi (fp32-grade, ~2^-17 per product);
  * passes = 1: hi planes only (bf16 mode).  Same operand-major convention, epilogue and call sites as vqa_gemm_f32;

@@ -114,6 +114,20 @@ def test_split_planes_reconstruct_fp32(kn):
     assert h.lo is None and (h.hi[:, :2052] == s.hi[:, :2052]).all()
 
 
+def test_dropout_split_matches_dropout_then_split(kn):
+    x = torch.randn(37, 2052, device=DEV)
+    for p in (0.5, 0.4):
+        ref = kn.dropout(x, p, seed=77, offset=5)                    # cols % 4 == 0: identical Philox counters -> identical mask
+        s = kn.dropout_split(x, p, seed=77, offset=5)
+        assert torch.equal(s.float() != 0, ref != 0)
+        assert rel_err(s.float().cpu(), ref.cpu()) < 2 ** -16
+    y = torch.randn(11, 30, device=DEV)                              # ragged width: statistics only
+    s = kn.dropout_split(y.repeat(200, 1), 0.5, seed=1, offset=1)
+    assert abs((s.float() != 0).float().mean().item() - 0.5) < 0.02
+    step = torch.tensor(3, dtype=torch.int64, device=DEV)
+    assert not torch.equal(kn.dropout_split(x, 0.5, 77, 5, step).hi, kn.dropout_split(x, 0.5, 77, 5).hi)
+
+
 @pytest.mark.parametrize("M,N,K,a_mn,b_mn,tile_n", GEMM_CASES)
 @pytest.mark.parametrize("passes,tol", [(3, 3e-5), (1, 8e-3)])
 def test_gemm_split_bf16_matches_fp64(kn, M, N, K, a_mn, b_mn, tile_n, passes, tol):

@@ -86,7 +86,7 @@ def test_model_forward_backward_matches_reference(name):
     assert worst[1] < 5e-4
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp32_strict", "bf16"])
 def test_model_tensor_core_aggregate_path_matches_oracle(precision):
     """'medium' is the smallest shape on which both graph convolutions run the tcgen05 aggregate (graphconv_mma.cu); the
     golden workloads above take the CUDA-core fallback.  Checker: the oracle (pinned to the reference by
@@ -114,7 +114,7 @@ def test_model_tensor_core_aggregate_path_matches_oracle(precision):
                                                                         b["target"], w.neighbourhood, w.n_kernels)
     # bf16 mode, stated tolerance: logits 2e-2, weight gradients 1e-1, Gaussian-kernel parameter gradients (sums of
     # cancelling per-edge terms) 2e-1 -- max-norm relative
-    tol_out, tol_grad, tol_gauss = (TIGHT, 5e-4, 5e-4) if precision == "fp32" else (2e-2, 1e-1, 2e-1)
+    tol_out, tol_grad, tol_gauss = (TIGHT, 5e-4, 5e-4) if precision != "bf16" else (2e-2, 1e-1, 2e-1)
     assert rel_err(adj.detach().cpu(), ref_adj) < TIGHT          # graph-learner forward is fp32-grade in both modes
     assert rel_err(logits.detach().cpu(), ref_logits) < tol_out
     worst = ("", 0.0)

@@ -375,6 +375,42 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x,
   }
 }
 
+// fused inverted dropout + split: hi/lo planes of dropout(x) in one pass (x read once, no fp32 intermediate).
+// Mask: Philox4x32-10(seed; counter = (row * ceil(cols/4) + col/4, offset)), one call per 4 consecutive columns.
+__global__ void __launch_bounds__(256) dropout_split_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ hi,
+                                                           __nv_bfloat16* __restrict__ lo, long long ldp, long long rows, int cols,
+                                                           float p, float scale, unsigned long long seed, unsigned long long offset,
+                                                           const unsigned long long* __restrict__ step_ptr, int vec) {
+  const Philox rng(seed);
+  if (step_ptr) offset += *step_ptr * 16ull;
+  const int groups = (cols + 7) >> 3, q4 = (cols + 3) >> 2;
+  const long long total = rows * groups;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+    const long long r = g / groups;
+    const int c = (int)(g - r * groups) << 3;
+    const float* src = x + r * ldx + c;
+    float v[8];
+    if (vec && c + 8 <= cols) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = c + e < cols ? src[e] : 0.f;
+    }
+    const uint4 r0 = rng((unsigned long long)(r * q4 + (c >> 2)), offset), r1 = rng((unsigned long long)(r * q4 + (c >> 2) + 1), offset);
+    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = u32_to_unit(rr[e]) >= p ? v[e] * scale : 0.f;
+    float h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
+    *reinterpret_cast<uint4*>(hi + r * ldp + c) = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+    if (lo)
+      *reinterpret_cast<uint4*>(lo + r * ldp + c) = make_uint4(pack_bf16(v[0] - h[0], v[1] - h[1]), pack_bf16(v[2] - h[2], v[3] - h[3]),
+                                                               pack_bf16(v[4] - h[4], v[5] - h[5]), pack_bf16(v[6] - h[6], v[7] - h[7]));
+  }
+}
+
 }  // namespace sb
 }  // namespace vqa
 
@@ -443,4 +479,21 @@ extern "C" int vqa_gemm_bf16s(const void* A_hi, const void* A_lo, long long lda,
   if (bn == 128) return VQA_DISPATCH(128);
   return VQA_DISPATCH(64);
 #undef VQA_DISPATCH
+}
+
+extern "C" int vqa_dropout_split_f32(const float* x, long long ldx, void* hi, void* lo, long long ldp, long long rows, int cols, float p,
+                                     unsigned long long seed, unsigned long long offset, const unsigned long long* step_ptr,
+                                     cudaStream_t stream) {
+  VQA_CHECK_ARG(x && hi && rows > 0 && cols > 0, "vqa_dropout_split_f32: bad arguments");
+  VQA_CHECK_ARG(p >= 0.f && p < 1.f, "vqa_dropout_split_f32: p must be in [0,1)");
+  VQA_CHECK_ARG((ldp & 7) == 0 && ldp >= ((cols + 7) & ~7) && aligned16(hi) && (!lo || aligned16(lo)),
+                "vqa_dropout_split_f32: planes need 16-byte aligned rows with ld %% 8 == 0 and ld >= cols rounded up to 8");
+  const int vec = aligned16(x) && (ldx & 3) == 0;
+  const long long groups = rows * ((cols + 7) >> 3);
+  long long blocks = (groups + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  sb::dropout_split_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, ldx, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo),
+                                                                ldp, rows, cols, p, 1.f / (1.f - p), seed, offset, step_ptr, vec);
+  VQA_LAUNCH_CHECK("dropout_split_kernel");
+  return VQA_OK;
 }

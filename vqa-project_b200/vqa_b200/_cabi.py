@@ -29,6 +29,7 @@ _u64 = C.c_ulonglong
 SIGNATURES = {
     "vqa_gemm_f32": [_p, _ll, _i, _p, _ll, _i, _p, _ll, _i, _i, _i, _p, _p, _ll, _i, _p, _ll, _f, _i, _i, _i, _i, _p],
     "vqa_split_bf16_f32": [_p, _ll, _p, _p, _ll, _ll, _i, _p],
+    "vqa_dropout_split_f32": [_p, _ll, _p, _p, _ll, _ll, _i, _f, _u64, _u64, _p, _p],
     "vqa_gemm_bf16s": [_p, _p, _ll, _i, _p, _p, _ll, _i, _p, _ll, _p, _p, _ll, _i, _i, _i, _p, _p, _ll, _i, _p, _ll, _p, _ll,
                        _f, _i, _i, _i, _i, _p],
     "vqa_dropout_f32": [_p, _p, _ll, _f, _u64, _u64, _p, _p],

@@ -143,6 +143,16 @@ def split(x: torch.Tensor, with_lo: bool = True) -> SplitT:
     return out
 
 
+def dropout_split(x: torch.Tensor, p: float, seed: int, offset: int, step: Optional[torch.Tensor] = None, with_lo: bool = True) -> SplitT:
+    """Planes of dropout(x) for a 2-D fp32 x (rows, cols) in one pass."""
+    x, ldx = _rows_view(_chk(x, "dropout_split x"), "dropout_split x")
+    rows, cols = x.shape
+    out = empty_split(rows, cols, x.device, with_lo)
+    _call("vqa_dropout_split_f32", x.data_ptr(), ldx, out.hi.data_ptr(), _ptr(out.lo), out.ld, rows, cols, float(p), seed, offset,
+          _ptr(step), _stream())
+    return out
+
+
 def gemm_s(a: SplitT, b: SplitT, *, a_mn: bool = False, b_mn: bool = False, out: Optional[torch.Tensor] = None,
            out_split: Optional[SplitT] = None, want_f32: bool = True, bias: Optional[torch.Tensor] = None,
            rowbcast: Optional[torch.Tensor] = None, group: int = 1, aux=None, aux_scale: float = 1.0, relu: bool = False,
