@@ -41,6 +41,10 @@ def parse():
     return ap.parse_args()
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/), bytes
+NCU_TRAFFIC = {}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -146,6 +150,11 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+def _dbg(msg):
+    if os.environ.get("VQA_BENCH_DEBUG"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_b200(args, workload):
     import torch.distributed as dist
     from vqa_b200 import kernels as kn, ops
@@ -165,11 +174,13 @@ def run_b200(args, workload):
         dist.init_process_group("nccl", device_id=dev)
     ops.set_precision(args.precision)
     w = workload
+    _dbg("process group up")
 
     torch.manual_seed(1000)
     model = M.Model(pretrained_wemb=make_wemb(w), **w.model_kwargs()).to(dev)
     model.max_question_len = w.max_qlen
     broadcast_parameters(model)
+    _dbg("parameters broadcast")
     model.train()
     criterion = torch.nn.MultiLabelSoftMarginLoss()
     reducer = GradReducer(model.parameters())
@@ -206,6 +217,9 @@ def run_b200(args, workload):
     # ---- device-resident throughput ------------------------------------------------------------
     for i in range(max(args.warmup, 3)):
         run(resident[i % NB])
+        if i == 0:
+            torch.cuda.synchronize()
+            _dbg("first step (capture) done")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -217,6 +231,7 @@ def run_b200(args, workload):
     e1.record()
     barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
+    _dbg(f"resident loop done: {ms_total / args.steps:.3f} ms/step")
     launches = step.launches_per_step
     sampler.stop_flag = True
     ms_step = ms_total / args.steps
@@ -245,27 +260,37 @@ def run_b200(args, workload):
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    _dbg(f"e2e loop done: {ms_e2e:.3f} ms/step")
     e2e_value = w.batch * world / (ms_e2e * 1e-3)
 
     # ---- per-kernel CUDA-event times: an eager pass over the same step (individual launches cannot be bracketed inside a
     # graph replay), same inputs, same stream ------------------------------------------------------------------
     GC, ADJ = "vqa_graphconv_fwd_f32", "vqa_adjacency_topk_fwd_f32"
+    # every rank runs it (the gradient all-reduce inside the step is a collective); rank 0 reads the timers
     timers = {}
-    if rank == 0:
-        eager = TrainStep(model, opt, criterion, reducer=reducer, use_graph=False, seed=99)
-        for i in range(3):
-            eager(*(resident[i % NB][k] for k in keys))
-        kn.enable_timing(GC, ADJ, "vqa_graphconv_bwd_f32", "vqa_graphconv_pool_fwd_f32", "vqa_adjacency_topk_bwd_f32", "vqa_gemm_bf16s")
-        for i in range(6):
-            eager(*(resident[i % NB][k] for k in keys))
-        torch.cuda.synchronize()
-        timers = {k: [a.elapsed_time(b) for a, b in v] for k, v in kn.TIMERS.items()}
-        kn.enable_timing()
+    eager = TrainStep(model, opt, criterion, reducer=reducer, use_graph=False, seed=99)
+    for i in range(3):
+        eager(*(resident[i % NB][k] for k in keys))
+    kn.enable_timing(GC, ADJ, "vqa_graphconv_mma_fwd", "vqa_graphconv_mma_pool_fwd", "vqa_graphconv_mma_bwd_data", "vqa_graphconv_mma_bwd_edges",
+                     "vqa_adjacency_topk_bwd_f32", "vqa_gemm_bf16s")
+    for i in range(6):
+        eager(*(resident[i % NB][k] for k in keys))
+    torch.cuda.synchronize()
+    timers = {k: [a.elapsed_time(b) for a, b in v] for k, v in kn.TIMERS.items()}
+    kn.enable_timing()
+    _dbg("eager timing pass done")
     barrier()
 
-    if rank != 0:
+    def leave():
+        """Multi-rank runs end with a hard exit after a final barrier: tearing down NCCL communicators that captured CUDA
+        graphs still reference can block in destroy_process_group (seen at N=2), and there is nothing left to clean up."""
         if world > 1:
-            dist.destroy_process_group()
+            barrier()
+            sys.stdout.flush(); sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        leave()
         return
 
     # ---- roofline of the graph kernels (algorithmic bytes, SURVEY.md 8d / DESIGN.md) --------------------------
@@ -277,28 +302,41 @@ def run_b200(args, workload):
         xs = sorted(xs)
         return xs[len(xs) // 2] if xs else None
 
-    gc_ms = med(timers.get(GC, []))
-    gc_bytes = 2 * Mrows * 2 * H * 4 + 2 * Mrows * nb * 4 + Mrows * 16      # read Y1 + write G1 + idx/alpha + boxes
+    GCM = "vqa_graphconv_mma_fwd"
+    gc_name = GCM if timers.get(GCM) else GC
+    gc_ms = med(timers.get(gc_name, []))
+    gc_bytes = 2 * Mrows * 2 * H * 4 + 2 * Mrows * nb * 4 + Mrows * 16      # read Y1 + write G1 (4 B/element each: fp32 or hi+lo bf16) + idx/alpha + boxes
     roof = None
     extra = {}
     if gc_ms:
         ach = gc_bytes / (gc_ms * 1e-3) / 1e9
-        roof = {"kernel": "graphconv_fwd_kernel (layer 1: Gaussian weights + gather + aggregate + ReLU + dropout)", "bound": "hbm",
-                "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "traffic": None,
-                "algorithmic_bytes": gc_bytes, "us_per_launch": round(gc_ms * 1e3, 2), "peak_source": peak_src}
+        roof = {"kernel": gc_name + " (layer 1: Gaussian weights on selected edges + neighbourhood aggregate + ReLU + dropout)", "bound": "hbm",
+                "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "traffic": NCU_TRAFFIC.get(gc_name),
+                "algorithmic_bytes": gc_bytes, "us_per_launch": round(gc_ms * 1e3, 2), "peak_source": peak_src,
+                "timed": "CUDA events on the launching stream in an eager pass of the same step (launches inside a graph replay cannot be bracketed)"}
     alg = {ADJ: Mrows * 512 * 4 + Mrows * K * 4 + 2 * Mrows * nb * 4,
-           "vqa_graphconv_pool_fwd_f32": Mrows * H * 4 + Mrows * nb * 4 + Mrows * 16 + 4 * B * H * 4,
+           "vqa_graphconv_mma_pool_fwd": Mrows * H * 4 + Mrows * nb * 4 + Mrows * 16 + 4 * B * H * 4,
+           "vqa_graphconv_mma_bwd_data": 2 * Mrows * 2 * H * 4 + 2 * Mrows * nb * 4 + Mrows * 16,
            "vqa_adjacency_topk_bwd_f32": 2 * Mrows * 512 * 4 + 3 * Mrows * nb * 4}
     for k, nbytes in alg.items():
         m = med(timers.get(k, []))
         if m:
             extra[k] = {"us": round(m * 1e3, 2), "GB/s": round(nbytes / (m * 1e-3) / 1e9, 1), "frac": round(nbytes / (m * 1e-3) / 1e9 / hbm_peak, 4)}
-    bw = sorted(timers.get("vqa_graphconv_bwd_f32", []))
-    if bw:
-        extra["vqa_graphconv_bwd_f32"] = {"us_median_over_both_layers": round(med(bw) * 1e3, 2)}
-
+    ed = sorted(timers.get("vqa_graphconv_mma_bwd_edges", []))
+    if ed:   # two launches per step: layer 2 (pooled upstream, reads Y2) then layer 1 (reads dG1 and Y1)
+        extra["vqa_graphconv_mma_bwd_edges"] = {"us_layer2_layer1": [round(ed[0] * 1e3, 2), round(ed[-1] * 1e3, 2)],
+                                                "GB/s_layer1": round((2 * Mrows * 2 * H * 4) / (ed[-1] * 1e-3) / 1e9, 1)}
+    # dense projections: total tensor-core time and rate of the split-bf16 GEMMs in one step
+    gm = timers.get("vqa_gemm_bf16s", [])
+    roof_gemm = None
+    if gm:
+        per_step = sum(gm) / 6.0                                             # 6 timed eager steps
+        passes = 1 if args.precision == "bf16" else 3
+        roof_gemm = {"kernel": "gemm_bf16s_kernel (all dense projections of one step, event-bracketed launches incl. gaps)", "bound": "tensor",
+                     "ms_per_step": round(per_step, 3), "launches_per_step": len(gm) // 6, "passes": passes,
+                     "peak": tf_peak, "unit": "TFLOP/s (bf16 sustained, measured)" if peak_src == "measured" else "TFLOP/s (fallback)"}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only
         from vqa_b200.synthetic import WORKLOADS
         cores = os.cpu_count() or 1
         t, _ = cpu_train_steps(WORKLOADS["vqa2_b64"], args.cpu_sample, 4, 1, cores)
@@ -314,12 +352,11 @@ def run_b200(args, workload):
         "e2e": {"value": round(e2e_value, 1), "unit": "questions/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": round(ms_e2e, 4), "last_loss": last_loss},
         "gpu_launches": int(launches),
-        "roofline": roof, "roofline_other_kernels": extra, "cpu_baseline": cpu,
+        "roofline": roof, "roofline_other_kernels": extra, "roofline_gemm": roof_gemm, "cpu_baseline": cpu,
         "clocks": sampler.summary(), "final_loss": final_loss,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 def main():

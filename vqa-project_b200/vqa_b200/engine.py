@@ -95,6 +95,7 @@ class TrainStep:
             for _ in range(self.warmup):
                 self._body(self.slots[0])
         torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
         pool = None
         for s in range(self.nslots):
             g = torch.cuda.CUDAGraph()
