@@ -34,9 +34,10 @@ def main():
         a[0] += 1
         a[1] += us
     tot = sum(a[1] for a in agg.values())
-    ours = sum(a[1] for n, a in agg.items() if n.startswith("vqa::"))
+    OURS = ("vqa::", "sb::", "gm::")          # ncu drops the outer namespace of templated kernels
+    ours = sum(a[1] for n, a in agg.items() if n.startswith(OURS))
     print(f"launches {len(rows)} (ids {rows[0][0]}..{rows[-1][0]}), total device time {tot:.1f} us; "
-          f"vqa:: kernels {ours:.1f} us = {100 * ours / tot:.1f} %\n")
+          f"kernels of libvqa_sm100.so {ours:.1f} us = {100 * ours / tot:.1f} %\n")
     print("| kernel | launches | total us | share | avg us | grid | block |")
     print("|---|---:|---:|---:|---:|---|---|")
     for n, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
