@@ -30,6 +30,7 @@ typedef struct CUstream_st* vqa_stream_t; /* cudaStream_t */
 /* GEMM epilogue flags */
 #define VQA_GEMM_RELU 1
 #define VQA_GEMM_ATOMIC_ADD 4 /* set internally for split-K: C must be zero-filled by the caller */
+#define VQA_GEMM_NO_CLUSTER 16 /* vqa_gemm_bf16s: never pair CTAs (B-tile multicast); for A/B measurements */
 #define VQA_GEMM_ACCUMULATE 8 /* C += A.B^T with fp32 atomics into a caller-initialised C (plain epilogue, any split_k) */
 
 /* graph-conv flags */

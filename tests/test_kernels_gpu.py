@@ -189,6 +189,26 @@ def test_gemm_split_bf16_split_k(kn, split):
     assert rel_err(out.cpu(), a.double().t() @ b.double()) < 3e-5
 
 
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,split", [(1100, 520, 200, False, False, 1), (1088, 512, 320, False, True, 1),
+                                                    (1200, 300, 1000, True, True, 3), (2048, 2052, 1100, True, True, 1)])
+@pytest.mark.parametrize("passes,tol", [(3, 3e-5), (1, 8e-3)])
+def test_gemm_split_bf16_cta_pairs(kn, M, N, K, a_mn, b_mn, split, passes, tol):
+    """>= 8 tile rows at BN = 256: CTA pairs with the B tile multicast to both (odd tile-row counts get a padding tile)."""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn(N, K, generator=g)
+    ref = a.double() @ b.double().t()
+    a_s = kn.split((a.t().contiguous() if a_mn else a).to(DEV))
+    b_s = kn.split((b.t().contiguous() if b_mn else b).to(DEV))
+    out = kn.gemm_s(a_s, b_s, a_mn=a_mn, b_mn=b_mn, passes=passes, tile_n=256, split_k=split)
+    assert rel_err(out.cpu(), ref) < tol
+    solo = kn.gemm_s(a_s, b_s, a_mn=a_mn, b_mn=b_mn, passes=passes, tile_n=256, split_k=split, cluster=False)
+    if split == 1:
+        assert torch.equal(out, solo)                    # same arithmetic, only the operand delivery differs
+    else:
+        assert rel_err(out.cpu(), solo.cpu().double()) < 1e-6
+
+
 def test_gemm_split_bf16_accumulate_and_auto_tile(kn):
     g = torch.Generator().manual_seed(11)
     M, N, Kc = 512, 1024, 3072            # the GRU backward product: few tiles -> BN = 64 tile, split-K, accumulate into C

@@ -24,6 +24,7 @@ ref = (X.double()[:512] @ W1.double().t())
 for passes in (3, 1):
     for bn in (128, 256):
         timeit(f"Y1 = X.W1^T  passes={passes} bn={bn}", lambda: kn.gemm_s(Xs, W1s, passes=passes, tile_n=bn), 2 * M * 2048 * F)
+    timeit(f"Y1 = X.W1^T  passes={passes} bn=256 no pairs", lambda: kn.gemm_s(Xs, W1s, passes=passes, tile_n=256, cluster=False), 2 * M * 2048 * F)
     out = kn.gemm_s(Xs, W1s, passes=passes)
     print("   rel err vs fp64 (first 512 rows):", ((out[:512].double() - ref).abs().max() / ref.abs().max()).item())
     timeit(f"Y2 = G1.W2^T passes={passes}", lambda: kn.gemm_s(G1s, W2s, passes=passes), 2 * M * 1024 * 2048)

@@ -183,11 +183,31 @@ struct Epi {
 
 struct Maps { CUtensorMap a_hi, a_lo, b_hi, b_lo; };
 
-template <int BN, int PASSES>
+// ---- thread-block-cluster helpers (CL = 2: the two CTAs of a pair own vertically adjacent output tiles and share B) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load delivered to the same shared-memory offset (and signalling the mbarrier at the same offset) in every CTA of cta_mask
+__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+// MMA-completion arrive on the barrier at this offset in every CTA of cta_mask (a stage is refilled by both producers)
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
+template <int BN, int PASSES, int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_bf16s_kernel(const __grid_constant__ Maps tm, const Params p) {
   using C = Cfg<BN, PASSES>;
   constexpr int S = C::S;
+  const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * C::STAGE);
@@ -208,7 +228,7 @@ gemm_bf16s_kernel(const __grid_constant__ Maps tm, const Params p) {
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }   // CL = 2: both CTAs' MMAs release a stage
       mbar_init(acc_full, 1);
       fence_barrier_init();
     }
@@ -218,6 +238,7 @@ gemm_bf16s_kernel(const __grid_constant__ Maps tm, const Params p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();          // the peer's barriers are initialised before any multicast can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -241,7 +262,18 @@ gemm_bf16s_kernel(const __grid_constant__ Maps tm, const Params p) {
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c) tma_load_2d(a_dst + c * 8192, ma, &full[s], m0 + c * 64, k0);
           }
-          if (!p.b_mn) {
+          if (CL == 2) {
+            // this CTA fetches its half of the shared B tile and multicasts it into both CTAs of the pair
+            if (!p.b_mn) {
+              tma_load_2d_mc(b_dst + crank * (BN / 2) * 128, mb, &full[s], k0, n0 + (int)crank * (BN / 2), (uint16_t)3);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BN / 128; ++c) {
+                const int cc = (int)crank * (BN / 128) + c;
+                tma_load_2d_mc(b_dst + cc * 8192, mb, &full[s], n0 + cc * 64, k0, (uint16_t)3);
+              }
+            }
+          } else if (!p.b_mn) {
             tma_load_2d(b_dst, mb, &full[s], k0, n0);
           } else {
 #pragma unroll
@@ -276,7 +308,8 @@ gemm_bf16s_kernel(const __grid_constant__ Maps tm, const Params p) {
             tc_mma<1>(tmem_base, dah, dbh, idesc, acc);
           }
         }
-        tc_commit(&empty[s]);                       // smem slot reusable once these MMAs retire
+        if (CL == 2) tc_commit_mc(&empty[s], (uint16_t)3);   // the slot is refilled by both producers: release it in both CTAs
+        else tc_commit(&empty[s]);                  // smem slot reusable once these MMAs retire
         if (i == nkb - 1) tc_commit(acc_full);      // accumulator complete
       }
       __syncwarp();
@@ -300,6 +333,7 @@ gemm_bf16s_kernel(const __grid_constant__ Maps tm, const Params p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();          // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
   }
@@ -334,16 +368,28 @@ static int make_map(CUtensorMap* tm, const void* ptr, long long ld, int mn_exten
   return VQA_OK;
 }
 
-template <int BN, int PASSES>
+template <int BN, int PASSES, int CL>
 static int launch(const Maps& tm, const Params& p, int splits, cudaStream_t st) {
   using C = Cfg<BN, PASSES>;
   static bool attr_set = false;
   if (!attr_set) {
-    VQA_CUDA(cudaFuncSetAttribute(gemm_bf16s_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    VQA_CUDA(cudaFuncSetAttribute(gemm_bf16s_kernel<BN, PASSES, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr_set = true;
   }
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, splits);
-  gemm_bf16s_kernel<BN, PASSES><<<grid, THREADS, C::SMEM, st>>>(tm, p);
+  int mt = (p.M + BM - 1) / BM;
+  if (CL == 2) mt = (mt + 1) & ~1;                 // pairs of vertically adjacent tiles; a padding tile only sees zero-filled rows
+  dim3 grid((p.N + BN - 1) / BN, mt, splits);
+  if (CL == 1) {
+    gemm_bf16s_kernel<BN, PASSES, CL><<<grid, THREADS, C::SMEM, st>>>(tm, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    VQA_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16s_kernel<BN, PASSES, CL>, tm, p));
+  }
   VQA_LAUNCH_CHECK("gemm_bf16s_kernel");
   return VQA_OK;
 }
@@ -464,17 +510,23 @@ extern "C" int vqa_gemm_bf16s(const void* A_hi, const void* A_lo, long long lda,
   }
   VQA_CHECK_ARG(bn == 64 || bn == 128 || bn == 256, "%s: tile_n must be 64, 128 or 256", who);
 
+  // CTA pairs (cluster 1x2x1) with the B tile multicast to both: the big projections are L2->SM bandwidth bound (96 KB per
+  // k-block and CTA at BN = 256), sharing B cuts that to 64 KB.  Worth it only when there are plenty of tile rows.
+  const int mtiles = (M + sb::BM - 1) / sb::BM;
+  int cl = (bn == 256 && mtiles >= 8 && !(flags & VQA_GEMM_NO_CLUSTER)) ? 2 : 1;
   sb::Maps tm;
   memset(&tm, 0, sizeof(tm));
+  const int b_box = cl == 2 ? bn / 2 : bn;
   int rc = sb::make_map(&tm.a_hi, A_hi, lda, M, Kc, a_mn_major, sb::BM);
-  if (!rc) rc = sb::make_map(&tm.b_hi, B_hi, ldb, N, Kc, b_mn_major, bn);
+  if (!rc) rc = sb::make_map(&tm.b_hi, B_hi, ldb, N, Kc, b_mn_major, b_box);
   if (!rc && passes == 3) rc = sb::make_map(&tm.a_lo, A_lo, lda, M, Kc, a_mn_major, sb::BM);
-  if (!rc && passes == 3) rc = sb::make_map(&tm.b_lo, B_lo, ldb, N, Kc, b_mn_major, bn);
+  if (!rc && passes == 3) rc = sb::make_map(&tm.b_lo, B_lo, ldb, N, Kc, b_mn_major, b_box);
   if (rc) return rc;
   sb::Params p{C, ldc, reinterpret_cast<__nv_bfloat16*>(C_hi), reinterpret_cast<__nv_bfloat16*>(C_lo), ldcs, M, N, Kc,
                a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, bias, rowbcast, ldrb, group, aux, ldaux,
                reinterpret_cast<const __nv_bfloat16*>(aux_hi), ldauxh, aux_scale, flags, per, num_kb};
-#define VQA_DISPATCH(BN_) (passes == 3 ? sb::launch<BN_, 3>(tm, p, splits, stream) : sb::launch<BN_, 1>(tm, p, splits, stream))
+#define VQA_DISPATCH(BN_) (passes == 3 ? sb::launch<BN_, 3, 1>(tm, p, splits, stream) : sb::launch<BN_, 1, 1>(tm, p, splits, stream))
+  if (bn == 256 && cl == 2) return passes == 3 ? sb::launch<256, 3, 2>(tm, p, splits, stream) : sb::launch<256, 1, 2>(tm, p, splits, stream);
   if (bn == 256) return VQA_DISPATCH(256);
   if (bn == 128) return VQA_DISPATCH(128);
   return VQA_DISPATCH(64);

@@ -17,6 +17,7 @@ PREC_TF32 = 1
 PREC_TF32X3_HP = 2
 GEMM_RELU = 1
 GEMM_ACCUMULATE = 8
+GEMM_NO_CLUSTER = 16
 GC_RELU = 1
 
 _p = C.c_void_p

@@ -11,7 +11,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import PREC_TF32, PREC_TF32X3, PREC_TF32X3_HP, GEMM_RELU, GEMM_ACCUMULATE, GC_RELU
+from ._cabi import PREC_TF32, PREC_TF32X3, PREC_TF32X3_HP, GEMM_RELU, GEMM_ACCUMULATE, GEMM_NO_CLUSTER, GC_RELU
 
 LAUNCHES = 0
 _LAUNCH_COST = {"vqa_colsum_f32": 2}
@@ -156,7 +156,7 @@ def dropout_split(x: torch.Tensor, p: float, seed: int, offset: int, step: Optio
 def gemm_s(a: SplitT, b: SplitT, *, a_mn: bool = False, b_mn: bool = False, out: Optional[torch.Tensor] = None,
            out_split: Optional[SplitT] = None, want_f32: bool = True, bias: Optional[torch.Tensor] = None,
            rowbcast: Optional[torch.Tensor] = None, group: int = 1, aux=None, aux_scale: float = 1.0, relu: bool = False,
-           passes: int = 3, split_k: int = 1, tile_n: int = 0, accumulate: bool = False):
+           passes: int = 3, split_k: int = 1, tile_n: int = 0, accumulate: bool = False, cluster: bool = True):
     """C[M,N] = epi(A . B^T) on the split-bf16 tcgen05 GEMM (``accumulate``: ``out += A . B^T`` with fp32 atomics).  ``a`` is (M,K) [a_mn=False] or (K,M) [a_mn=True]; same
     for ``b`` with N.  ``aux`` (mask source) may be an fp32 tensor or a SplitT.  Returns ``out`` (fp32) or, when
     ``want_f32`` is False, ``out_split``."""
@@ -196,7 +196,7 @@ def gemm_s(a: SplitT, b: SplitT, *, a_mn: bool = False, b_mn: bool = False, out:
           b.hi.data_ptr(), _ptr(b.lo) if passes == 3 else None, b.ld, int(b_mn), _ptr(out), ldc,
           None if out_split is None else out_split.hi.data_ptr(), None if out_split is None else _ptr(out_split.lo),
           0 if out_split is None else out_split.ld, M, N, Ka, _ptr(bias), _ptr(rowbcast), ldrb, group,
-          _ptr(aux_f), ldaux, _ptr(aux_h), ldauxh, float(aux_scale), (GEMM_RELU if relu else 0) | (GEMM_ACCUMULATE if accumulate else 0),
+          _ptr(aux_f), ldaux, _ptr(aux_h), ldauxh, float(aux_scale), (GEMM_RELU if relu else 0) | (GEMM_ACCUMULATE if accumulate else 0) | (0 if cluster else GEMM_NO_CLUSTER),
           passes, split_k, tile_n, _stream())
     return out if want_f32 else out_split
 

@@ -306,9 +306,10 @@ class QuestionEncoderFn(torch.autograd.Function):
         Hs = kn.empty_split((T + 1) * B, H, dev)
         Hall[0].zero_(); Hs.hi[:B].zero_(); Hs.lo[:B].zero_()
         gates = torch.empty((T, B, 4 * H), device=dev, dtype=torch.float32)
-        fsplit = max(1, min(4, 384 // max(1, ((B + 127) // 128) * ((3 * H + 63) // 64))))   # ~384 CTAs for the per-step product
+        # per-step product h W_hh^T: L2-bandwidth bound at M = B rows (measured sweep, tools/gru_gemm_sweep.py): 128-wide tiles, no split
+        tile = 128 if B <= 1024 else 0
         for t in range(T):
-            GH = kn.gemm_s(Hs.rows_slice(t * B, (t + 1) * B), Whhs, split_k=fsplit) if t > 0 else None
+            GH = kn.gemm_s(Hs.rows_slice(t * B, (t + 1) * B), Whhs, tile_n=tile) if t > 0 else None
             kn.gru_cell_fwd(GI[t * B:(t + 1) * B], GH, b_hh, Hall[t] if t > 0 else None, qlen, t, Hall[t + 1],
                             Hs.rows_slice((t + 1) * B, (t + 2) * B), gates[t])
         ctx.T = T
@@ -328,14 +329,15 @@ class QuestionEncoderFn(torch.autograd.Function):
         dGH = torch.empty((T * B, 3 * H), device=dev, dtype=torch.float32)
         dGIs = kn.empty_split(T * B, 3 * H, dev)
         dGHs = kn.empty_split(T * B, 3 * H, dev)
-        ksplit = max(1, min(8, 256 // max(1, ((B + 127) // 128) * ((H + 63) // 64))))   # ~256 CTAs for the per-step product
+        tile = 128 if B <= 1024 else 0
+        ksplit = max(1, min(8, 128 // max(1, ((B + 127) // 128) * ((H + 127) // 128))))   # ~128 CTAs for the per-step product (sweep)
         for t in reversed(range(T)):
             r0, r1 = t * B, (t + 1) * B
             dh_part = torch.empty((B, H), device=dev, dtype=torch.float32)
             kn.gru_cell_bwd(dh, gates[t], Hall[t] if t > 0 else None, qlen, t, dGI[r0:r1], dGH[r0:r1],
                             dGIs.rows_slice(r0, r1), dGHs.rows_slice(r0, r1), dh_part)
             if t > 0:   # dL/dh_{t-1} = direct part + dgh . W_hh  (split-K accumulating into the direct part)
-                kn.gemm_s(dGHs.rows_slice(r0, r1), Whhs, b_mn=True, out=dh_part, accumulate=True, split_k=ksplit)
+                kn.gemm_s(dGHs.rows_slice(r0, r1), Whhs, b_mn=True, out=dh_part, accumulate=True, split_k=ksplit, tile_n=tile)
             dh = dh_part
         db_ih = kn.colsum(dGI)
         db_hh = kn.colsum(dGH)
