@@ -20,7 +20,7 @@ extern "C" {
 
 typedef struct CUstream_st* vqa_stream_t; /* cudaStream_t */
 
-#define VQA_ABI_VERSION 2
+#define VQA_ABI_VERSION 3
 
 /* GEMM precision modes */
 #define VQA_PREC_TF32X3 0 /* 3-pass split TF32 on tcgen05: fp32-grade results (parity mode)      */
@@ -140,18 +140,29 @@ int vqa_graphconv_edge_bwd_f32(const float* P, const int* idx, const float* alph
 /* ---- tensor-core graph convolution on split-bf16 planes (graphconv_mma.cu).  Same maths and reference call sites as
  * vqa_graphconv_fwd_f32 / _pool_fwd_f32 / the dY part of _bwd_f32; Y and the results are (hi, lo) bf16 planes (lo may
  * be NULL: bf16 mode), so the projections before and after exchange planes with no fp32 round trip.  Requires
- * (out_dim / nk) % 128 == 0 and K <= 128; returns VQA_ERR_UNSUPPORTED otherwise (callers use the fp32 kernels). */
+ * (out_dim / nk) % 128 == 0 and K <= 128; returns VQA_ERR_UNSUPPORTED otherwise (callers use the fp32 kernels).
+ *
+ * vqa_graphconv_edge_coef evaluates, once per layer and step, everything that depends only on the selected edges:
+ * coef (B,K,nb,nk) = Gaussian weight (normalised over the kernel axis, layers.py:109-123) * alpha (1 if alpha is NULL)
+ * and eoff (B,K,nb) = the packed positions of each edge inside the shared-memory coefficient matrices (forward |
+ * transposed << 16).  Passing coef/eoff to the three aggregates selects the persistent streaming kernels; with
+ * coef == NULL they evaluate the weights themselves (slower, same results). */
+int vqa_graphconv_edge_coef(const int* idx, const float* alpha, const float* boxes, long long ldbox, const float* gauss,
+                            float* coef, unsigned* eoff, int B, int K, int nb, int nk, vqa_stream_t stream);
 int vqa_graphconv_mma_fwd(const void* Y_hi, const void* Y_lo, long long ldy, const int* idx, const float* alpha,
                           const float* boxes, long long ldbox, const float* gauss, void* out_hi, void* out_lo, long long ldo,
                           int B, int K, int nb, int nk, int out_dim, int flags, float dropout_p, unsigned long long seed,
-                          unsigned long long offset, const unsigned long long* step_ptr, vqa_stream_t stream);
+                          unsigned long long offset, const unsigned long long* step_ptr, const float* coef,
+                          const unsigned* eoff, vqa_stream_t stream);
 int vqa_graphconv_mma_pool_fwd(const void* Y_hi, const void* Y_lo, long long ldy, const int* idx, const float* boxes,
                                long long ldbox, const float* gauss, const float* q, float* pooled, long long* argmax,
-                               float* hq, int B, int K, int nb, int nk, int out_dim, vqa_stream_t stream);
+                               float* hq, int B, int K, int nb, int nk, int out_dim, const float* coef,
+                               const unsigned* eoff, vqa_stream_t stream);
 /* dY[b,j, chunk k] = sum_{(i,m): idx[i,m]=j} w[i,m,k] alpha[i,m] dO[b,i, chunk k]  (the transposed aggregate) */
 int vqa_graphconv_mma_bwd_data(const void* dO_hi, const void* dO_lo, long long lddo, const int* idx, const float* alpha,
                                const float* boxes, long long ldbox, const float* gauss, void* dY_hi, void* dY_lo,
-                               long long lddy, int B, int K, int nb, int nk, int out_dim, vqa_stream_t stream);
+                               long long lddy, int B, int K, int nb, int nk, int out_dim, const float* coef,
+                               const unsigned* eoff, vqa_stream_t stream);
 
 /* Edge part of the backward on the tensor cores: P[i,m,k] = <dO[i,chunk k], Y[idx[i,m],chunk k]> per image as
  * dO_k Y_k^T, then dalpha (B,K,nb) (NULL when alpha is NULL) and the per-image partial sums of the Gaussian-parameter

@@ -22,12 +22,14 @@ h = torch.randn(B, K, 512, device=dev).clamp_(min=0)
 adj, idx, alpha = kn.adjacency_topk_fwd(h, nb)
 Y1s = kn.split(torch.randn(M, 2048, device=dev)); Y2s = kn.split(torch.randn(M, 1024, device=dev)); q = torch.randn(B, 1024, device=dev)
 b1 = 2 * M * 2048 * 4 + 2 * M * nb * 4 + M * 16
-timeit("mma fwd L1 relu", lambda: kn.graphconv_fwd_s(Y1s, idx, alpha, img, gauss, B, K), b1)
-timeit("mma fwd L1 relu+dropout", lambda: kn.graphconv_fwd_s(Y1s, idx, alpha, img, gauss, B, K, dropout_p=0.5, seed=1, offset=1), b1)
-timeit("mma fwd L1 relu (bf16 planes)", lambda: kn.graphconv_fwd_s(kn.SplitT(Y1s.hi, None, Y1s.rows, Y1s.cols, Y1s.ld), idx, alpha, img, gauss, B, K), b1 // 2)
-timeit("mma pool fwd L2", lambda: kn.graphconv_pool_fwd_s(Y2s, idx, img, gauss, q, B, K), M * 1024 * 4 + M * nb * 4 + M * 16 + 4 * B * 1024 * 4)
-timeit("mma bwd data L1", lambda: kn.graphconv_bwd_data_s(Y1s, idx, alpha, img, gauss, B, K), b1)
-timeit("mma bwd data L2", lambda: kn.graphconv_bwd_data_s(Y2s, idx, None, img, gauss, B, K), 2 * M * 1024 * 4 + M * nb * 4 + M * 16)
+ec1 = kn.graphconv_edge_coef(idx, alpha, img, gauss, B, K); ec2 = kn.graphconv_edge_coef(idx, None, img, gauss, B, K)
+timeit("edge coefficients (one layer)", lambda: kn.graphconv_edge_coef(idx, alpha, img, gauss, B, K), M * nb * (4 + 4 + 4 * nk + 4))
+timeit("mma fwd L1 relu", lambda: kn.graphconv_fwd_s(Y1s, idx, alpha, img, gauss, B, K, ec=ec1), b1)
+timeit("mma fwd L1 relu+dropout", lambda: kn.graphconv_fwd_s(Y1s, idx, alpha, img, gauss, B, K, dropout_p=0.5, seed=1, offset=1, ec=ec1), b1)
+timeit("mma fwd L1 relu (bf16 planes)", lambda: kn.graphconv_fwd_s(kn.SplitT(Y1s.hi, None, Y1s.rows, Y1s.cols, Y1s.ld), idx, alpha, img, gauss, B, K, ec=ec1), b1 // 2)
+timeit("mma pool fwd L2", lambda: kn.graphconv_pool_fwd_s(Y2s, idx, img, gauss, q, B, K, ec=ec2), M * 1024 * 4 + M * nb * 4 + M * 16 + 4 * B * 1024 * 4)
+timeit("mma bwd data L1", lambda: kn.graphconv_bwd_data_s(Y1s, idx, alpha, img, gauss, B, K, ec=ec1), b1)
+timeit("mma bwd data L2", lambda: kn.graphconv_bwd_data_s(Y2s, idx, None, img, gauss, B, K, ec=ec2), 2 * M * 1024 * 4 + M * nb * 4 + M * 16)
 dO1s = kn.split(torch.randn(M, 2048, device=dev))
 timeit("mma bwd edges L1 (P + edge finish)", lambda: kn.graphconv_bwd_edges_s(Y1s, idx, alpha, img, gauss, B, K, dOs=dO1s), 2 * M * 2048 * 4 + 3 * M * nb * 4)
 pooled, arg, hq = kn.graphconv_pool_fwd_s(Y2s, idx, img, gauss, q, B, K)

@@ -98,12 +98,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+  // suspend-time hint (ns): the hardware parks the thread until the phase completes or the hint expires, so a waiting warp
+  // does not burn issue slots (measured: without it the polling loops were ~30 % of all instructions of a warp-specialised kernel)
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
       : "memory");
   return ok != 0;
 }
@@ -111,9 +113,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  for (uint32_t it = 1;; ++it) {
-    if (mbar_try_wait(bar, parity)) return;
-    if ((it & 255u) == 0 && clock64() - t0 > 4000000000LL) break;
+  for (;;) {
+#pragma unroll 1
+    for (int it = 0; it < 64; ++it)
+      if (mbar_try_wait(bar, parity)) return;
+    if (clock64() - t0 > 4000000000LL) break;
   }
   printf("vqa_b200: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
   __trap();

@@ -26,6 +26,7 @@
 #include <cuda_bf16.h>
 #include <mutex>
 #include <cstring>
+#include <cstdlib>
 #include "../../include/vqa_b200.h"
 
 namespace vqa {
@@ -43,6 +44,7 @@ struct Maps { CUtensorMap in_hi, in_lo, out_hi, out_lo; };
 
 struct AggParams {
   const int* idx; const float* alpha; const float* boxes; long long ldbox; const float* gauss;
+  const float* coef; const unsigned* eoff;
   const float* q; float* pooled; long long* argmax; float* hq;
   int B, K, KP, nb, nk, out_dim, D, nkc, tiles_per_cta, ntiles, nstage, flags, with_lo;
   float drop_scale; unsigned drop_thresh16; unsigned long long seed, offset; const unsigned long long* step_ptr;
@@ -316,6 +318,425 @@ agg_kernel(const __grid_constant__ Maps tm, const AggParams p) {
       }
     }
     if (MODE != AGG_FWD_POOL && leader) bulk_wait_read<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+  }
+}
+
+// Epilogue work for two consecutive node rows (i, i+1) of one output column: optional ReLU, optional dropout (rnd: one
+// 32-bit hash, low / high half decide row i / i+1; thresh_hi = threshold << 16), split into hi / lo bf16 and staged.
+template <bool WITH_LO, bool DROP, bool RELU>
+__device__ __forceinline__ void epi_pair(float v0, float v1, bool ok1, uint32_t rnd, uint32_t thresh_hi, __nv_bfloat16* hi0,
+                                         __nv_bfloat16* lo0) {
+  if (RELU) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+  if (DROP) {                                             // the 1/(1-p) scale is folded into the coefficient matrix
+    v0 = (rnd << 16) >= thresh_hi ? v0 : 0.f;
+    v1 = rnd >= thresh_hi ? v1 : 0.f;
+  }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);   // one F2FP for both conversions
+  const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+  *reinterpret_cast<uint16_t*>(hi0) = (uint16_t)hb;
+  if (ok1) *reinterpret_cast<uint16_t*>(hi0 + MT) = (uint16_t)(hb >> 16);
+  if (WITH_LO) {
+    const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - __uint_as_float(hb << 16), v1 - __uint_as_float(hb & 0xFFFF0000u));
+    const uint32_t lb = *reinterpret_cast<const uint32_t*>(&l);
+    *reinterpret_cast<uint16_t*>(lo0) = (uint16_t)lb;
+    if (ok1) *reinterpret_cast<uint16_t*>(lo0 + MT) = (uint16_t)(lb >> 16);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ edge coefficients
+// One thread per selected edge e = (b, i, m), j = idx[b,i,m]:  polar pseudo-coordinates of centre_i - centre_j
+// (sparse_graph_model.py:106-108,258-267), the nk Gaussian weights normalised over the KERNEL axis (layers.py:109-123) and
+// the edge weight alpha (sparse_graph_model.py:239-240):  coef[e][k] = w[e][k] * alpha[e].  Also the byte offsets of the
+// edge's entry inside a swizzled K-major coefficient plane, forward (row i, column j) in the low half-word and transposed
+// (row j, column i) in the high one.  Computed once per layer and step; the forward aggregate and the backward-data
+// aggregate both read it, so no transcendental is evaluated inside the streaming kernels.
+__global__ void __launch_bounds__(256)
+edge_coef_kernel(const int* __restrict__ idx, const float* __restrict__ alpha, const float* __restrict__ boxes, long long ldbox,
+                 const float* __restrict__ gauss, float* __restrict__ coef, unsigned* __restrict__ eoff, long long n_edges, int K, int nb,
+                 int nk, int KP) {
+  __shared__ float gs[4 * MAX_NK];
+  for (int k = threadIdx.x; k < nk; k += blockDim.x) {
+    const float sr = gauss[nk + k], st = gauss[3 * nk + k];
+    gs[k] = gauss[k];
+    gs[nk + k] = -0.5f * 1.4426950408889634f / (GM_EPS_F + sr * sr);
+    gs[2 * nk + k] = gauss[2 * nk + k];
+    gs[3 * nk + k] = -0.5f * 1.4426950408889634f / (GM_EPS_F + st * st);
+  }
+  __syncthreads();
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const long long row = e / nb;                       // b * K + i
+  const int i = (int)(row % K), j = idx[e];
+  const float* bi = boxes + row * ldbox;
+  const float* bj = boxes + (row - i + j) * ldbox;
+  const float xi = bi[0] + 0.5f * (bi[2] - bi[0]), yi = bi[1] + 0.5f * (bi[3] - bi[1]);   // sparse_graph_model.py:106-108
+  const float xj = bj[0] + 0.5f * (bj[2] - bj[0]), yj = bj[1] + 0.5f * (bj[3] - bj[1]);
+  const float dx = xi - xj, dy = yi - yj;                                                   // centre_i - centre_j (:258-259)
+  const float rho = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+  const float theta = atan2f(dx, dy);                                                       // x FIRST (:264-265)
+  float Ssum = 0.f;
+  for (int k = 0; k < nk; ++k) Ssum += gauss_val(rho, theta, gs[k], gs[nk + k], gs[2 * nk + k], gs[3 * nk + k]);
+  const float a_over_S = __fdiv_rn(alpha ? alpha[e] : 1.f, Ssum);    // Ssum == 0 -> inf/NaN, as the reference
+  float* c = coef + e * nk;
+  for (int k = 0; k < nk; ++k) c[k] = gauss_val(rho, theta, gs[k], gs[nk + k], gs[2 * nk + k], gs[3 * nk + k]) * a_over_S;
+  eoff[e] = coef_off(i, j, KP) | (coef_off(j, i, KP) << 16);
+}
+
+// ------------------------------------------------------------------------------------------ persistent aggregate
+// Same maths and tile mapping as agg_kernel, restructured so that no phase waits for another: one persistent CTA per SM
+// walks a contiguous range of work items (image, slab of kernels) and every phase has its own warps, all handshakes are
+// mbarriers polled by ONE lane per warp:
+//   warp 0       TMA producer (Y tiles, multi-stage ring across items)
+//   warps 1-3    MMA issuers, tile g belongs to issuer g % 3 (issuing one of these small MMAs costs a single thread ~130
+//                cycles - measured - so one issuer cannot keep up with HBM); warp 1 owns the TMEM allocation (4 accumulators)
+//   warps 4-15   epilogue: three warps per TMEM lane quarter split the node rows; ReLU / dropout / hi-lo split / staging
+//                (latency-bound instruction streams: more warps, not fewer instructions, is what buys throughput here)
+//   warps 16-19  coefficient builders, one item ahead: scatter the precomputed edge coefficients (edge_coef_kernel) of the
+//                item's kernels into the swizzled hi/lo planes (double-buffered); next item's values prefetched in registers
+//   warp 20      TMA stores of the staged output tiles (double-buffered staging, mbarrier handshake with the epilogue)
+constexpr int P_EG = 3;                                // epilogue row groups (4 warps each)
+constexpr int P_EPI = P_EG * 128, P_BLD = 128, P_NI = 3;
+constexpr int P_W_BLD = 4 + 4 * P_EG, P_W_ST = P_W_BLD + 4;     // first builder warp, store warp
+constexpr int P_THREADS = 32 * (P_W_ST + 1);
+constexpr int P_CH = 5, P_MAXKC = 4;                   // builder: edges per thread per chunk, kernels per item
+
+struct Agg2Params {
+  const float* coef; const unsigned* eoff;
+  const float* q; float* pooled; long long* argmax; float* hq;
+  int B, K, KP, nb, nk, out_dim, D, nkc, tpk, slabs, nitems, nstage, nacc, rpg, flags, with_lo;
+  float drop_scale; unsigned drop_thresh16; unsigned long long seed, offset; const unsigned long long* step_ptr;
+  int off_coef, coef_plane, coef_buf, off_stage, stage_bytes, off_out, out_plane, off_pool, off_bars, tmem_cols;
+};
+
+// DEBUG timeline (flags 0x4000): per-role clock64 stamps of CTA 0's first TL_N tiles / items
+constexpr int TL_N = 96;
+__device__ long long g_timeline[10][TL_N];
+#define TL(row, i) do { if ((p.flags & 0x4000) && blockIdx.x == 0 && (i) < TL_N) g_timeline[row][i] = clock64(); } while (0)
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// FR: node rows per epilogue warp handled by straight-line code (the common case rpg == FR; anything else takes the
+// bounds-checked path)
+template <int MODE, bool WITH_LO, bool DROP, int FR>
+__global__ void __launch_bounds__(P_THREADS, 1)
+agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
+  extern __shared__ uint8_t gsm_raw[];
+  uint8_t* sm = gsm_raw + ((1024u - (smem_u32(gsm_raw) & 1023u)) & 1023u);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = p.K, KP = p.KP, NP = p.KP, S = p.nstage, NACC = p.nacc;
+  constexpr int planes = WITH_LO ? 2 : 1;
+  const int tiles_per_item = p.nkc * p.tpk;
+  const int it0 = (int)((long long)blockIdx.x * p.nitems / gridDim.x), it1 = (int)((long long)(blockIdx.x + 1) * p.nitems / gridDim.x);
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + p.off_bars);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + S;
+  uint64_t* tfull = bars + 2 * S;
+  uint64_t* tempty = tfull + 8;
+  uint64_t* cfull = tempty + 8;
+  uint64_t* cempty = cfull + 2;
+  uint64_t* sfull = cempty + 2;
+  uint64_t* sempty = sfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + 2);
+
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      for (int a = 0; a < 8; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], P_EPI / 32); }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&cfull[a], 1); mbar_init(&cempty[a], P_NI);
+        mbar_init(&sfull[a], P_EPI / 32); mbar_init(&sempty[a], 1);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm.in_hi);
+    if (p.with_lo) tma_prefetch_desc(&tm.in_lo);
+    if (MODE != AGG_FWD_POOL) { tma_prefetch_desc(&tm.out_hi); if (p.with_lo) tma_prefetch_desc(&tm.out_lo); }
+  }
+  // rows [K, KP) of every staged Y tile are never written by TMA (the boxes have K rows): zero them once, so that the
+  // K-padding of the contraction multiplies zero coefficients with zeros (stale shared memory could hold NaN patterns)
+  if (KP > K) {
+    const int pad16 = (KP - K) * 8, nbox = S * planes * 2;
+    for (int v = tid; v < nbox * pad16; v += P_THREADS) {
+      const int bx = v / pad16, w = v - bx * pad16;
+      *reinterpret_cast<uint4*>(sm + p.off_stage + (size_t)bx * KP * 128 + K * 128 + w * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int g = 0, s = 0; uint32_t sph = 0;                 // ring position / phase kept incrementally (no divisions in the loops)
+      int b = it0 / p.slabs, sl = it0 - b * p.slabs;
+      for (int it = it0; it < it1; ++it) {
+        for (int t = 0; t < tiles_per_item; ++t, ++g) {
+          mbar_wait(&empty[s], sph ^ 1);
+          TL(0, g);
+          mbar_arrive_expect_tx(&full[s], (uint32_t)(planes * 2 * K * 128));   // boxes hold exactly the image's K rows
+          uint8_t* dst = sm + p.off_stage + (size_t)s * p.stage_bytes;
+          const int c0 = (sl * tiles_per_item + t) * MT;
+          for (int pl = 0; pl < planes; ++pl) {
+            const CUtensorMap* m = pl ? &tm.in_lo : &tm.in_hi;
+            tma_load_2d(dst + (pl * 2 + 0) * KP * 128, m, &full[s], c0, b * K);
+            tma_load_2d(dst + (pl * 2 + 1) * KP * 128, m, &full[s], c0 + 64, b * K);
+          }
+          if (++s == S) { s = 0; sph ^= 1; }
+        }
+        if (++sl == p.slabs) { sl = 0; ++b; }
+      }
+    }
+  } else if (warp <= P_NI) {
+    // ------------------------------------------------------------ MMA issuers (one thread per warp runs the whole loop)
+    if (lane == 0) {
+      uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
+      const uint32_t lbo = (uint32_t)KP * 128;
+      const int me = warp - 1;
+      int g = 0, n = 0, s = 0, acc = 0, owner = 0; uint32_t sph = 0, aph = 0;
+      auto next_tile = [&]() {
+        if (++s == S) { s = 0; sph ^= 1; }
+        if (++acc == NACC) { acc = 0; aph ^= 1; }
+        if (++owner == P_NI) owner = 0;
+      };
+      for (int it = it0; it < it1; ++it, ++n) {
+        const int cb = n & 1;
+        bool waited = false, mine = false;
+        int kk = 0, tk = 0;                               // kernel of the item this tile belongs to
+        for (int t = 0; t < tiles_per_item; ++t, ++g, next_tile()) {
+          const int kcur = kk;
+          if (++tk == p.tpk) { tk = 0; ++kk; }
+          if (owner != me) continue;
+          if (!waited) { mbar_wait(&cfull[cb], (n >> 1) & 1); waited = true; }
+          mbar_wait(&tempty[acc], aph ^ 1);
+          TL(1, g);
+          mbar_wait(&full[s], sph);
+          tc_fence_after();
+          TL(2, g);
+          const uint32_t a_hi = smem_u32(sm + p.off_stage + (size_t)s * p.stage_bytes), a_lo = a_hi + 2 * KP * 128;
+          const uint32_t b_hi = smem_u32(sm + p.off_coef + (size_t)cb * p.coef_buf + (size_t)(kcur * planes) * p.coef_plane), b_lo = b_hi + p.coef_plane;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NP);
+          for (int ks = 0; ks < KP / 16; ++ks) {
+            const uint32_t ao = ks * 2048, bo = (ks >> 2) * NP * 128 + (ks & 3) * 32;
+            const uint64_t dah = desc_mnmajor(a_hi + ao, lbo), dbh = desc_kmajor(b_hi + bo);
+            if (WITH_LO) {
+              const uint64_t dal = desc_mnmajor(a_lo + ao, lbo), dbl = desc_kmajor(b_lo + bo);
+              tc_mma<1>(d_tmem, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+              tc_mma<1>(d_tmem, dah, dbl, idesc, 1u);
+              tc_mma<1>(d_tmem, dah, dbh, idesc, 1u);
+            } else {
+              tc_mma<1>(d_tmem, dah, dbh, idesc, ks > 0 ? 1u : 0u);
+            }
+          }
+          tc_commit(&empty[s]);
+          tc_commit(&tfull[acc]);
+          mine = t + P_NI >= tiles_per_item;                        // my last tile of this item
+          if (mine) tc_commit(&cempty[cb]);                          // coefficient buffer free once every issuer's MMAs of the item retire
+          TL(3, g);
+        }
+        if (!mine) mbar_arrive(&cempty[cb]);                        // no tile of this item was mine
+      }
+    }
+    __syncwarp();
+  } else if (warp < P_W_BLD) {
+    // ------------------------------------------------------------ epilogue, thread = output column, P_EG warps per lane quarter
+    const int et = tid - 128;
+    const int q4 = warp & 3, grp = (warp - 4) >> 2;
+    const int r0 = grp * p.rpg, r1 = min(K, r0 + p.rpg);   // my node rows
+    const int cl = q4 * 32 + lane;
+    const unsigned long long rng_off = p.offset + (p.step_ptr ? *p.step_ptr * 16ull : 0ull);
+    const uint32_t key = hash32((uint32_t)p.seed ^ hash32((uint32_t)(p.seed >> 32) ^ hash32((uint32_t)rng_off * 0x9E3779B1u + 0x85EBCA77u)));
+    const bool leader = et == 0;
+    constexpr bool RELU = MODE == AGG_FWD;                 // layer-1 forward always applies the ReLU (flags checked on the host)
+    const uint32_t thresh_hi = p.drop_thresh16 << 16;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    int g = 0, acc = 0; uint32_t aph = 0;
+    int b = it0 / p.slabs, sl = it0 - b * p.slabs;
+    for (int it = it0; it < it1; ++it) {
+      for (int t = 0; t < tiles_per_item; ++t, ++g) {
+        const int buf = g & 1;
+        const int col0 = (sl * tiles_per_item + t) * MT, col = col0 + cl;
+        __nv_bfloat16* st_hi = reinterpret_cast<__nv_bfloat16*>(sm + p.off_out + (size_t)buf * planes * p.out_plane);
+        __nv_bfloat16* st_lo = st_hi + p.out_plane / 2;
+        float best = -1.f; int barg = 0;
+        // dropout: one counter hash per (pair of node rows, column)
+        const uint32_t ctr0 = (((uint32_t)b * (uint32_t)((K + 1) >> 1)) * (uint32_t)p.out_dim + (uint32_t)col) ^ key;
+        auto chunk = [&](const uint32_t (&r)[16], int i0) {       // rows [i0, min(i0 + 16, r1))
+          if (MODE == AGG_FWD_POOL) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float v = fmaxf(__uint_as_float(r[e]), 0.f);
+              if (i0 + e < r1 && v > best) { best = v; barg = i0 + e; }   // strict > : first index on ties
+            }
+          } else {
+            __nv_bfloat16* h0 = st_hi + i0 * MT + cl;
+            __nv_bfloat16* l0 = st_lo + i0 * MT + cl;
+            const uint32_t cbase = ctr0 + (uint32_t)(i0 >> 1) * (uint32_t)p.out_dim;
+            if (i0 + FR == r1) {                          // the whole group in one chunk: straight-line code, no bounds checks
+#pragma unroll
+              for (int e = 0; e < FR; e += 2) {
+                const uint32_t rnd = DROP ? hash32(cbase + (uint32_t)(e >> 1) * (uint32_t)p.out_dim) : 0u;
+                epi_pair<WITH_LO, DROP, RELU>(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), true, rnd, thresh_hi, h0 + e * MT, l0 + e * MT);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; e += 2) {
+                if (i0 + e < r1) {
+                  const uint32_t rnd = DROP ? hash32(cbase + (uint32_t)(e >> 1) * (uint32_t)p.out_dim) : 0u;
+                  epi_pair<WITH_LO, DROP, RELU>(__uint_as_float(r[e]), __uint_as_float(r[e + 1]), i0 + e + 1 < r1, rnd, thresh_hi, h0 + e * MT, l0 + e * MT);
+                }
+              }
+            }
+          }
+        };
+        if (lane == 0) {                                  // one poller per warp
+          mbar_wait(&tfull[acc], aph);
+          if (MODE != AGG_FWD_POOL) mbar_wait(&sempty[buf], ((g >> 1) & 1) ^ 1);   // the store of two tiles ago has read this staging buffer
+        }
+        __syncwarp();
+        tc_fence_after();
+        if (leader) TL(4, g);
+        if (!(p.flags & 0x100)) {                         // DEBUG 0x100: skip element work
+          for (int i0 = r0; i0 < r1; i0 += 32) {
+            uint32_t ra[16], rb[16];
+            const bool two = i0 + 16 < r1;                // both TMEM loads in flight before the wait
+            tc_ld_32x16(lane_base + (uint32_t)(acc * NP + i0), ra);
+            if (two) tc_ld_32x16(lane_base + (uint32_t)(acc * NP + i0 + 16), rb);
+            tc_wait_ld();
+            chunk(ra, i0);
+            if (two) chunk(rb, i0 + 16);
+          }
+        }
+        tc_fence_before();
+        if (MODE == AGG_FWD_POOL) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);       // accumulator drained: one arrival per epilogue warp
+          float* pool_v = reinterpret_cast<float*>(sm + p.off_pool) + (g & 1) * 2 * P_EG * MT;   // scratch double-buffered by tile
+          int* pool_a = reinterpret_cast<int*>(pool_v + P_EG * MT);                             // parity: one barrier per tile
+          if (grp > 0) { pool_v[grp * MT + cl] = best; pool_a[grp * MT + cl] = barg; }
+          named_bar_sync(1, P_EPI);
+          if (grp == 0) {
+#pragma unroll
+            for (int o = 1; o < P_EG; ++o) {              // groups hold increasing row ranges: strict > keeps the first index on ties
+              const float ov = pool_v[o * MT + cl]; const int oa = pool_a[o * MT + cl];
+              if (ov > best) { best = ov; barg = oa; }
+            }
+            const long long o = (long long)b * p.out_dim + col;
+            p.pooled[o] = best;
+            p.argmax[o] = barg;
+            p.hq[o] = fmaxf(p.q[o], 0.f) * best;
+          }
+        } else {
+          fence_proxy_async();                            // staging writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(&tempty[acc]); mbar_arrive(&sfull[buf]); }
+        }
+        if (leader) TL(5, g);
+        if (++acc == NACC) { acc = 0; aph ^= 1; }
+      }
+      if (++sl == p.slabs) { sl = 0; ++b; }
+    }
+  } else if (warp < P_W_ST) {
+    // ------------------------------------------------------------ coefficient builders
+    const int bt = tid - P_W_BLD * 32;
+    const int E = K * p.nb, nkc = p.nkc, nk = p.nk;
+    float pc[P_CH][P_MAXKC]; unsigned po[P_CH];
+    auto load_chunk = [&](int it, int ch) {               // edge values of item `it`, chunk `ch`, into registers
+      const int b = it / p.slabs, k_lo = (it - b * p.slabs) * nkc;
+#pragma unroll
+      for (int u = 0; u < P_CH; ++u) {
+        const int e = (ch * P_CH + u) * P_BLD + bt;
+        if (e < E) {
+          const long long ge = (long long)b * E + e;
+          po[u] = p.eoff[ge];
+#pragma unroll
+          for (int kk = 0; kk < P_MAXKC; ++kk)
+            if (kk < nkc) pc[u][kk] = p.coef[ge * nk + k_lo + kk];
+        }
+      }
+    };
+    const int nchunks = (E + P_CH * P_BLD - 1) / (P_CH * P_BLD);
+    if (it0 < it1) load_chunk(it0, 0);
+    int n = 0;
+    for (int it = it0; it < it1; ++it, ++n) {
+      const int cb = n & 1;
+      if (bt == 0) TL(8, 2 * n);
+      if (lane == 0) mbar_wait(&cempty[cb], ((n >> 1) & 1) ^ 1);   // every issuer's MMAs of two items ago are done with this buffer
+      __syncwarp();
+      if (bt == 0) TL(8, 2 * n + 1);
+      uint8_t* cbase = sm + p.off_coef + (size_t)cb * p.coef_buf;
+      if (!(p.flags & 0x400)) {                           // DEBUG 0x400: skip coefficient build
+        uint4* cz = reinterpret_cast<uint4*>(cbase);
+        const int n16 = nkc * planes * p.coef_plane / 16;
+        for (int v = bt; v < n16; v += P_BLD) cz[v] = make_uint4(0u, 0u, 0u, 0u);
+        named_bar_sync(2, P_BLD);
+        for (int ch = 0; ch < nchunks; ++ch) {
+          if (ch > 0) load_chunk(it, ch);
+#pragma unroll
+          for (int u = 0; u < P_CH; ++u) {
+            const int e = (ch * P_CH + u) * P_BLD + bt;
+            if (e < E) {
+              const uint32_t off = MODE == AGG_BWD ? (po[u] >> 16) : (po[u] & 0xFFFFu);   // bwd: dY[j] += c * dO[i]  (transposed matrix)
+#pragma unroll
+              for (int kk = 0; kk < P_MAXKC; ++kk) {
+                if (kk < nkc) {
+                  // the dropout scale 1/(1-p) rides on the coefficients (ReLU commutes with a positive scale)
+                  const float c = DROP ? pc[u][kk] * p.drop_scale : pc[u][kk];
+                  const __nv_bfloat16 h = __float2bfloat16_rn(c);
+                  uint8_t* base = cbase + (size_t)(kk * planes) * p.coef_plane;
+                  *reinterpret_cast<__nv_bfloat16*>(base + off) = h;
+                  if (WITH_LO) *reinterpret_cast<__nv_bfloat16*>(base + p.coef_plane + off) = __float2bfloat16_rn(c - __bfloat162float(h));
+                }
+              }
+            }
+          }
+        }
+      }
+      fence_proxy_async();                                // generic-proxy smem writes -> visible to the tensor core
+      named_bar_sync(2, P_BLD);
+      if (bt == 0) mbar_arrive(&cfull[cb]);
+      if (bt == 0) TL(9, 2 * n);
+      if (it + 1 < it1) load_chunk(it + 1, 0);            // next item's values in flight while waiting for its buffer
+    }
+  } else if (MODE != AGG_FWD_POOL) {
+    // ------------------------------------------------------------ last warp: TMA stores of the staged tiles
+    if (lane == 0) {
+      int g = 0;
+      int b = it0 / p.slabs, sl = it0 - b * p.slabs;
+      for (int it = it0; it < it1; ++it) {
+        for (int t = 0; t < tiles_per_item; ++t, ++g) {
+          const int buf = g & 1;
+          const int col0 = (sl * tiles_per_item + t) * MT;
+          const uint8_t* st_hi = sm + p.off_out + (size_t)buf * planes * p.out_plane;
+          mbar_wait(&sfull[buf], (g >> 1) & 1);
+          TL(6, g);
+          if (!(p.flags & 0x200)) {                       // DEBUG 0x200: skip stores
+            tma_store_2d(&tm.out_hi, st_hi, col0, b * K);
+            if (WITH_LO) tma_store_2d(&tm.out_lo, st_hi + p.out_plane, col0, b * K);
+          }
+          bulk_commit();
+          bulk_wait_read<0>();                            // ~18 KB of shared memory read: a few hundred cycles
+          mbar_arrive(&sempty[buf]);                      // staging buffer free again
+          TL(7, g);
+        }
+        if (++sl == p.slabs) { sl = 0; ++b; }
+      }
+      bulk_wait_read<0>();
+    }
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -658,6 +1079,59 @@ static int agg_launch(const void* in_hi, const void* in_lo, long long ldin, void
     if (!rc && p.with_lo) rc = make_plane_map(&tm.out_lo, out_lo, ldout, rows, p.out_dim, MT, K, false);
   }
   if (rc) return rc;
+  // ---- preferred: the persistent, fully warp-specialised kernel (one CTA per SM)
+  Maps tm2 = tm;                                             // its input boxes hold exactly K rows (no over-read into the next image)
+  if (int rc2 = make_plane_map(&tm2.in_hi, in_hi, ldin, rows, p.out_dim, 64, K, true)) return rc2;
+  if (p.with_lo) { if (int rc2 = make_plane_map(&tm2.in_lo, in_lo, ldin, rows, p.out_dim, 64, K, true)) return rc2; }
+  static const bool force_v1 = getenv("VQA_AGG_V1") != nullptr;
+  if (!force_v1 && p.coef && p.eoff && (MODE != AGG_FWD || (p.flags & VQA_GC_RELU))) {
+    Agg2Params a{};
+    a.coef = p.coef; a.eoff = p.eoff;
+    a.q = p.q; a.pooled = p.pooled; a.argmax = p.argmax; a.hq = p.hq;
+    a.B = B; a.K = K; a.KP = KP; a.nb = p.nb; a.nk = p.nk; a.out_dim = p.out_dim; a.D = p.D; a.flags = p.flags; a.with_lo = p.with_lo;
+    if (const char* dbg = getenv("VQA_AGG_DBG")) a.flags |= atoi(dbg);
+    a.drop_scale = p.drop_scale; a.drop_thresh16 = p.drop_thresh16; a.seed = p.seed; a.offset = p.offset; a.step_ptr = p.step_ptr;
+    a.tpk = tpk;
+    int nkc2 = (4 + tpk - 1) / tpk;                           // ~4 M-tiles per item
+    if (nkc2 > p.nk) nkc2 = p.nk;
+    if (nkc2 > P_MAXKC) nkc2 = P_MAXKC;
+    while (p.nk % nkc2) --nkc2;                               // slabs tile the kernel axis exactly
+    a.nkc = nkc2; a.slabs = p.nk / nkc2; a.nitems = B * a.slabs;
+    a.coef_plane = p.coef_plane; a.coef_buf = nkc2 * planes * p.coef_plane; a.stage_bytes = p.stage_bytes; a.out_plane = p.out_plane;
+    const int pool = MODE == AGG_FWD_POOL ? 2 * P_EG * MT * 8 : 0;
+    a.rpg = (((K + P_EG - 1) / P_EG) + 1) & ~1;               // node rows per epilogue group (even: dropout hashes cover row pairs)
+    const int fixed2 = 2 * a.coef_buf + 2 * planes * p.out_plane + pool + 1024;
+    int S2 = (226 * 1024 - 2048 - fixed2) / p.stage_bytes;
+    if (S2 >= 2) {
+      if (S2 > 8) S2 = 8;
+      if (const char* e = getenv("VQA_AGG_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= S2) S2 = v; }
+      a.nstage = S2;
+      int o2 = 0;
+      a.off_coef = o2; o2 += 2 * a.coef_buf; o2 = (o2 + 1023) & ~1023;
+      a.off_stage = o2; o2 += S2 * p.stage_bytes;
+      a.off_out = o2; o2 += 2 * planes * p.out_plane; o2 = (o2 + 127) & ~127;
+      a.off_pool = o2; o2 += pool;
+      a.off_bars = o2; o2 += (2 * S2 + 26) * 8;
+      a.nacc = (512 - 16) / KP < 4 ? (512 - 16) / KP : 4;     // accumulators in flight between the MMA issuers and the epilogue
+      a.tmem_cols = 32; while (a.tmem_cols < a.nacc * KP + 16) a.tmem_cols <<= 1;   // +16: the last 16-column epilogue read may overhang
+      const size_t smem2 = (size_t)o2 + 1024;
+      int grid2 = kNumSMs < a.nitems ? kNumSMs : a.nitems;
+      const bool dropk = MODE == AGG_FWD && a.drop_thresh16 != 0;
+      auto go = [&](auto kern) -> int {
+        VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        kern<<<grid2, P_THREADS, smem2, stream>>>(tm2, a);
+        VQA_LAUNCH_CHECK("graphconv agg_persistent_kernel");
+        return VQA_OK;
+      };
+      const bool fr12 = a.rpg == 12;                          // K = 36: three groups of exactly 12 rows
+      if (MODE == AGG_FWD && dropk) {
+        if (a.with_lo) return fr12 ? go(agg_persistent_kernel<MODE, true, MODE == AGG_FWD, 12>) : go(agg_persistent_kernel<MODE, true, MODE == AGG_FWD, 16>);
+        return fr12 ? go(agg_persistent_kernel<MODE, false, MODE == AGG_FWD, 12>) : go(agg_persistent_kernel<MODE, false, MODE == AGG_FWD, 16>);
+      }
+      if (a.with_lo) return fr12 ? go(agg_persistent_kernel<MODE, true, false, 12>) : go(agg_persistent_kernel<MODE, true, false, 16>);
+      return fr12 ? go(agg_persistent_kernel<MODE, false, false, 12>) : go(agg_persistent_kernel<MODE, false, false, 16>);
+    }
+  }
   dim3 grid((p.ntiles + p.tiles_per_cta - 1) / p.tiles_per_cta, B);
   VQA_CUDA(cudaFuncSetAttribute(agg_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   agg_kernel<MODE><<<grid, THREADS, smem, stream>>>(tm, p);
@@ -752,34 +1226,51 @@ extern "C" int vqa_graphconv_mma_fwd(const void* Y_hi, const void* Y_lo, long lo
                                      const float* boxes, long long ldbox, const float* gauss, void* out_hi, void* out_lo,
                                      long long ldo, int B, int K, int nb, int nk, int out_dim, int flags, float dropout_p,
                                      unsigned long long seed, unsigned long long offset, const unsigned long long* step_ptr,
-                                     cudaStream_t stream) {
+                                     const float* coef, const unsigned* eoff, cudaStream_t stream) {
   VQA_CHECK_ARG(idx && boxes && gauss, "vqa_graphconv_mma_fwd: null pointer");
   VQA_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "vqa_graphconv_mma_fwd: dropout p must be in [0,1)");
   gm::AggParams p{};
   p.idx = idx; p.alpha = alpha; p.boxes = boxes; p.ldbox = ldbox; p.gauss = gauss;
   p.B = B; p.K = K; p.nb = nb; p.nk = nk; p.out_dim = out_dim; p.flags = flags;
   p.drop_scale = 1.f / (1.f - dropout_p); p.drop_thresh16 = (unsigned)(dropout_p * 65536.f + 0.5f);
-  p.seed = seed; p.offset = offset; p.step_ptr = step_ptr;
+  p.seed = seed; p.offset = offset; p.step_ptr = step_ptr; p.coef = coef; p.eoff = eoff;
   return gm::agg_launch<gm::AGG_FWD>(Y_hi, Y_lo, ldy, out_hi, out_lo, ldo, p, stream, "vqa_graphconv_mma_fwd");
 }
 
 extern "C" int vqa_graphconv_mma_pool_fwd(const void* Y_hi, const void* Y_lo, long long ldy, const int* idx, const float* boxes,
                                           long long ldbox, const float* gauss, const float* q, float* pooled, long long* argmax,
-                                          float* hq, int B, int K, int nb, int nk, int out_dim, cudaStream_t stream) {
+                                          float* hq, int B, int K, int nb, int nk, int out_dim, const float* coef,
+                                          const unsigned* eoff, cudaStream_t stream) {
   VQA_CHECK_ARG(idx && boxes && gauss && q && pooled && argmax && hq, "vqa_graphconv_mma_pool_fwd: null pointer");
   gm::AggParams p{};
   p.idx = idx; p.alpha = nullptr; p.boxes = boxes; p.ldbox = ldbox; p.gauss = gauss;
   p.q = q; p.pooled = pooled; p.argmax = argmax; p.hq = hq;
-  p.B = B; p.K = K; p.nb = nb; p.nk = nk; p.out_dim = out_dim; p.flags = VQA_GC_RELU;
+  p.B = B; p.K = K; p.nb = nb; p.nk = nk; p.out_dim = out_dim; p.flags = VQA_GC_RELU; p.coef = coef; p.eoff = eoff;
   return gm::agg_launch<gm::AGG_FWD_POOL>(Y_hi, Y_lo, ldy, nullptr, nullptr, 0, p, stream, "vqa_graphconv_mma_pool_fwd");
 }
 
 extern "C" int vqa_graphconv_mma_bwd_data(const void* dO_hi, const void* dO_lo, long long lddo, const int* idx, const float* alpha,
                                           const float* boxes, long long ldbox, const float* gauss, void* dY_hi, void* dY_lo,
-                                          long long lddy, int B, int K, int nb, int nk, int out_dim, cudaStream_t stream) {
+                                          long long lddy, int B, int K, int nb, int nk, int out_dim, const float* coef,
+                                          const unsigned* eoff, cudaStream_t stream) {
   VQA_CHECK_ARG(idx && boxes && gauss, "vqa_graphconv_mma_bwd_data: null pointer");
   gm::AggParams p{};
   p.idx = idx; p.alpha = alpha; p.boxes = boxes; p.ldbox = ldbox; p.gauss = gauss;
-  p.B = B; p.K = K; p.nb = nb; p.nk = nk; p.out_dim = out_dim;
+  p.B = B; p.K = K; p.nb = nb; p.nk = nk; p.out_dim = out_dim; p.coef = coef; p.eoff = eoff;
   return gm::agg_launch<gm::AGG_BWD>(dO_hi, dO_lo, lddo, dY_hi, dY_lo, lddy, p, stream, "vqa_graphconv_mma_bwd_data");
+}
+
+extern "C" int vqa_graphconv_edge_coef(const int* idx, const float* alpha, const float* boxes, long long ldbox, const float* gauss,
+                                       float* coef, unsigned* eoff, int B, int K, int nb, int nk, cudaStream_t stream) {
+  VQA_CHECK_ARG(idx && boxes && gauss && coef && eoff, "vqa_graphconv_edge_coef: null pointer");
+  VQA_CHECK_ARG(B > 0 && K > 0 && K <= 128 && nb > 0 && nb <= K && nk > 0 && nk <= gm::MAX_NK, "vqa_graphconv_edge_coef: bad sizes (B=%d K=%d nb=%d nk=%d)", B, K, nb, nk);
+  const long long n_edges = (long long)B * K * nb;
+  const int KP = (K + 15) & ~15;
+  gm::edge_coef_kernel<<<(unsigned)((n_edges + 255) / 256), 256, 0, stream>>>(idx, alpha, boxes, ldbox, gauss, coef, eoff, n_edges, K, nb, nk, KP);
+  VQA_LAUNCH_CHECK("graphconv edge_coef_kernel");
+  return VQA_OK;
+}
+
+extern "C" int vqa_debug_agg_timeline(long long* host_out) {      // DEBUG: not part of the ABI
+  return (int)cudaMemcpyFromSymbol(host_out, vqa::gm::g_timeline, sizeof(long long) * 10 * vqa::gm::TL_N);
 }

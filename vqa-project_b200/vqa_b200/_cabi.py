@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqa_sm100.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 PREC_TF32X3 = 0
 PREC_TF32 = 1
 PREC_TF32X3_HP = 2
@@ -44,9 +44,10 @@ SIGNATURES = {
     "vqa_graphconv_fwd_f32": [_p, _ll, _p, _p, _p, _ll, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _f, _u64, _u64, _p, _p],
     "vqa_graphconv_pool_fwd_f32": [_p, _ll, _p, _p, _ll, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "vqa_graphconv_bwd_f32": [_p, _ll, _p, _p, _p, _ll, _p, _p, _p, _ll, _p, _p, _ll, _p, _i, _i, _i, _i, _i, _p],
-    "vqa_graphconv_mma_fwd": [_p, _p, _ll, _p, _p, _p, _ll, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _f, _u64, _u64, _p, _p],
-    "vqa_graphconv_mma_pool_fwd": [_p, _p, _ll, _p, _p, _ll, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
-    "vqa_graphconv_mma_bwd_data": [_p, _p, _ll, _p, _p, _p, _ll, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _p],
+    "vqa_graphconv_edge_coef": [_p, _p, _p, _ll, _p, _p, _p, _i, _i, _i, _i, _p],
+    "vqa_graphconv_mma_fwd": [_p, _p, _ll, _p, _p, _p, _ll, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _f, _u64, _u64, _p, _p, _p, _p],
+    "vqa_graphconv_mma_pool_fwd": [_p, _p, _ll, _p, _p, _ll, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p],
+    "vqa_graphconv_mma_bwd_data": [_p, _p, _ll, _p, _p, _p, _ll, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _p, _p, _p],
     "vqa_graphconv_mma_bwd_edges": [_p, _p, _ll, _p, _p, _p, _p, _ll, _p, _p, _p, _ll, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "vqa_graphconv_edge_blocks": [_i, _i, _i],
     "vqa_graphconv_edge_bwd_f32": [_p, _p, _p, _p, _ll, _p, _p, _p, _i, _i, _i, _i, _p],

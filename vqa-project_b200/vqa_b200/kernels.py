@@ -359,37 +359,55 @@ def mma_eligible(K: int, out_dim: int, nk: int) -> bool:
     return K <= 128 and out_dim % nk == 0 and (out_dim // nk) % 128 == 0
 
 
-def graphconv_fwd_s(Ys: SplitT, idx, alpha, image, gauss, B, K, relu=True, dropout_p=0.0, seed=0, offset=0, step=None) -> SplitT:
-    """Layer-1 style aggregate on planes: Ys (B*K, out) -> relu/dropout(aggregate) as planes."""
+def graphconv_edge_coef(idx, alpha, image, gauss, B, K):
+    """Per-edge coefficients of one layer, evaluated once per step: (coef (B,K,nb,nk) f32 = normalised Gaussian weight * alpha,
+    eoff (B,K,nb) i32 = packed positions inside the shared-memory coefficient matrices).  Feeds the three aggregates below."""
+    nb, nk = idx.shape[-1], gauss.numel() // 4
+    bptr, ldbox = _boxes_view(image)
+    coef = torch.empty((B, K, nb, nk), device=idx.device, dtype=torch.float32)
+    eoff = torch.empty((B, K, nb), device=idx.device, dtype=torch.int32)
+    _call("vqa_graphconv_edge_coef", idx.data_ptr(), _ptr(alpha), bptr, ldbox, gauss.data_ptr(), coef.data_ptr(), eoff.data_ptr(),
+          B, K, nb, nk, _stream())
+    return coef, eoff
+
+
+def graphconv_fwd_s(Ys: SplitT, idx, alpha, image, gauss, B, K, relu=True, dropout_p=0.0, seed=0, offset=0, step=None, ec=None) -> SplitT:
+    """Layer-1 style aggregate on planes: Ys (B*K, out) -> relu/dropout(aggregate) as planes.  ec: graphconv_edge_coef() result."""
     nb, nk, out_dim = idx.shape[-1], gauss.numel() // 4, Ys.cols
     bptr, ldbox = _boxes_view(image)
+    if ec is None:
+        ec = graphconv_edge_coef(idx, alpha, image, gauss, B, K)
     out = empty_split(B * K, out_dim, Ys.hi.device, Ys.lo is not None)
     _call("vqa_graphconv_mma_fwd", Ys.hi.data_ptr(), _ptr(Ys.lo), Ys.ld, idx.data_ptr(), _ptr(alpha), bptr, ldbox, gauss.data_ptr(),
           out.hi.data_ptr(), _ptr(out.lo), out.ld, B, K, nb, nk, out_dim, GC_RELU if relu else 0, float(dropout_p), seed, offset,
-          _ptr(step), _stream())
+          _ptr(step), ec[0].data_ptr(), ec[1].data_ptr(), _stream())
     return out
 
 
-def graphconv_pool_fwd_s(Ys: SplitT, idx, image, gauss, q, B, K):
+def graphconv_pool_fwd_s(Ys: SplitT, idx, image, gauss, q, B, K, ec=None):
     nb, nk, out_dim = idx.shape[-1], gauss.numel() // 4, Ys.cols
     bptr, ldbox = _boxes_view(image)
+    if ec is None:
+        ec = graphconv_edge_coef(idx, None, image, gauss, B, K)
     q = _chk(q, "q").contiguous()
     dev = Ys.hi.device
     pooled = torch.empty((B, out_dim), device=dev, dtype=torch.float32)
     argmax = torch.empty((B, out_dim), device=dev, dtype=torch.int64)
     hq = torch.empty((B, out_dim), device=dev, dtype=torch.float32)
     _call("vqa_graphconv_mma_pool_fwd", Ys.hi.data_ptr(), _ptr(Ys.lo), Ys.ld, idx.data_ptr(), bptr, ldbox, gauss.data_ptr(), q.data_ptr(),
-          pooled.data_ptr(), argmax.data_ptr(), hq.data_ptr(), B, K, nb, nk, out_dim, _stream())
+          pooled.data_ptr(), argmax.data_ptr(), hq.data_ptr(), B, K, nb, nk, out_dim, ec[0].data_ptr(), ec[1].data_ptr(), _stream())
     return pooled, argmax, hq
 
 
-def graphconv_bwd_data_s(dOs: SplitT, idx, alpha, image, gauss, B, K) -> SplitT:
+def graphconv_bwd_data_s(dOs: SplitT, idx, alpha, image, gauss, B, K, ec=None) -> SplitT:
     """dY = M^T dO on planes."""
     nb, nk, out_dim = idx.shape[-1], gauss.numel() // 4, dOs.cols
     bptr, ldbox = _boxes_view(image)
+    if ec is None:
+        ec = graphconv_edge_coef(idx, alpha, image, gauss, B, K)
     out = empty_split(B * K, out_dim, dOs.hi.device, dOs.lo is not None)
     _call("vqa_graphconv_mma_bwd_data", dOs.hi.data_ptr(), _ptr(dOs.lo), dOs.ld, idx.data_ptr(), _ptr(alpha), bptr, ldbox, gauss.data_ptr(),
-          out.hi.data_ptr(), _ptr(out.lo), out.ld, B, K, nb, nk, out_dim, _stream())
+          out.hi.data_ptr(), _ptr(out.lo), out.ld, B, K, nb, nk, out_dim, ec[0].data_ptr(), ec[1].data_ptr(), _stream())
     return out
 
 

@@ -178,10 +178,12 @@ class ConditionedGraphFn(torch.autograd.Function):
         mma2 = kn.mma_eligible(K, Wc2s.rows, nk)
         with_lo = _PASSES == 3
         gseed, goff, gstep = next_philox(dev) if drop else (0, 0, None)
+        ec1 = None
         if mma1:
             Y1 = _gemm_s(Xs, Wc1s, out_split=kn.empty_split(B * K, Wc1s.rows, dev, with_lo), want_f32=False)   # planes only
+            ec1 = kn.graphconv_edge_coef(idx, alpha, image, gs1, B, K)      # edge coefficients: once per layer, reused by backward
             G1s = kn.graphconv_fwd_s(Y1, idx, alpha, image, gs1, B, K, relu=True, dropout_p=p_drop if drop else 0.0,
-                                     seed=gseed, offset=goff, step=gstep)
+                                     seed=gseed, offset=goff, step=gstep, ec=ec1)
         else:
             Y1 = _gemm_s(Xs, Wc1s)
             G1 = kn.graphconv_fwd(Y1, idx, alpha, image, gs1, B, K, relu=True, dropout_p=p_drop if drop else 0.0,
@@ -191,7 +193,7 @@ class ConditionedGraphFn(torch.autograd.Function):
         # graph convolution 2 with max-pool over nodes + question gate fused (sparse_graph_model.py:146-151)
         if mma2:
             Y2 = _gemm_s(G1s, Wc2s, out_split=kn.empty_split(B * K, Wc2s.rows, dev, with_lo), want_f32=False)
-            pooled, argmax, hq = kn.graphconv_pool_fwd_s(Y2, idx, image, gs2, qenc, B, K)
+            pooled, argmax, hq = kn.graphconv_pool_fwd_s(Y2, idx, image, gs2, qenc, B, K, ec=kn.graphconv_edge_coef(idx, None, image, gs2, B, K))
         else:
             Y2 = _gemm_s(G1s, Wc2s)
             pooled, argmax, hq = kn.graphconv_pool_fwd(Y2, idx, image, gs2, qenc, B, K)
@@ -206,6 +208,7 @@ class ConditionedGraphFn(torch.autograd.Function):
         logits = _gemm_s(o1s, Wo2s, bias=bo2)
 
         ctx.cfg = dict(B=B, K=K, F=F, H=H, nk=nk, nb=nb, scale=scale, mma1=mma1, mma2=mma2)
+        ctx.ec1 = ec1
         ctx.splits = (Xs, qs, h1s, G1s, hqs, o1s, W1qs, W2s, Wo1s, Wo2s, Wc1s, Wc2s, Y1, Y2)   # Y1/Y2: SplitT on the tensor-core path, fp32 else
         ctx.save_for_backward(image, qenc, v1, g1, v2, g2, vo1, go1, vo2, go2, gs1, gs2, h2, idx, alpha, pooled, argmax)
         ctx.mark_non_differentiable(argmax)
@@ -244,7 +247,7 @@ class ConditionedGraphFn(torch.autograd.Function):
         # graph convolution 1
         if c["mma1"]:
             dG1s = _gemm_s(dY2s, Wc2s, b_mn=True, aux=G1s, aux_scale=scale, out_split=kn.empty_split(M, G1s.cols, dev, with_lo), want_f32=False)
-            dY1s = kn.graphconv_bwd_data_s(dG1s, idx, alpha, image, gs1, B, K)          # dY = M^T dO on the tensor cores
+            dY1s = kn.graphconv_bwd_data_s(dG1s, idx, alpha, image, gs1, B, K, ec=ctx.ec1)   # dY = M^T dO on the tensor cores
             dalpha, dgs1 = kn.graphconv_bwd_edges_s(Y1, idx, alpha, image, gs1, B, K, dOs=dG1s)
         else:
             dG1 = _gemm_s(dY2s, Wc2s, b_mn=True, aux=G1s, aux_scale=scale)
