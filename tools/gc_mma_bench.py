@@ -10,7 +10,7 @@ def timeit(name, fn, nbytes, iters=7):
     for _ in range(2): fn()
     ts = []
     for _ in range(iters):
-        flush.zero_(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); torch.cuda._sleep(400000); flush.zero_(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)   # host runs ahead: no launch gap inside the bracket
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) * 1e3)
     t = sorted(ts)[len(ts) // 2]
     print(f"{name:44s} {t:8.1f} us  {nbytes / t / 1e3:7.1f} GB/s  {nbytes / t / 1e3 / 6544:5.3f} of HBM peak", flush=True)

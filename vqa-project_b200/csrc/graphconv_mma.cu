@@ -26,7 +26,6 @@
 #include <cuda_bf16.h>
 #include <mutex>
 #include <cstring>
-#include <cstdlib>
 #include "../../include/vqa_b200.h"
 
 namespace vqa {
@@ -413,11 +412,7 @@ struct Agg2Params {
   int off_coef, coef_plane, coef_buf, off_stage, stage_bytes, off_out, out_plane, off_pool, off_bars, tmem_cols;
 };
 
-// DEBUG timeline (flags 0x4000): per-role clock64 stamps of CTA 0's first TL_N tiles / items
-constexpr int TL_N = 96;
-__device__ long long g_timeline[10][TL_N];
-#define TL(row, i) do { if ((p.flags & 0x4000) && blockIdx.x == 0 && (i) < TL_N) g_timeline[row][i] = clock64(); } while (0)
-
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // FR: node rows per epilogue warp handled by straight-line code (the common case rpg == FR; anything else takes the
@@ -473,6 +468,19 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
     }
     fence_proxy_async();
   }
+ // the builders' first reads (edge coefficients of the first two images) go to L2 while the CTA sets itself up
+  auto prefetch_image = [&](int b, int t, int nthreads) {
+    const int E = K * p.nb;
+    const char* c0 = reinterpret_cast<const char*>(p.coef + (long long)b * E * p.nk);
+    const char* e0 = reinterpret_cast<const char*>(p.eoff + (long long)b * E);
+    for (int o = t * 128; o < E * p.nk * 4; o += nthreads * 128) prefetch_l2(c0 + o);
+    for (int o = t * 128; o < E * 4; o += nthreads * 128) prefetch_l2(e0 + o);
+  };
+  if (warp >= P_W_BLD && warp < P_W_ST && it0 < it1) {
+    const int b0 = it0 / p.slabs;
+    prefetch_image(b0, tid - P_W_BLD * 32, P_BLD);
+    if ((b0 + 1) * p.slabs < it1) prefetch_image(b0 + 1, tid - P_W_BLD * 32, P_BLD);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -486,7 +494,6 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
       for (int it = it0; it < it1; ++it) {
         for (int t = 0; t < tiles_per_item; ++t, ++g) {
           mbar_wait(&empty[s], sph ^ 1);
-          TL(0, g);
           mbar_arrive_expect_tx(&full[s], (uint32_t)(planes * 2 * K * 128));   // boxes hold exactly the image's K rows
           uint8_t* dst = sm + p.off_stage + (size_t)s * p.stage_bytes;
           const int c0 = (sl * tiles_per_item + t) * MT;
@@ -522,10 +529,8 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
           if (owner != me) continue;
           if (!waited) { mbar_wait(&cfull[cb], (n >> 1) & 1); waited = true; }
           mbar_wait(&tempty[acc], aph ^ 1);
-          TL(1, g);
           mbar_wait(&full[s], sph);
           tc_fence_after();
-          TL(2, g);
           const uint32_t a_hi = smem_u32(sm + p.off_stage + (size_t)s * p.stage_bytes), a_lo = a_hi + 2 * KP * 128;
           const uint32_t b_hi = smem_u32(sm + p.off_coef + (size_t)cb * p.coef_buf + (size_t)(kcur * planes) * p.coef_plane), b_lo = b_hi + p.coef_plane;
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NP);
@@ -545,7 +550,6 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
           tc_commit(&tfull[acc]);
           mine = t + P_NI >= tiles_per_item;                        // my last tile of this item
           if (mine) tc_commit(&cempty[cb]);                          // coefficient buffer free once every issuer's MMAs of the item retire
-          TL(3, g);
         }
         if (!mine) mbar_arrive(&cempty[cb]);                        // no tile of this item was mine
       }
@@ -553,13 +557,11 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
     __syncwarp();
   } else if (warp < P_W_BLD) {
     // ------------------------------------------------------------ epilogue, thread = output column, P_EG warps per lane quarter
-    const int et = tid - 128;
     const int q4 = warp & 3, grp = (warp - 4) >> 2;
     const int r0 = grp * p.rpg, r1 = min(K, r0 + p.rpg);   // my node rows
     const int cl = q4 * 32 + lane;
     const unsigned long long rng_off = p.offset + (p.step_ptr ? *p.step_ptr * 16ull : 0ull);
     const uint32_t key = hash32((uint32_t)p.seed ^ hash32((uint32_t)(p.seed >> 32) ^ hash32((uint32_t)rng_off * 0x9E3779B1u + 0x85EBCA77u)));
-    const bool leader = et == 0;
     constexpr bool RELU = MODE == AGG_FWD;                 // layer-1 forward always applies the ReLU (flags checked on the host)
     const uint32_t thresh_hi = p.drop_thresh16 << 16;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
@@ -602,14 +604,15 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
             }
           }
         };
+        float qv = 0.f;
+        if (MODE == AGG_FWD_POOL && grp == 0) qv = p.q[(long long)b * p.out_dim + col];   // in flight during the wait
         if (lane == 0) {                                  // one poller per warp
           mbar_wait(&tfull[acc], aph);
           if (MODE != AGG_FWD_POOL) mbar_wait(&sempty[buf], ((g >> 1) & 1) ^ 1);   // the store of two tiles ago has read this staging buffer
         }
         __syncwarp();
         tc_fence_after();
-        if (leader) TL(4, g);
-        if (!(p.flags & 0x100)) {                         // DEBUG 0x100: skip element work
+        {
           for (int i0 = r0; i0 < r1; i0 += 32) {
             uint32_t ra[16], rb[16];
             const bool two = i0 + 16 < r1;                // both TMEM loads in flight before the wait
@@ -637,14 +640,13 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
             const long long o = (long long)b * p.out_dim + col;
             p.pooled[o] = best;
             p.argmax[o] = barg;
-            p.hq[o] = fmaxf(p.q[o], 0.f) * best;
+            p.hq[o] = fmaxf(qv, 0.f) * best;
           }
         } else {
           fence_proxy_async();                            // staging writes -> visible to the TMA store
           __syncwarp();
           if (lane == 0) { mbar_arrive(&tempty[acc]); mbar_arrive(&sfull[buf]); }
         }
-        if (leader) TL(5, g);
         if (++acc == NACC) { acc = 0; aph ^= 1; }
       }
       if (++sl == p.slabs) { sl = 0; ++b; }
@@ -673,12 +675,10 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
     int n = 0;
     for (int it = it0; it < it1; ++it, ++n) {
       const int cb = n & 1;
-      if (bt == 0) TL(8, 2 * n);
       if (lane == 0) mbar_wait(&cempty[cb], ((n >> 1) & 1) ^ 1);   // every issuer's MMAs of two items ago are done with this buffer
       __syncwarp();
-      if (bt == 0) TL(8, 2 * n + 1);
       uint8_t* cbase = sm + p.off_coef + (size_t)cb * p.coef_buf;
-      if (!(p.flags & 0x400)) {                           // DEBUG 0x400: skip coefficient build
+      {
         uint4* cz = reinterpret_cast<uint4*>(cbase);
         const int n16 = nkc * planes * p.coef_plane / 16;
         for (int v = bt; v < n16; v += P_BLD) cz[v] = make_uint4(0u, 0u, 0u, 0u);
@@ -708,8 +708,11 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
       fence_proxy_async();                                // generic-proxy smem writes -> visible to the tensor core
       named_bar_sync(2, P_BLD);
       if (bt == 0) mbar_arrive(&cfull[cb]);
-      if (bt == 0) TL(9, 2 * n);
       if (it + 1 < it1) load_chunk(it + 1, 0);            // next item's values in flight while waiting for its buffer
+      {                                                   // two images ahead -> L2 (an LDG to cold HBM lines takes microseconds
+        const int b = it / p.slabs;                       // while the TMA streams saturate the memory system)
+        if (it == b * p.slabs && (b + 2) * p.slabs < it1) prefetch_image(b + 2, bt, P_BLD);
+      }
     }
   } else if (MODE != AGG_FWD_POOL) {
     // ------------------------------------------------------------ last warp: TMA stores of the staged tiles
@@ -722,15 +725,11 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
           const int col0 = (sl * tiles_per_item + t) * MT;
           const uint8_t* st_hi = sm + p.off_out + (size_t)buf * planes * p.out_plane;
           mbar_wait(&sfull[buf], (g >> 1) & 1);
-          TL(6, g);
-          if (!(p.flags & 0x200)) {                       // DEBUG 0x200: skip stores
-            tma_store_2d(&tm.out_hi, st_hi, col0, b * K);
-            if (WITH_LO) tma_store_2d(&tm.out_lo, st_hi + p.out_plane, col0, b * K);
-          }
+          tma_store_2d(&tm.out_hi, st_hi, col0, b * K);
+          if (WITH_LO) tma_store_2d(&tm.out_lo, st_hi + p.out_plane, col0, b * K);
           bulk_commit();
           bulk_wait_read<0>();                            // ~18 KB of shared memory read: a few hundred cycles
           mbar_arrive(&sempty[buf]);                      // staging buffer free again
-          TL(7, g);
         }
         if (++sl == p.slabs) { sl = 0; ++b; }
       }
@@ -1083,13 +1082,11 @@ static int agg_launch(const void* in_hi, const void* in_lo, long long ldin, void
   Maps tm2 = tm;                                             // its input boxes hold exactly K rows (no over-read into the next image)
   if (int rc2 = make_plane_map(&tm2.in_hi, in_hi, ldin, rows, p.out_dim, 64, K, true)) return rc2;
   if (p.with_lo) { if (int rc2 = make_plane_map(&tm2.in_lo, in_lo, ldin, rows, p.out_dim, 64, K, true)) return rc2; }
-  static const bool force_v1 = getenv("VQA_AGG_V1") != nullptr;
-  if (!force_v1 && p.coef && p.eoff && (MODE != AGG_FWD || (p.flags & VQA_GC_RELU))) {
+  if (p.coef && p.eoff && (MODE != AGG_FWD || (p.flags & VQA_GC_RELU))) {
     Agg2Params a{};
     a.coef = p.coef; a.eoff = p.eoff;
     a.q = p.q; a.pooled = p.pooled; a.argmax = p.argmax; a.hq = p.hq;
     a.B = B; a.K = K; a.KP = KP; a.nb = p.nb; a.nk = p.nk; a.out_dim = p.out_dim; a.D = p.D; a.flags = p.flags; a.with_lo = p.with_lo;
-    if (const char* dbg = getenv("VQA_AGG_DBG")) a.flags |= atoi(dbg);
     a.drop_scale = p.drop_scale; a.drop_thresh16 = p.drop_thresh16; a.seed = p.seed; a.offset = p.offset; a.step_ptr = p.step_ptr;
     a.tpk = tpk;
     int nkc2 = (4 + tpk - 1) / tpk;                           // ~4 M-tiles per item
@@ -1104,7 +1101,6 @@ static int agg_launch(const void* in_hi, const void* in_lo, long long ldin, void
     int S2 = (226 * 1024 - 2048 - fixed2) / p.stage_bytes;
     if (S2 >= 2) {
       if (S2 > 8) S2 = 8;
-      if (const char* e = getenv("VQA_AGG_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= S2) S2 = v; }
       a.nstage = S2;
       int o2 = 0;
       a.off_coef = o2; o2 += 2 * a.coef_buf; o2 = (o2 + 1023) & ~1023;
@@ -1269,8 +1265,4 @@ extern "C" int vqa_graphconv_edge_coef(const int* idx, const float* alpha, const
   gm::edge_coef_kernel<<<(unsigned)((n_edges + 255) / 256), 256, 0, stream>>>(idx, alpha, boxes, ldbox, gauss, coef, eoff, n_edges, K, nb, nk, KP);
   VQA_LAUNCH_CHECK("graphconv edge_coef_kernel");
   return VQA_OK;
-}
-
-extern "C" int vqa_debug_agg_timeline(long long* host_out) {      // DEBUG: not part of the ABI
-  return (int)cudaMemcpyFromSymbol(host_out, vqa::gm::g_timeline, sizeof(long long) * 10 * vqa::gm::TL_N);
 }
