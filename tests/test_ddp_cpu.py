@@ -62,11 +62,68 @@ def test_two_rank_training_equals_single_process_on_the_concatenated_batch():
 def test_reducer_single_process_keeps_views_and_zeroes():
     sys.path[:0] = [ROOT, os.path.join(ROOT, "vqa-project_b200")]
     from vqa_b200.ddp import GradReducer
-    net = torch.nn.Linear(5, 4)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Linear(4, 3))
     red = GradReducer(net.parameters())
-    net(torch.randn(3, 5)).sum().backward()
+    w = net[0].weight
+
+    def in_flat(p):
+        return p.grad.data_ptr() == red.flat.data_ptr() + p._vqa_flat_off * 4
+
+    # registration order inside the flat buffer (consecutive conv weights stay consecutive), buckets cover it exactly once
+    offs = [p._vqa_flat_off for p in net.parameters()]
+    assert offs == sorted(offs)
+    covered = sorted((s.start, s.stop) for s in red.bucket_slices)
+    assert covered[0][0] == 0 and covered[-1][1] == red.flat.numel()
+    assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    net(torch.randn(3, 5)).sum().backward()               # .grad defined: autograd accumulates in place
     red.finish()
-    assert net.weight.grad.data_ptr() == red.flat.data_ptr() + net.weight._vqa_flat_off * 4
-    assert red.flat.abs().sum() > 0
+    assert all(in_flat(p) for p in net.parameters()) and red.flat.abs().sum() > 0
+    # default step start: gradients dropped, nothing zeroed; a gradient produced outside the sink is moved into its view
     red.zero_grad()
-    assert red.flat.abs().sum() == 0 and net.weight.grad.abs().sum() == 0
+    assert all(p.grad is None for p in net.parameters())
+    assert red.sink(w) is not None and red.sink(w).data_ptr() == red.flat.data_ptr() + w._vqa_flat_off * 4
+    x = torch.randn(3, 5)
+    net(x).sum().backward()
+    red.finish()
+    assert all(in_flat(p) for p in net.parameters())
+    ref = torch.nn.Sequential(torch.nn.Linear(5, 4), torch.nn.Linear(4, 3))
+    ref.load_state_dict(net.state_dict())
+    ref(x).sum().backward()
+    assert all(torch.allclose(a.grad, b.grad) for a, b in zip(net.parameters(), ref.parameters()))
+    assert red.sink(w) is None                            # .grad exists: accumulation is autograd's job
+    # accumulation mode: one memset, views kept
+    red.zero_grad(set_to_none=False)
+    assert red.flat.abs().sum() == 0 and w.grad.abs().sum() == 0 and in_flat(w)
+    red.remove()
+
+
+def test_sink_views_are_adopted_by_autograd_without_a_copy():
+    """The mechanism vqa_b200.ops relies on: a custom Function whose backward writes into the sink's view and returns it."""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "vqa-project_b200")]
+    from vqa_b200.ddp import GradReducer
+    lin = torch.nn.Linear(4, 5, bias=False)
+    red = GradReducer(lin.parameters())
+
+    class F(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w):
+            ctx.save_for_backward(x, w)
+            return x @ w.t()
+
+        @staticmethod
+        def backward(ctx, g):
+            x, w = ctx.saved_tensors
+            out = red.sink(w)
+            assert out is not None
+            torch.mm(g.t(), x, out=out)
+            return None, out
+
+    x = torch.randn(3, 4)
+    for _ in range(2):
+        red.zero_grad()
+        red.flat.fill_(7.0)                               # stale content must be overwritten, not accumulated
+        F.apply(x, lin.weight).sum().backward()
+        red.finish()
+        assert lin.weight.grad.data_ptr() == red.flat.data_ptr() + lin.weight._vqa_flat_off * 4
+        assert torch.allclose(lin.weight.grad, torch.ones(3, 5).t() @ x)
+    red.remove()

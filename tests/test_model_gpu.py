@@ -185,6 +185,35 @@ def test_fused_dropout_training_step_is_stochastic_but_seeded():
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
 
 
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_gradient_sink_path_equals_plain_autograd(name):
+    """ddp.GradReducer's sink: the operators write parameter gradients straight into the flat buffer and autograd adopts the
+    views.  Same gradients as the plain path, every .grad inside the flat buffer, no accumulation of stale content."""
+    from vqa_b200.ddp import GradReducer
+    g = load_golden(name)
+    _, model = _build(name, g)
+    model.train()
+    q, img, K, qlen, tgt = _inputs(g)
+    crit = torch.nn.MultiLabelSoftMarginLoss()
+    crit(model(q, img, K, qlen)[0], tgt).backward()
+    plain = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+    model.zero_grad(set_to_none=True)
+    red = GradReducer(model.parameters())
+    try:
+        for _ in range(2):
+            red.zero_grad()
+            red.flat.fill_(3.0)                             # stale content: must be overwritten
+            crit(model(q, img, K, qlen)[0], tgt).backward()
+            red.finish()
+            for n, p in model.named_parameters():
+                if n in plain:
+                    assert p.grad is not None, n
+                    assert p.grad.data_ptr() == red.flat.data_ptr() + p._vqa_flat_off * 4, n
+                    assert torch.allclose(p.grad, plain[n], rtol=1e-5, atol=1e-7), (n, rel_err(p.grad, plain[n]))
+    finally:
+        red.remove()
+
+
 def test_shape_errors_raise_before_launch():
     g = load_golden("tiny")
     _, model = _build("tiny", g)

@@ -5,9 +5,13 @@ The reference has no distributed code (single process, ``nn.DataPar
 The model path shards over the batch with no forward exchange (every question/image is independent), so
 the only collective is the gradient all-reduce.
 
-``GradReducer`` owns one flat fp32 gradient buffer; every ``param.grad`` is a view into it.  Parameters are
-assigned to buckets in REVERSE registration order (= the order autograd finishes them: classifier first, GRU
-and embedding last).  A post-accumulate-grad hook counts finished parameters per bucket and launches
+``GradReducer`` owns one flat fp32 gradient buffer; every ``param.grad`` is a view into it.  The buffer is laid out
+in registration order (so the nk per-kernel conv weights stay consecutive and one GEMM can write all their gradients);
+buckets are contiguous ranges taken from its END backwards (= the order autograd finishes them: classifier first,
+GRU and embedding last).  Gradients are WRITTEN, not accumulated: ``zero_grad`` sets every ``.grad`` to None (no memset),
+the operators of ``vqa_b200.ops`` ask ``sink(param)`` for the parameter's view and let their last kernel write straight
+into it, and autograd adopts that view as ``.grad`` without a copy; a gradient that arrives any other way is copied
+into its view by the hook.  A post-accumulate-grad hook counts finished parameters per bucket and launches
 ``all_reduce(bucket, async_op=True)`` the moment a bucket is complete, so the transfer of the 36 MB ``out_2``
 bucket runs under the graph-convolution backward kernels.  ``finish()`` waits and leaves averaged gradients.
 Works with any backend (``gloo`` in the CPU tests, ``nccl`` on the B200s).
@@ -29,39 +33,62 @@ class GradReducer:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         dev, dt = self.params[0].device, self.params[0].dtype
-        # pass 1: offsets.  Reverse order = completion order of backward; 64-element alignment keeps views 256-byte aligned
+        # pass 1: offsets in registration order (64-element alignment keeps views 256-byte aligned)
+        off = 0
+        for p in self.params:
+            off = (off + 63) // 64 * 64
+            p._vqa_flat_off = off
+            off += p.numel()
+        total = off
+        # pass 2: buckets = contiguous ranges from the end backwards (completion order of backward)
         self.bucket_of = [0] * len(self.params)
         self.bucket_slices: List[slice] = []
         self.bucket_size: List[int] = []
-        off = start = nbytes = count = 0
+        end, nbytes, count = total, 0, 0
         for i in reversed(range(len(self.params))):
             p = self.params[i]
-            off = (off + 63) // 64 * 64
-            p._vqa_flat_off = off
             self.bucket_of[i] = len(self.bucket_slices)
-            off += p.numel()
             nbytes += p.numel() * p.element_size()
             count += 1
-            if nbytes >= bucket_bytes:
-                self.bucket_slices.append(slice(start, off))
+            if nbytes >= bucket_bytes or i == 0:
+                self.bucket_slices.append(slice(p._vqa_flat_off, end))
                 self.bucket_size.append(count)
-                start, nbytes, count = off, 0, 0
-        if count:
-            self.bucket_slices.append(slice(start, off))
-            self.bucket_size.append(count)
-        # pass 2: one buffer, every .grad a view into it
-        self.flat = torch.zeros(off, device=dev, dtype=dt)
+                end, nbytes, count = p._vqa_flat_off, 0, 0
+        # pass 3: one buffer, every .grad a view into it
+        self.flat = torch.zeros(total, device=dev, dtype=dt)
+        self._by_ptr = {p.data_ptr(): p for p in self.params}
         for p in self.params:
-            p.grad = self.flat[p._vqa_flat_off:p._vqa_flat_off + p.numel()].view_as(p)
+            p.grad = self._view(p)
         self._ready = [0] * len(self.bucket_size)
         self._handles = []
         self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
         self.launched = 0
+        try:                                              # the fused operators write their parameter gradients through the sink
+            from . import ops
+            ops.set_grad_sink(self.sink)
+        except Exception:                                 # pragma: no cover - CPU-only use of the reducer (tests)
+            pass
+
+    def _view(self, p: torch.nn.Parameter) -> torch.Tensor:
+        """A fresh view of the flat buffer shaped like ``p`` (a new tensor object each call, so autograd can adopt it)."""
+        return self.flat[p._vqa_flat_off:p._vqa_flat_off + p.numel()].view_as(p)
+
+    def sink(self, t: torch.Tensor) -> Optional[torch.Tensor]:
+        """Destination for the gradient of the parameter whose storage ``t`` starts at (None if it is not one of ours)."""
+        p = self._by_ptr.get(t.data_ptr())
+        if p is None or p.shape != t.shape or p.grad is not None:      # accumulating into an existing .grad: autograd's job
+            return None
+        return self._view(p)
 
     def _make_hook(self, i: int):
         b = self.bucket_of[i]
 
         def hook(param):
+            g = param.grad
+            if g is not None and g.data_ptr() != self.flat.data_ptr() + param._vqa_flat_off * self.flat.element_size():
+                v = self._view(param)                     # produced outside the sink: move it into the flat buffer
+                v.copy_(g)
+                param.grad = v
             self._ready[b] += 1
             if self._ready[b] == self.bucket_size[b]:
                 self._launch(b)
@@ -73,12 +100,17 @@ class GradReducer:
             self._handles.append(h)
         self.launched += 1
 
-    def zero_grad(self) -> None:
-        """Zero the flat buffer in one memset and (re)attach the views (``optimizer.zero_grad()`` would detach them)."""
-        self.flat.zero_()
-        for p in self.params:
-            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + p._vqa_flat_off * self.flat.element_size():
-                p.grad = self.flat[p._vqa_flat_off:p._vqa_flat_off + p.numel()].view_as(p)
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        """Start a step.  Default: drop every ``.grad`` (the step WRITES gradients into the flat buffer, nothing to zero).
+        ``set_to_none=False``: zero the flat buffer in one memset and (re)attach the views, for accumulation over micro-batches."""
+        if set_to_none:
+            for p in self.params:
+                p.grad = None
+        else:
+            self.flat.zero_()
+            for p in self.params:
+                if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + p._vqa_flat_off * self.flat.element_size():
+                    p.grad = self._view(p)
         self._ready = [0] * len(self.bucket_size)
 
     def finish(self) -> None:
@@ -97,6 +129,12 @@ class GradReducer:
         for h in self._hooks:
             h.remove()
         self._hooks.clear()
+        try:
+            from . import ops
+            if ops._GRAD_SINK == self.sink:
+                ops.set_grad_sink(None)
+        except Exception:                                 # pragma: no cover
+            pass
 
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:

@@ -217,18 +217,26 @@ def weight_norm_fwd(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     return w
 
 
-def weight_norm_bwd(dw: torch.Tensor, v: torch.Tensor, g: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+def weight_norm_bwd(dw: torch.Tensor, v: torch.Tensor, g: torch.Tensor, out=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``out``: optional (dv, dg) destinations (contiguous, e.g. views of a flat gradient buffer)."""
     dw = _chk(dw, "weight_norm dw").contiguous(); v = v.contiguous(); g = g.contiguous()
-    dv = torch.empty_like(v)
-    dg = torch.empty_like(g)
+    dv, dg = out if out is not None and out[0] is not None and out[1] is not None else (None, None)
+    if dv is None:
+        dv = torch.empty_like(v)
+        dg = torch.empty_like(g)
+    elif dv.shape != v.shape or dg.shape != g.shape or not dv.is_contiguous() or not dg.is_contiguous():
+        raise RuntimeError("weight_norm_bwd: out tensors must be contiguous and shaped like (v, g)")
     _call("vqa_weight_norm_bwd_f32", dw.data_ptr(), v.data_ptr(), g.data_ptr(), dv.data_ptr(), dg.data_ptr(),
           v.shape[0], v.shape[1], _stream())
     return dv, dg
 
 
-def colsum(x: torch.Tensor) -> torch.Tensor:
+def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     x, ldx = _rows_view(_chk(x, "colsum x"), "colsum x")
-    out = torch.empty(x.shape[1], device=x.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(x.shape[1], device=x.device, dtype=torch.float32)
+    elif out.numel() != x.shape[1] or not out.is_contiguous():
+        raise RuntimeError("colsum: out must be a contiguous tensor with one element per column")
     scratch = torch.empty(256 * x.shape[1], device=x.device, dtype=torch.float32)
     _call("vqa_colsum_f32", x.data_ptr(), ldx, out.data_ptr(), scratch.data_ptr(), x.shape[0], x.shape[1], _stream())
     return out

@@ -75,6 +75,29 @@ def _split_for(out_rows: int, out_cols: int, contraction: int) -> int:
     return s
 
 
+_GRAD_SINK = None   # callable(parameter tensor) -> fresh view of a flat gradient buffer, or None (ddp.GradReducer.sink)
+
+
+def set_grad_sink(fn=None) -> None:
+    """Install (or remove) the gradient sink: backward then lets the LAST kernel of every parameter gradient write straight
+    into the view the sink returns and hands that view to autograd, which adopts it as ``.grad`` without an add or a copy
+    (the reference's autograd allocates, zero-fills and accumulates: SURVEY.md 2a k20)."""
+    global _GRAD_SINK
+    _GRAD_SINK = fn
+
+
+def _sink(t):
+    return None if _GRAD_SINK is None or t is None else _GRAD_SINK(t)
+
+
+def _into(sink_view, value):
+    """Tiny gradients assembled elsewhere (Gaussian parameters): copy into the sink view when there is one."""
+    if sink_view is None:
+        return value
+    sink_view.copy_(value.view(sink_view.shape))
+    return sink_view
+
+
 _GRAPH_RNG = None   # (seed, device int64 step counter) while a CUDA-graph-safe RNG is installed (engine.TrainStep)
 _GRAPH_RNG_SITE = 0
 
@@ -117,6 +140,23 @@ def flat_weight(ws: Sequence[torch.Tensor]) -> torch.Tensor:
         except RuntimeError:
             pass
     return torch.cat([w.detach() for w in ws], dim=0)
+
+
+def _conv_sink(ws, zero: bool):
+    """One (nk*D, in) destination covering the gradient views of the nk per-kernel conv weights, when the sink lays them out
+    consecutively (it does: registration order); None otherwise.  ``zero``: the product accumulates split-K partials."""
+    vs = [_sink(w) for w in ws]
+    if any(v is None for v in vs):
+        return None
+    v0 = vs[0]
+    d, fin = v0.shape
+    step = d * fin * v0.element_size()
+    if not all(v.is_contiguous() and v.data_ptr() == v0.data_ptr() + i * step for i, v in enumerate(vs)):
+        return None
+    out = v0.as_strided((len(vs) * d, fin), (fin, 1))
+    if zero:
+        out.zero_()
+    return out
 
 
 class ConditionedGraphFn(torch.autograd.Function):
@@ -208,6 +248,7 @@ class ConditionedGraphFn(torch.autograd.Function):
         logits = _gemm_s(o1s, Wo2s, bias=bo2)
 
         ctx.cfg = dict(B=B, K=K, F=F, H=H, nk=nk, nb=nb, scale=scale, mma1=mma1, mma2=mma2)
+        ctx.prm = (b1, b2, bo1, bo2, (mr1, pr1, mt1, pt1), (mr2, pr2, mt2, pt2), conv_ws)   # identities for the gradient sink
         ctx.ec1 = ec1
         ctx.splits = (Xs, qs, h1s, G1s, hqs, o1s, W1qs, W2s, Wo1s, Wo2s, Wc1s, Wc2s, Y1, Y2)   # Y1/Y2: SplitT on the tensor-core path, fp32 else
         ctx.save_for_backward(image, qenc, v1, g1, v2, g2, vo1, go1, vo2, go2, gs1, gs2, h2, idx, alpha, pooled, argmax)
@@ -227,11 +268,12 @@ class ConditionedGraphFn(torch.autograd.Function):
 
         # classifier
         dls = _split(dlogits)
-        dbo2 = kn.colsum(dlogits)
+        b1_, b2_, bo1_, bo2_, g1p, g2p, conv_ws = ctx.prm
+        dbo2 = kn.colsum(dlogits, out=_sink(bo2_))
         dWo2 = _gemm_s(dls, o1s, a_mn=True, b_mn=True)
         do1s = kn.empty_split(o1s.rows, o1s.cols, dev, with_lo)
         do1 = _gemm_s(dls, Wo2s, b_mn=True, aux=o1s, aux_scale=scale, out_split=do1s)   # ReLU + dropout mask from the stored output
-        dbo1 = kn.colsum(do1)
+        dbo1 = kn.colsum(do1, out=_sink(bo1_))
         dWo1 = _gemm_s(do1s, hqs, a_mn=True, b_mn=True)
         dhq = _gemm_s(do1s, Wo1s, b_mn=True)
         dpooled, dq = kn.gate_bwd(dhq, qenc, pooled)
@@ -243,7 +285,8 @@ class ConditionedGraphFn(torch.autograd.Function):
         else:
             dY2, _, dgs2 = kn.graphconv_bwd(Y2, idx, None, image, gs2, B, K, dpooled=dpooled, argmax=argmax)
         dY2s = _split(dY2)
-        dWc2 = _gemm_s(dY2s, G1s, a_mn=True, b_mn=True, split_k=_split_for(Wc2s.rows, Wc2s.cols, M))
+        sk2 = _split_for(Wc2s.rows, Wc2s.cols, M)
+        dWc2 = _gemm_s(dY2s, G1s, a_mn=True, b_mn=True, split_k=sk2, out=_conv_sink(conv_ws[nk:], sk2 > 1))
         # graph convolution 1
         if c["mma1"]:
             dG1s = _gemm_s(dY2s, Wc2s, b_mn=True, aux=G1s, aux_scale=scale, out_split=kn.empty_split(M, G1s.cols, dev, with_lo), want_f32=False)
@@ -253,17 +296,18 @@ class ConditionedGraphFn(torch.autograd.Function):
             dG1 = _gemm_s(dY2s, Wc2s, b_mn=True, aux=G1s, aux_scale=scale)
             dY1, dalpha, dgs1 = kn.graphconv_bwd(Y1, idx, alpha, image, gs1, B, K, dO=dG1)
             dY1s = _split(dY1)
-        dWc1 = _gemm_s(dY1s, Xs, a_mn=True, b_mn=True, split_k=_split_for(Wc1s.rows, Wc1s.cols, M))
+        sk1 = _split_for(Wc1s.rows, Wc1s.cols, M)
+        dWc1 = _gemm_s(dY1s, Xs, a_mn=True, b_mn=True, split_k=sk1, out=_conv_sink(conv_ws[:nk], sk1 > 1))
 
         # graph learner
         Cdim = h2.shape[1]
         dh2 = kn.adjacency_topk_bwd(h2.view(B, K, Cdim), idx, alpha, dalpha, dadj).view(M, Cdim)
         dh2s = _split(dh2)
-        db2 = kn.colsum(dh2)
+        db2 = kn.colsum(dh2, out=_sink(b2_))
         dW2 = _gemm_s(dh2s, h1s, a_mn=True, b_mn=True, split_k=_split_for(Cdim, Cdim, M))
         dh1s = kn.empty_split(M, Cdim, dev, with_lo)
         dh1 = _gemm_s(dh2s, W2s, b_mn=True, aux=h1s, aux_scale=1.0, out_split=dh1s)
-        db1 = kn.colsum(dh1)
+        db1 = kn.colsum(dh1, out=_sink(b1_))
         s1 = _split_for(Cdim, F, M)
         dW1 = torch.zeros((Cdim, F + H), device=dev, dtype=torch.float32) if s1 > 1 else torch.empty((Cdim, F + H), device=dev, dtype=torch.float32)
         _gemm_s(dh1s, Xs, a_mn=True, b_mn=True, out=dW1[:, :F], split_k=s1)
@@ -273,18 +317,17 @@ class ConditionedGraphFn(torch.autograd.Function):
         dq_gl = _gemm_s(dqts, W1qs, b_mn=True)
         dq = dq + dq_gl
 
-        dv1, dg1 = kn.weight_norm_bwd(dW1, v1, g1)
-        dv2, dg2 = kn.weight_norm_bwd(dW2, v2, g2)
-        dvo1, dgo1 = kn.weight_norm_bwd(dWo1, vo1, go1)
-        dvo2, dgo2 = kn.weight_norm_bwd(dWo2, vo2, go2)
+        dv1, dg1 = kn.weight_norm_bwd(dW1, v1, g1, out=(_sink(v1), _sink(g1)))
+        dv2, dg2 = kn.weight_norm_bwd(dW2, v2, g2, out=(_sink(v2), _sink(g2)))
+        dvo1, dgo1 = kn.weight_norm_bwd(dWo1, vo1, go1, out=(_sink(vo1), _sink(go1)))
+        dvo2, dgo2 = kn.weight_norm_bwd(dWo2, vo2, go2, out=(_sink(vo2), _sink(go2)))
 
         d1 = Wc1s.rows // nk
         d2 = Wc2s.rows // nk
         conv_grads = [dWc1[i * d1:(i + 1) * d1] for i in range(nk)] + [dWc2[i * d2:(i + 1) * d2] for i in range(nk)]
         gsh = (nk, 1)
-        return (None, None, dq, dv1, dg1, db1, dv2, dg2, db2,
-                dgs1[0:nk].view(gsh), dgs1[nk:2 * nk].view(gsh), dgs1[2 * nk:3 * nk].view(gsh), dgs1[3 * nk:].view(gsh),
-                dgs2[0:nk].view(gsh), dgs2[nk:2 * nk].view(gsh), dgs2[2 * nk:3 * nk].view(gsh), dgs2[3 * nk:].view(gsh),
+        gauss_grads = [_into(_sink(prm), dgs[i * nk:(i + 1) * nk].view(gsh)) for dgs, ps in ((dgs1, g1p), (dgs2, g2p)) for i, prm in enumerate(ps)]
+        return (None, None, dq, dv1, dg1, db1, dv2, dg2, db2, *gauss_grads,
                 dvo1, dgo1, dbo1, dvo2, dgo2, dbo2, *conv_grads)
 
 
@@ -316,6 +359,7 @@ class QuestionEncoderFn(torch.autograd.Function):
             kn.gru_cell_fwd(GI[t * B:(t + 1) * B], GH, b_hh, Hall[t] if t > 0 else None, qlen, t, Hall[t + 1],
                             Hs.rows_slice((t + 1) * B, (t + 2) * B), gates[t])
         ctx.T = T
+        ctx.prm = (w_ih, w_hh, b_ih, b_hh)
         ctx.splits = (Es, Wihs, Whhs, Hs)
         ctx.save_for_backward(question, qlen, wemb, Hall, gates)
         return Hall[T]
@@ -342,16 +386,27 @@ class QuestionEncoderFn(torch.autograd.Function):
             if t > 0:   # dL/dh_{t-1} = direct part + dgh . W_hh  (split-K accumulating into the direct part)
                 kn.gemm_s(dGHs.rows_slice(r0, r1), Whhs, b_mn=True, out=dh_part, accumulate=True, split_k=ksplit, tile_n=tile)
             dh = dh_part
-        db_ih = kn.colsum(dGI)
-        db_hh = kn.colsum(dGH)
+        w_ih_, w_hh_, b_ih_, b_hh_ = ctx.prm
+        db_ih = kn.colsum(dGI, out=_sink(b_ih_))
+        db_hh = kn.colsum(dGH, out=_sink(b_hh_))
         TB = T * B
-        s_ih = _split_for(3 * H, Es.cols, TB)
-        dW_ih = kn.gemm_s(dGIs, Es, a_mn=True, b_mn=True, split_k=s_ih)
-        dW_hh = kn.gemm_s(dGHs, Hs.rows_slice(0, TB), a_mn=True, b_mn=True, split_k=_split_for(3 * H, H, TB))
+
+        def wgrad(a, b, prm):
+            sk = _split_for(a.cols, b.cols, TB)
+            out = _sink(prm)
+            if out is not None and sk > 1:
+                out.zero_()
+            return kn.gemm_s(a, b, a_mn=True, b_mn=True, split_k=sk, out=out)
+        dW_ih = wgrad(dGIs, Es, w_ih_)
+        dW_hh = wgrad(dGHs, Hs.rows_slice(0, TB), w_hh_)
         dwemb = None
         if ctx.needs_input_grad[3]:
             dE = kn.gemm_s(dGIs, Wihs, b_mn=True)                             # (T*B, E)
-            dwemb = torch.zeros_like(wemb)
+            dwemb = _sink(wemb)
+            if dwemb is None:
+                dwemb = torch.zeros_like(wemb)
+            else:
+                dwemb.zero_()
             kn.embed_scatter_add(dE, question, qlen, dwemb, T)
         return None, None, None, dwemb, dW_ih, dW_hh, db_ih, db_hh
 
