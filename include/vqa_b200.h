@@ -20,7 +20,7 @@ extern "C" {
 
 typedef struct CUstream_st* vqa_stream_t; /* cudaStream_t */
 
-#define VQA_ABI_VERSION 3
+#define VQA_ABI_VERSION 4
 
 /* GEMM precision modes */
 #define VQA_PREC_TF32X3 0 /* 3-pass split TF32 on tcgen05: fp32-grade results (parity mode)      */
@@ -67,12 +67,16 @@ int vqa_dropout_split_f32(const float* x, long long ldx, void* hi, void* lo, lon
  * tcgen05.mma, fp32 TMEM accumulator).  passes = 3: lo*hi + hi*lo + hi*hi (fp32-grade, ~2^-17 per product);
  * passes = 1: hi planes only (bf16 mode).  Same operand-major convention, epilogue and call sites as vqa_gemm_f32;
  * the mask may also be given as the hi plane of a split tensor (aux_hi), and the result can be written as fp32 (C),
- * as split planes (C_hi, C_lo; C_lo may be NULL), or both. */
+ * as split planes (C_hi, C_lo; C_lo may be NULL), or both.
+ * tile_gate (optional, device, one int per 128-row tile of C): the CTAs of row tile m do nothing when
+ * tile_gate[m] <= gate_t - used by the padded GRU recurrence (tile_gate[m] = longest question in the tile, gate_t = time
+ * step), where those rows are never read (forward) or would only accumulate zeros (backward). */
 int vqa_gemm_bf16s(const void* A_hi, const void* A_lo, long long lda, int a_mn_major, const void* B_hi,
                    const void* B_lo, long long ldb, int b_mn_major, float* C, long long ldc, void* C_hi, void* C_lo,
                    long long ldcs, int M, int N, int Kc, const float* bias, const float* rowbcast, long long ldrb,
                    int group, const float* aux, long long ldaux, const void* aux_hi, long long ldauxh,
-                   float aux_scale, int flags, int passes, int split_k, int tile_n, vqa_stream_t stream);
+                   float aux_scale, int flags, int passes, int split_k, int tile_n, const int* tile_gate, int gate_t,
+                   vqa_stream_t stream);
 
 /* y = x * keep / (1-p), keep ~ Bernoulli(1-p) from Philox4x32-10(seed; counter = (element/4, offset)).
  * step_ptr (optional, device): *step_ptr * 16 is added to offset at run time, so a CUDA-graph replay that bumps the
@@ -163,6 +167,12 @@ int vqa_graphconv_mma_bwd_data(const void* dO_hi, const void* dO_lo, long long l
                                const float* boxes, long long ldbox, const float* gauss, void* dY_hi, void* dY_lo,
                                long long lddy, int B, int K, int nb, int nk, int out_dim, const float* coef,
                                const unsigned* eoff, vqa_stream_t stream);
+
+/* Data path of the backward of the POOLED layer (max over nodes, sparse_graph_model.py:150, then the transposed
+ * aggregate): dY[b, idx[b,a,m], c] = coef[b,a,m,k(c)] * dpooled[b,c] with a = argmax[b,c], zero elsewhere, written as
+ * (hi, lo) planes (lo may be NULL).  coef from vqa_graphconv_edge_coef of that layer (alpha = NULL). */
+int vqa_graphconv_pool_bwd_data(const float* dpooled, const long long* argmax, const int* idx, const float* coef, void* dY_hi,
+                                void* dY_lo, long long lddy, int B, int K, int nb, int nk, int out_dim, vqa_stream_t stream);
 
 /* Edge part of the backward on the tensor cores: P[i,m,k] = <dO[i,chunk k], Y[idx[i,m],chunk k]> per image as
  * dO_k Y_k^T, then dalpha (B,K,nb) (NULL when alpha is NULL) and the per-image partial sums of the Gaussian-parameter

@@ -224,15 +224,20 @@ def test_gemm_split_bf16_accumulate_and_auto_tile(kn):
 
 
 # --------------------------------------------------------------------------------------------- question encoder
-@pytest.mark.parametrize("B,T,H,V,E", [(9, 7, 64, 50, 300), (33, 14, 128, 200, 300), (4, 3, 32, 11, 24)])
-def test_question_encoder_matches_packed_gru(B, T, H, V, E):
+@pytest.mark.parametrize("B,T,H,V,E,sort", [(9, 7, 64, 50, 300, False), (33, 14, 128, 200, 300, False), (4, 3, 32, 11, 24, False),
+                                            (300, 12, 64, 40, 24, True), (260, 9, 32, 40, 24, False)])
+def test_question_encoder_matches_packed_gru(B, T, H, V, E, sort):
     """ops.QuestionEncoderFn (padded, masked recurrence on our kernels) vs nn.Embedding + pack_padded_sequence + nn.GRU
-    in fp64 on the CPU (the reference's construction, sparse_graph_model.py:117-121), forward and every gradient."""
+    in fp64 on the CPU (the reference's construction, sparse_graph_model.py:117-121), forward and every gradient.
+    The B > 128 cases exercise the row-tile gate of the per-step products (sorted as collate_fn does: whole tiles end early;
+    unsorted: tiles stay alive as long as any of their rows is)."""
     from torch.nn.utils.rnn import pack_padded_sequence
     from vqa_b200 import ops
     g = torch.Generator().manual_seed(B * 100 + T)
     lens = torch.randint(1, T + 1, (B,), generator=g)
     lens[0] = T
+    if sort:
+        lens = lens.sort(descending=True).values
     q = torch.zeros(B, T + 5, dtype=torch.int64)
     for b in range(B):
         q[b, :lens[b]] = torch.randint(1, V, (int(lens[b]),), generator=g)
@@ -454,6 +459,46 @@ def test_graphconv_bwd(kn, B, K, nb, nk, out_dim, mode):
         assert rel_err(dalpha.cpu(), grads[5]) < 2e-5
     else:
         assert dalpha is None
+
+
+def test_gemm_row_tile_gate(kn):
+    """vqa_gemm_bf16s tile_gate: row tiles whose gate value is <= t are not computed (left untouched), the others are exact."""
+    M, N, K = 520, 384, 256
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(M, K, generator=g).to(DEV); b = torch.randn(N, K, generator=g).to(DEV)
+    As, Bs = kn.split(a), kn.split(b)
+    full = kn.gemm_s(As, Bs, tile_n=128)
+    gate = torch.tensor([9, 4, 7, 4, 2], dtype=torch.int32, device=DEV)          # 5 row tiles of 128
+    out = torch.full((M, N), -7.0, device=DEV)
+    kn.gemm_s(As, Bs, out=out, tile_n=128, row_gate=(gate, 4))
+    for mt, gv in enumerate(gate.tolist()):
+        rows = slice(mt * 128, min(M, (mt + 1) * 128))
+        if gv <= 4:
+            assert torch.all(out[rows] == -7.0), mt
+        else:
+            assert torch.equal(out[rows], full[rows]), mt
+    acc = full.clone()                                                            # accumulate mode (the GRU backward's use)
+    kn.gemm_s(As, Bs, out=acc, accumulate=True, split_k=2, tile_n=128, row_gate=(gate, 4))
+    assert torch.equal(acc[128:256], full[128:256]) and rel_err(acc[0:128], 2 * full[0:128]) < 1e-6
+
+
+@pytest.mark.parametrize("B,K,nb,nk,out_dim", [(4, 36, 16, 8, 1024), (2, 51, 19, 4, 512), (2, 100, 32, 8, 1024), (3, 12, 5, 2, 264)])
+@pytest.mark.parametrize("with_lo", [True, False])
+def test_graphconv_pool_bwd_data(kn, B, K, nb, nk, out_dim, with_lo):
+    """Backward data path of the pooled layer as a scatter of coef * dpooled vs the fp64 transposed aggregate."""
+    image, Y, idx, alpha, gp = _gc_inputs(B, K, nb, nk, out_dim, seed=K + nb)
+    Yr = Y.clone().requires_grad_(True)
+    out = _gc_reference(Yr, idx, None, image, gp, "gc", nk)
+    g = torch.Generator().manual_seed(2)
+    arg = torch.randint(0, K, (B, out_dim), generator=g)
+    dpooled = torch.randn(B, out_dim, generator=g, dtype=torch.float64)
+    dO = torch.zeros(B, K, out_dim, dtype=torch.float64).scatter_(1, arg.unsqueeze(1), dpooled.unsqueeze(1))
+    ref, = torch.autograd.grad((out * dO).sum(), [Yr])
+    idx_d, img_d = idx.int().to(DEV), image.float().to(DEV)
+    ec = kn.graphconv_edge_coef(idx_d, None, img_d, _pack_gauss(gp, "gc"), B, K)
+    dY = kn.graphconv_pool_bwd_data_s(dpooled.float().to(DEV), arg.to(DEV), idx_d, ec, B, K, out_dim, with_lo=with_lo)
+    assert (dY.lo is None) == (not with_lo)
+    assert rel_err(dY.float().view(B, K, -1).cpu(), ref) < (2e-5 if with_lo else 6e-3)
 
 
 # ---- tensor-core aggregate on split planes (graphconv_mma.cu) -----------------------------------------------------

@@ -35,3 +35,4 @@ timeit("mma bwd edges L1 (P + edge finish)", lambda: kn.graphconv_bwd_edges_s(Y1
 pooled, arg, hq = kn.graphconv_pool_fwd_s(Y2s, idx, img, gauss, q, B, K)
 dp = torch.randn(B, 1024, device=dev)
 timeit("mma bwd edges L2 (pooled upstream)", lambda: kn.graphconv_bwd_edges_s(Y2s, idx, None, img, gauss, B, K, dpooled=dp, argmax=arg), M * 1024 * 4 + M * nb * 4)
+timeit("pool bwd data L2 (scatter coef * dpooled)", lambda: kn.graphconv_pool_bwd_data_s(dp, arg, idx, ec2, B, K, 1024), M * 1024 * 4 + 2 * B * 1024 * 4)

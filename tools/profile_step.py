@@ -40,7 +40,7 @@ for e in prof.events():
         d = kern.setdefault(k, [0.0, 0]); d[0] += e.device_time / 3 if hasattr(e, "device_time") else e.cuda_time / 3; d[1] += 1
 tot = sum(v[0] for v in kern.values())
 print(f"GPU kernel time per step: {tot/1e3:.3f} ms")
-for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])[:32]:
+for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])[:48]:
     print(f"{v[0]:10.1f} us  x{v[1]/3:5.1f}  {k}")
 # H2D bandwidth
 img = hb["image"].pin_memory()

@@ -45,6 +45,7 @@ struct Params {
   const __nv_bfloat16* auxh; long long ldauxh;                  // ... or the hi plane of a split tensor
   float aux_scale;
   int flags, kb_per_split, num_kb;
+  const int* tile_gate; int gate_t;                            // optional: the CTA of row tile m exits when tile_gate[m] <= gate_t
 };
 
 template <int BN, int PASSES>
@@ -216,6 +217,10 @@ gemm_bf16s_kernel(const __grid_constant__ Maps tm, const Params p) {
   uint64_t* acc_full = bars + 2 * S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
 
+  // Row-tile gate (padded recurrences): a 128-row tile whose sequences have all ended contributes nothing - its rows of the
+  // output are never read (forward) or would only receive zeros (backward accumulate) - so the whole CTA leaves before it
+  // touches a barrier.  Uniform per CTA; never combined with CTA pairs (host side).
+  if (CL == 1 && p.tile_gate != nullptr && p.tile_gate[blockIdx.y] <= p.gate_t) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const int kb_begin = blockIdx.z * p.kb_per_split;
@@ -480,7 +485,8 @@ extern "C" int vqa_gemm_bf16s(const void* A_hi, const void* A_lo, long long lda,
                               const void* B_lo, long long ldb, int b_mn_major, float* C, long long ldc, void* C_hi, void* C_lo,
                               long long ldcs, int M, int N, int Kc, const float* bias, const float* rowbcast, long long ldrb,
                               int group, const float* aux, long long ldaux, const void* aux_hi, long long ldauxh,
-                              float aux_scale, int flags, int passes, int split_k, int tile_n, cudaStream_t stream) {
+                              float aux_scale, int flags, int passes, int split_k, int tile_n, const int* tile_gate, int gate_t,
+                              cudaStream_t stream) {
   const char* who = "vqa_gemm_bf16s";
   VQA_CHECK_ARG(A_hi && B_hi && (C || C_hi), "%s: null operand", who);
   VQA_CHECK_ARG(passes == 1 || passes == 3, "%s: passes must be 1 (bf16) or 3 (split-bf16, fp32-grade), got %d", who, passes);
@@ -513,7 +519,7 @@ extern "C" int vqa_gemm_bf16s(const void* A_hi, const void* A_lo, long long lda,
   // CTA pairs (cluster 1x2x1) with the B tile multicast to both: the big projections are L2->SM bandwidth bound (96 KB per
   // k-block and CTA at BN = 256), sharing B cuts that to 64 KB.  Worth it only when there are plenty of tile rows.
   const int mtiles = (M + sb::BM - 1) / sb::BM;
-  int cl = (bn == 256 && mtiles >= 8 && !(flags & VQA_GEMM_NO_CLUSTER)) ? 2 : 1;
+  int cl = (bn == 256 && mtiles >= 8 && !(flags & VQA_GEMM_NO_CLUSTER) && !tile_gate) ? 2 : 1;
   sb::Maps tm;
   memset(&tm, 0, sizeof(tm));
   const int b_box = cl == 2 ? bn / 2 : bn;
@@ -524,7 +530,7 @@ extern "C" int vqa_gemm_bf16s(const void* A_hi, const void* A_lo, long long lda,
   if (rc) return rc;
   sb::Params p{C, ldc, reinterpret_cast<__nv_bfloat16*>(C_hi), reinterpret_cast<__nv_bfloat16*>(C_lo), ldcs, M, N, Kc,
                a_mn_major ? 1 : 0, b_mn_major ? 1 : 0, bias, rowbcast, ldrb, group, aux, ldaux,
-               reinterpret_cast<const __nv_bfloat16*>(aux_hi), ldauxh, aux_scale, flags, per, num_kb};
+               reinterpret_cast<const __nv_bfloat16*>(aux_hi), ldauxh, aux_scale, flags, per, num_kb, tile_gate, gate_t};
 #define VQA_DISPATCH(BN_) (passes == 3 ? sb::launch<BN_, 3, 1>(tm, p, splits, stream) : sb::launch<BN_, 1, 1>(tm, p, splits, stream))
   if (bn == 256 && cl == 2) return passes == 3 ? sb::launch<256, 3, 2>(tm, p, splits, stream) : sb::launch<256, 1, 2>(tm, p, splits, stream);
   if (bn == 256) return VQA_DISPATCH(256);

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqa_sm100.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 PREC_TF32X3 = 0
 PREC_TF32 = 1
 PREC_TF32X3_HP = 2
@@ -32,7 +32,7 @@ SIGNATURES = {
     "vqa_split_bf16_f32": [_p, _ll, _p, _p, _ll, _ll, _i, _p],
     "vqa_dropout_split_f32": [_p, _ll, _p, _p, _ll, _ll, _i, _f, _u64, _u64, _p, _p],
     "vqa_gemm_bf16s": [_p, _p, _ll, _i, _p, _p, _ll, _i, _p, _ll, _p, _p, _ll, _i, _i, _i, _p, _p, _ll, _i, _p, _ll, _p, _ll,
-                       _f, _i, _i, _i, _i, _p],
+                       _f, _i, _i, _i, _i, _p, _i, _p],
     "vqa_dropout_f32": [_p, _p, _ll, _f, _u64, _u64, _p, _p],
     "vqa_weight_norm_fwd_f32": [_p, _p, _p, _i, _i, _p],
     "vqa_weight_norm_bwd_f32": [_p, _p, _p, _p, _p, _i, _i, _p],
@@ -48,6 +48,7 @@ SIGNATURES = {
     "vqa_graphconv_mma_fwd": [_p, _p, _ll, _p, _p, _p, _ll, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _i, _f, _u64, _u64, _p, _p, _p, _p],
     "vqa_graphconv_mma_pool_fwd": [_p, _p, _ll, _p, _p, _ll, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p],
     "vqa_graphconv_mma_bwd_data": [_p, _p, _ll, _p, _p, _p, _ll, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _p, _p, _p],
+    "vqa_graphconv_pool_bwd_data": [_p, _p, _p, _p, _p, _p, _ll, _i, _i, _i, _i, _i, _p],
     "vqa_graphconv_mma_bwd_edges": [_p, _p, _ll, _p, _p, _p, _p, _ll, _p, _p, _p, _ll, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "vqa_graphconv_edge_blocks": [_i, _i, _i],
     "vqa_graphconv_edge_bwd_f32": [_p, _p, _p, _p, _ll, _p, _p, _p, _i, _i, _i, _i, _p],

@@ -156,10 +156,12 @@ def dropout_split(x: torch.Tensor, p: float, seed: int, offset: int, step: Optio
 def gemm_s(a: SplitT, b: SplitT, *, a_mn: bool = False, b_mn: bool = False, out: Optional[torch.Tensor] = None,
            out_split: Optional[SplitT] = None, want_f32: bool = True, bias: Optional[torch.Tensor] = None,
            rowbcast: Optional[torch.Tensor] = None, group: int = 1, aux=None, aux_scale: float = 1.0, relu: bool = False,
-           passes: int = 3, split_k: int = 1, tile_n: int = 0, accumulate: bool = False, cluster: bool = True):
+           passes: int = 3, split_k: int = 1, tile_n: int = 0, accumulate: bool = False, cluster: bool = True,
+           row_gate=None):
     """C[M,N] = epi(A . B^T) on the split-bf16 tcgen05 GEMM (``accumulate``: ``out += A . B^T`` with fp32 atomics).  ``a`` is (M,K) [a_mn=False] or (K,M) [a_mn=True]; same
     for ``b`` with N.  ``aux`` (mask source) may be an fp32 tensor or a SplitT.  Returns ``out`` (fp32) or, when
-    ``want_f32`` is False, ``out_split``."""
+    ``want_f32`` is False, ``out_split``.  ``row_gate`` = (int32 device tensor with one entry per 128-row tile of the output,
+    t): row tiles with entry <= t are skipped entirely (padded recurrences)."""
     M, Ka = (a.cols, a.rows) if a_mn else (a.rows, a.cols)
     N, Kb = (b.cols, b.rows) if b_mn else (b.rows, b.cols)
     if Ka != Kb:
@@ -197,7 +199,7 @@ def gemm_s(a: SplitT, b: SplitT, *, a_mn: bool = False, b_mn: bool = False, out:
           None if out_split is None else out_split.hi.data_ptr(), None if out_split is None else _ptr(out_split.lo),
           0 if out_split is None else out_split.ld, M, N, Ka, _ptr(bias), _ptr(rowbcast), ldrb, group,
           _ptr(aux_f), ldaux, _ptr(aux_h), ldauxh, float(aux_scale), (GEMM_RELU if relu else 0) | (GEMM_ACCUMULATE if accumulate else 0) | (0 if cluster else GEMM_NO_CLUSTER),
-          passes, split_k, tile_n, _stream())
+          passes, split_k, tile_n, None if row_gate is None else row_gate[0].data_ptr(), 0 if row_gate is None else int(row_gate[1]), _stream())
     return out if want_f32 else out_split
 
 
@@ -416,6 +418,16 @@ def graphconv_bwd_data_s(dOs: SplitT, idx, alpha, image, gauss, B, K, ec=None) -
     out = empty_split(B * K, out_dim, dOs.hi.device, dOs.lo is not None)
     _call("vqa_graphconv_mma_bwd_data", dOs.hi.data_ptr(), _ptr(dOs.lo), dOs.ld, idx.data_ptr(), _ptr(alpha), bptr, ldbox, gauss.data_ptr(),
           out.hi.data_ptr(), _ptr(out.lo), out.ld, B, K, nb, nk, out_dim, ec[0].data_ptr(), ec[1].data_ptr(), _stream())
+    return out
+
+
+def graphconv_pool_bwd_data_s(dpooled, argmax, idx, ec, B, K, out_dim, with_lo=True) -> SplitT:
+    """dY of the pooled layer as planes: the nb products coef * dpooled of every column land in the rows of its arg-max node's neighbours."""
+    nb, nk = idx.shape[-1], ec[0].shape[-1]
+    dpooled = _chk(dpooled, "dpooled").contiguous()
+    out = empty_split(B * K, out_dim, dpooled.device, with_lo)
+    _call("vqa_graphconv_pool_bwd_data", dpooled.data_ptr(), argmax.data_ptr(), idx.data_ptr(), ec[0].data_ptr(), out.hi.data_ptr(), _ptr(out.lo),
+          out.ld, B, K, nb, nk, out_dim, _stream())
     return out
 
 

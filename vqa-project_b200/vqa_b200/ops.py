@@ -218,7 +218,7 @@ class ConditionedGraphFn(torch.autograd.Function):
         mma2 = kn.mma_eligible(K, Wc2s.rows, nk)
         with_lo = _PASSES == 3
         gseed, goff, gstep = next_philox(dev) if drop else (0, 0, None)
-        ec1 = None
+        ec1 = ec2 = None
         if mma1:
             Y1 = _gemm_s(Xs, Wc1s, out_split=kn.empty_split(B * K, Wc1s.rows, dev, with_lo), want_f32=False)   # planes only
             ec1 = kn.graphconv_edge_coef(idx, alpha, image, gs1, B, K)      # edge coefficients: once per layer, reused by backward
@@ -233,7 +233,8 @@ class ConditionedGraphFn(torch.autograd.Function):
         # graph convolution 2 with max-pool over nodes + question gate fused (sparse_graph_model.py:146-151)
         if mma2:
             Y2 = _gemm_s(G1s, Wc2s, out_split=kn.empty_split(B * K, Wc2s.rows, dev, with_lo), want_f32=False)
-            pooled, argmax, hq = kn.graphconv_pool_fwd_s(Y2, idx, image, gs2, qenc, B, K, ec=kn.graphconv_edge_coef(idx, None, image, gs2, B, K))
+            ec2 = kn.graphconv_edge_coef(idx, None, image, gs2, B, K)
+            pooled, argmax, hq = kn.graphconv_pool_fwd_s(Y2, idx, image, gs2, qenc, B, K, ec=ec2)
         else:
             Y2 = _gemm_s(G1s, Wc2s)
             pooled, argmax, hq = kn.graphconv_pool_fwd(Y2, idx, image, gs2, qenc, B, K)
@@ -249,7 +250,7 @@ class ConditionedGraphFn(torch.autograd.Function):
 
         ctx.cfg = dict(B=B, K=K, F=F, H=H, nk=nk, nb=nb, scale=scale, mma1=mma1, mma2=mma2)
         ctx.prm = (b1, b2, bo1, bo2, (mr1, pr1, mt1, pt1), (mr2, pr2, mt2, pt2), conv_ws)   # identities for the gradient sink
-        ctx.ec1 = ec1
+        ctx.ec1, ctx.ec2 = ec1, ec2
         ctx.splits = (Xs, qs, h1s, G1s, hqs, o1s, W1qs, W2s, Wo1s, Wo2s, Wc1s, Wc2s, Y1, Y2)   # Y1/Y2: SplitT on the tensor-core path, fp32 else
         ctx.save_for_backward(image, qenc, v1, g1, v2, g2, vo1, go1, vo2, go2, gs1, gs2, h2, idx, alpha, pooled, argmax)
         ctx.mark_non_differentiable(argmax)
@@ -281,10 +282,10 @@ class ConditionedGraphFn(torch.autograd.Function):
         # graph convolution 2: max-pool scatter by argmax is done inside the kernel
         if c["mma2"]:
             _, dgs2 = kn.graphconv_bwd_edges_s(Y2, idx, None, image, gs2, B, K, dpooled=dpooled, argmax=argmax)
-            dY2, _, _ = kn.graphconv_bwd(None, idx, None, image, gs2, B, K, dpooled=dpooled, argmax=argmax, want_edges=False, out_dim=Y2.cols)
+            dY2s = kn.graphconv_pool_bwd_data_s(dpooled, argmax, idx, ctx.ec2, B, K, Y2.cols, with_lo)   # scatter, no contraction
         else:
             dY2, _, dgs2 = kn.graphconv_bwd(Y2, idx, None, image, gs2, B, K, dpooled=dpooled, argmax=argmax)
-        dY2s = _split(dY2)
+            dY2s = _split(dY2)
         sk2 = _split_for(Wc2s.rows, Wc2s.cols, M)
         dWc2 = _gemm_s(dY2s, G1s, a_mn=True, b_mn=True, split_k=sk2, out=_conv_sink(conv_ws[nk:], sk2 > 1))
         # graph convolution 1
@@ -354,12 +355,17 @@ class QuestionEncoderFn(torch.autograd.Function):
         gates = torch.empty((T, B, 4 * H), device=dev, dtype=torch.float32)
         # per-step product h W_hh^T: L2-bandwidth bound at M = B rows (measured sweep, tools/gru_gemm_sweep.py): 128-wide tiles, no split
         tile = 128 if B <= 1024 else 0
+        # longest question per 128-row tile: the per-step products skip row tiles whose sequences have all ended (the reference's
+        # collate_fn sorts a batch by descending length, so the active rows are a shrinking prefix; any order stays correct)
+        pad = (-B) % 128
+        tile_len = torch.nn.functional.pad(qlen.to(torch.int32), (0, pad)).view(-1, 128).amax(dim=1).to(torch.int32).contiguous()
         for t in range(T):
-            GH = kn.gemm_s(Hs.rows_slice(t * B, (t + 1) * B), Whhs, tile_n=tile) if t > 0 else None
+            GH = kn.gemm_s(Hs.rows_slice(t * B, (t + 1) * B), Whhs, tile_n=tile, row_gate=(tile_len, t)) if t > 0 else None
             kn.gru_cell_fwd(GI[t * B:(t + 1) * B], GH, b_hh, Hall[t] if t > 0 else None, qlen, t, Hall[t + 1],
                             Hs.rows_slice((t + 1) * B, (t + 2) * B), gates[t])
         ctx.T = T
         ctx.prm = (w_ih, w_hh, b_ih, b_hh)
+        ctx.tile_len = tile_len
         ctx.splits = (Es, Wihs, Whhs, Hs)
         ctx.save_for_backward(question, qlen, wemb, Hall, gates)
         return Hall[T]
@@ -384,7 +390,8 @@ class QuestionEncoderFn(torch.autograd.Function):
             kn.gru_cell_bwd(dh, gates[t], Hall[t] if t > 0 else None, qlen, t, dGI[r0:r1], dGH[r0:r1],
                             dGIs.rows_slice(r0, r1), dGHs.rows_slice(r0, r1), dh_part)
             if t > 0:   # dL/dh_{t-1} = direct part + dgh . W_hh  (split-K accumulating into the direct part)
-                kn.gemm_s(dGHs.rows_slice(r0, r1), Whhs, b_mn=True, out=dh_part, accumulate=True, split_k=ksplit, tile_n=tile)
+                kn.gemm_s(dGHs.rows_slice(r0, r1), Whhs, b_mn=True, out=dh_part, accumulate=True, split_k=ksplit, tile_n=tile,
+                          row_gate=(ctx.tile_len, t))
             dh = dh_part
         w_ih_, w_hh_, b_ih_, b_hh_ = ctx.prm
         db_ih = kn.colsum(dGI, out=_sink(b_ih_))
