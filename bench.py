@@ -263,6 +263,28 @@ def run_b200(args, workload):
     _dbg(f"e2e loop done: {ms_e2e:.3f} ms/step")
     e2e_value = w.batch * world / (ms_e2e * 1e-3)
 
+    # ---- the same step in bf16 mode (BASELINE config[1] names both precisions): single-pass tensor-core products outside the
+    # graph-learner chain; same model, optimizer and batches, its own captured graph --------------------------------
+    bf16_mode = None
+    if args.precision == "fp32" and not args.no_graph:
+        ops.set_precision("bf16")
+        step16 = TrainStep(model, opt, criterion, reducer=reducer, use_graph=True, seed=4321 + rank)
+        for i in range(max(args.warmup, 3)):
+            step16(*(resident[i % NB][k] for k in keys))
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            l16 = step16(*(resident[i % NB][k] for k in keys))
+        e1.record()
+        barrier()
+        ms16 = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        bf16_mode = {"value": round(w.batch * world / (ms16 * 1e-3), 1), "unit": "questions/s", "ms_per_step": round(ms16, 4),
+                     "final_loss": float(l16.detach()),
+                     "note": "--precision bf16: 1-pass bf16 tcgen05 products (graph-learner chain stays 3-pass), device-resident batches"}
+        ops.set_precision(args.precision)
+        _dbg(f"bf16-mode loop done: {ms16:.3f} ms/step")
+
     # ---- per-kernel CUDA-event times: an eager pass over the same step (individual launches cannot be bracketed inside a
     # graph replay), same inputs, same stream ------------------------------------------------------------------
     GC, ADJ = "vqa_graphconv_fwd_f32", "vqa_adjacency_topk_fwd_f32"
@@ -358,7 +380,7 @@ def run_b200(args, workload):
                 "ms_per_step": round(ms_e2e, 4), "last_loss": last_loss},
         "gpu_launches": int(launches),
         "roofline": roof, "roofline_other_kernels": extra, "roofline_gemm": roof_gemm, "cpu_baseline": cpu,
-        "clocks": sampler.summary(), "final_loss": final_loss,
+        "clocks": sampler.summary(), "final_loss": final_loss, "bf16_mode": bf16_mode,
     }
     print(json.dumps(line), flush=True)
     leave()

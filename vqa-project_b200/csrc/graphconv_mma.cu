@@ -389,49 +389,43 @@ edge_coef_kernel(const int* __restrict__ idx, const float* __restrict__ alpha, c
 // ------------------------------------------------------------------------------------------ backward of the pooled layer, data path
 // Layer 2 ends in a max over the nodes (sparse_graph_model.py:150): its upstream gradient is one value per (image, column)
 // at node a = argmax[b,c], so the transposed aggregate  dY[b,j,c] = sum_i M_k[i,j] dO[b,i,c]  collapses to
-//   dY[b, idx[b,a,m], c] = coef[b,a,m,k(c)] * dpooled[b,c],   m < nb,   everything else zero
-// - no contraction at all.  One CTA per (image, 256 columns): thread c scatters its nb products (ids and coefficients of
-// node a come from L1/L2: 20 KB per image shared by all its CTAs) into a K x 256 fp32 shared-memory tile, the tile leaves
-// as hi/lo bf16 planes with 16-byte stores.
-constexpr int PB_COLS = 256;
-template <bool STAGE>      // STAGE: the image's ids and coefficients are copied to shared memory first (when they fit)
-__global__ void __launch_bounds__(PB_COLS)
+//   dY[b,j,c] = coef[b,a,m,k(c)] * dpooled[b,c]  if j = idx[b,a,m] for some m,   else 0
+// - no contraction at all.  One CTA per image: ids -> inverse table pos[a][j] = m, coefficients, arg-max nodes and upstream
+// values staged in shared memory; every thread then produces 8 consecutive columns of one output row per iteration and
+// writes them as hi / lo bf16 with 16-byte stores (pure streaming write of the planes, nothing is zero-filled or scattered).
+constexpr int PB_THREADS = 256;
+__global__ void __launch_bounds__(PB_THREADS)
 pool_bwd_data_kernel(const float* __restrict__ dpooled, const long long* __restrict__ argmax, const int* __restrict__ idx,
                      const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy_hi, __nv_bfloat16* __restrict__ dy_lo, long long ldy,
-                     int K, int nb, int nk, int out_dim, int D) {
+                     int K, int nb, int nk, int out_dim, int D, int stage_coef) {
   extern __shared__ __align__(16) uint8_t pb_sm[];
-  float* tile = reinterpret_cast<float*>(pb_sm);                          // [K][PB_COLS]
-  const int b = blockIdx.y, c0 = blockIdx.x * PB_COLS, tid = threadIdx.x;
-  const int c = c0 + tid;
-  int a = 0, k = 0; float dp = 0.f;
-  if (c < out_dim) {
-    const long long o = (long long)b * out_dim + c;
-    a = (int)argmax[o]; k = c / D; dp = dpooled[o];
+  float* dp_s = reinterpret_cast<float*>(pb_sm);                          // [out_dim]
+  uint8_t* a_s = reinterpret_cast<uint8_t*>(dp_s + out_dim);              // [out_dim]
+  int8_t* pos = reinterpret_cast<int8_t*>(a_s + ((out_dim + 15) & ~15));  // [K][K]: slot of j in node a's neighbour list, -1 if absent
+  float* cf = reinterpret_cast<float*>(pos + ((K * K + 15) & ~15));       // [K*nb][nk] (only if stage_coef)
+  const int b = blockIdx.x, tid = threadIdx.x, E = K * nb;
+  const float* cg = coef + (long long)b * E * nk;
+  for (int v = tid; v < out_dim; v += PB_THREADS) {
+    dp_s[v] = dpooled[(long long)b * out_dim + v];
+    a_s[v] = (uint8_t)argmax[(long long)b * out_dim + v];
   }
-  for (int v = tid; v < K * PB_COLS / 4; v += PB_COLS) reinterpret_cast<float4*>(tile)[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (STAGE) {
-    float* cf = tile + K * PB_COLS;                                       // [K*nb][nk]
-    uint8_t* id8 = reinterpret_cast<uint8_t*>(cf + K * nb * nk);          // [K*nb]
-    const int E = K * nb;
-    for (int v = tid; v < E * nk; v += PB_COLS) cf[v] = coef[(long long)b * E * nk + v];
-    for (int v = tid; v < E; v += PB_COLS) id8[v] = (uint8_t)idx[(long long)b * E + v];
-    __syncthreads();
-    if (c < out_dim)
-      for (int m = 0; m < nb; ++m) tile[id8[a * nb + m] * PB_COLS + tid] = cf[(a * nb + m) * nk + k] * dp;   // distinct ids: no collision
-  } else {
-    __syncthreads();
-    if (c < out_dim) {
-      const long long e0 = ((long long)b * K + a) * nb;
-      for (int m = 0; m < nb; ++m) tile[__ldg(idx + e0 + m) * PB_COLS + tid] = __ldg(coef + (e0 + m) * nk + k) * dp;
-    }
-  }
+  for (int v = tid; v < K * K; v += PB_THREADS) pos[v] = -1;
+  if (stage_coef)
+    for (int v = tid; v < E * nk / 4; v += PB_THREADS) reinterpret_cast<float4*>(cf)[v] = reinterpret_cast<const float4*>(cg)[v];
   __syncthreads();
-  const int ncol = min(PB_COLS, out_dim - c0);                            // multiple of 8 (checked on the host)
-  const int cpr = ncol >> 3;                                              // 16-byte chunks per row
-  for (int v = tid; v < K * cpr; v += PB_COLS) {
-    const int j = v / cpr, ch = v - j * cpr;
-    const float4 x0 = *reinterpret_cast<const float4*>(tile + j * PB_COLS + ch * 8), x1 = *reinterpret_cast<const float4*>(tile + j * PB_COLS + ch * 8 + 4);
-    const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+  for (int e = tid; e < E; e += PB_THREADS) pos[(e / nb) * K + idx[(long long)b * E + e]] = (int8_t)(e % nb);   // distinct ids per node
+  __syncthreads();
+  const float* cfp = stage_coef ? cf : cg;
+  const int cpr = out_dim >> 3;                                           // 16-byte chunks per row
+  for (int v = tid; v < K * cpr; v += PB_THREADS) {
+    const int j = v / cpr, c0 = (v - j * cpr) * 8;
+    const int k = c0 / D;                                                 // D % 8 == 0: the 8 columns share their kernel
+    float x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int a = a_s[c0 + u], m = pos[a * K + j];
+      x[u] = m >= 0 ? cfp[(a * nb + m) * nk + k] * dp_s[c0 + u] : 0.f;
+    }
     uint32_t h[4], l[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -440,7 +434,7 @@ pool_bwd_data_kernel(const float* __restrict__ dpooled, const long long* __restr
       const __nv_bfloat162 ll = __floats2bfloat162_rn(x[2 * e] - __uint_as_float(h[e] << 16), x[2 * e + 1] - __uint_as_float(h[e] & 0xFFFF0000u));
       l[e] = *reinterpret_cast<const uint32_t*>(&ll);
     }
-    const long long go = ((long long)b * K + j) * ldy + c0 + ch * 8;
+    const long long go = ((long long)b * K + j) * ldy + c0;
     *reinterpret_cast<uint4*>(dy_hi + go) = make_uint4(h[0], h[1], h[2], h[3]);
     if (dy_lo) *reinterpret_cast<uint4*>(dy_lo + go) = make_uint4(l[0], l[1], l[2], l[3]);
   }
@@ -1331,15 +1325,15 @@ extern "C" int vqa_graphconv_pool_bwd_data(const float* dpooled, const long long
                                            void* dY_lo, long long lddy, int B, int K, int nb, int nk, int out_dim, cudaStream_t stream) {
   VQA_CHECK_ARG(dpooled && argmax && idx && coef && dY_hi, "vqa_graphconv_pool_bwd_data: null pointer");
   VQA_CHECK_ARG(B > 0 && K > 0 && K <= 128 && nb > 0 && nb <= K && nk > 0 && out_dim > 0 && out_dim % nk == 0, "vqa_graphconv_pool_bwd_data: bad sizes (B=%d K=%d nb=%d nk=%d out=%d)", B, K, nb, nk, out_dim);
-  VQA_CHECK_ARG((out_dim & 7) == 0 && (lddy & 7) == 0 && lddy >= out_dim && aligned16(dY_hi) && (!dY_lo || aligned16(dY_lo)), "vqa_graphconv_pool_bwd_data: planes need 16-byte aligned rows, out_dim %% 8 == 0");
-  const size_t tile = (size_t)K * gm::PB_COLS * 4, staged = tile + (size_t)K * nb * nk * 4 + (((size_t)K * nb + 15) & ~(size_t)15);
-  const bool stage = staged <= 72 * 1024;                   // keep 3 CTAs per SM
-  const size_t smem = stage ? staged : tile;
-  auto kern = stage ? gm::pool_bwd_data_kernel<true> : gm::pool_bwd_data_kernel<false>;
-  VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((out_dim + gm::PB_COLS - 1) / gm::PB_COLS, B);
-  kern<<<grid, gm::PB_COLS, smem, stream>>>(dpooled, argmax, idx, coef, reinterpret_cast<__nv_bfloat16*>(dY_hi),
-                                            reinterpret_cast<__nv_bfloat16*>(dY_lo), lddy, K, nb, nk, out_dim, out_dim / nk);
+  VQA_CHECK_ARG(((out_dim / nk) & 7) == 0 && (lddy & 7) == 0 && lddy >= out_dim && aligned16(dY_hi) && (!dY_lo || aligned16(dY_lo)), "vqa_graphconv_pool_bwd_data: planes need 16-byte aligned rows, (out_dim / nk) %% 8 == 0");
+  const size_t base = (size_t)out_dim * 4 + (((size_t)out_dim + 15) & ~(size_t)15) + (((size_t)K * K + 15) & ~(size_t)15);
+  const size_t cbytes = (size_t)K * nb * nk * 4;
+  const int stage = ((K * nb * nk) % 4 == 0 && aligned16(coef) && base + cbytes <= 56 * 1024) ? 1 : 0;   // 4 CTAs per SM
+  const size_t smem = base + (stage ? cbytes : 0);
+  if (smem > 200 * 1024) return vqa_fail(VQA_ERR_UNSUPPORTED, "vqa_graphconv_pool_bwd_data: out_dim too large for shared memory (%zu B)", smem);
+  VQA_CUDA(cudaFuncSetAttribute(gm::pool_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gm::pool_bwd_data_kernel<<<B, gm::PB_THREADS, smem, stream>>>(dpooled, argmax, idx, coef, reinterpret_cast<__nv_bfloat16*>(dY_hi),
+                                                                reinterpret_cast<__nv_bfloat16*>(dY_lo), lddy, K, nb, nk, out_dim, out_dim / nk, stage);
   VQA_LAUNCH_CHECK("graphconv pool_bwd_data_kernel");
   return VQA_OK;
 }
