@@ -88,6 +88,10 @@ int vqa_dropout_f32(const float* x, float* y, long long n, float p, unsigned lon
 /* Old-style weight norm (dim=0): w[r,:] = v[r,:] * (g[r] / ||v[r,:]||).  torch._weight_norm at layers.py:171-172,
  * sparse_graph_model.py:88-89.  bwd: given dw returns dv, dg. */
 int vqa_weight_norm_fwd_f32(const float* v, const float* g, float* w, int rows, int cols, vqa_stream_t stream);
+/* The same, fused with the operand split: columns [c0, c1) of the effective weight written as (hi, lo) bf16 planes
+ * (lo may be NULL), no fp32 intermediate.  cols % 4 == 0, c0 % 4 == 0, ldp % 8 == 0. */
+int vqa_weight_norm_split_f32(const float* v, const float* g, int rows, int cols, int c0, int c1, void* hi, void* lo,
+                              long long ldp, vqa_stream_t stream);
 int vqa_weight_norm_bwd_f32(const float* dw, const float* v, const float* g, float* dv, float* dg, int rows,
                             int cols, vqa_stream_t stream);
 

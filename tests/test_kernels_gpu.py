@@ -270,9 +270,10 @@ def test_dropout_statistics_and_determinism(kn):
     assert y.shape == (1003,)
 
 
-def test_weight_norm_fwd_bwd(kn):
+@pytest.mark.parametrize("cols", [133, 3000, 512])          # scalar path and the float4 path
+def test_weight_norm_fwd_bwd(kn, cols):
     torch.manual_seed(3)
-    v = torch.randn(70, 133, device=DEV, requires_grad=True)
+    v = torch.randn(70, cols, device=DEV, requires_grad=True)
     g = torch.rand(70, 1, device=DEV, requires_grad=True) + 0.5
     g = g.detach().requires_grad_(True)
     w_ref = torch._weight_norm(v, g, 0)
@@ -285,8 +286,25 @@ def test_weight_norm_fwd_bwd(kn):
     assert rel_err(dg.cpu(), g.grad.cpu()) < 1e-5
 
 
+def test_weight_norm_split_matches_weight_norm_then_split(kn):
+    g_ = torch.Generator().manual_seed(8)
+    for rows, cols, c0, c1 in [(70, 3076, 0, 2052), (70, 3076, 2052, 3076), (33, 512, 0, 512), (9, 24, 4, 17)]:
+        v = torch.randn(rows, cols, generator=g_).to(DEV); g = (torch.rand(rows, 1, generator=g_) + 0.5).to(DEV)
+        ref = kn.split(kn.weight_norm_fwd(v, g)[:, c0:c1].contiguous())
+        got = kn.weight_norm_split(v, g, c0, c1)
+        assert got.shape == ref.shape
+        n = c1 - c0
+        w64 = v.double() * (g.double() / v.double().norm(dim=1, keepdim=True))
+        assert rel_err(got.float()[:, :n].cpu(), w64[:, c0:c1].cpu()) < 1e-5 and rel_err(got.float()[:, :n], ref.float()[:, :n]) < 1e-5   # two bf16 planes carry ~17 mantissa bits
+        assert torch.all(got.hi[:, n:] == 0) and torch.all(got.lo[:, n:] == 0)      # plane padding stays zero (TMA reads it)
+        assert kn.weight_norm_split(v, g, c0, c1, with_lo=False).lo is None
+
+
 def test_reductions_and_gate(kn):
     torch.manual_seed(4)
+    for shape in [(7168, 3072), (1001, 512), (64, 8), (5, 12)]:                    # vector path incl. ragged row counts
+        xb = torch.randn(*shape, device=DEV)
+        assert rel_err(kn.colsum(xb).cpu(), xb.double().sum(0).cpu()) < 2e-6, shape
     x = torch.randn(36 * 17, 200, device=DEV)
     assert rel_err(kn.colsum(x).cpu(), x.double().sum(0).cpu()) < 1e-6
     assert rel_err(kn.colsum(x[:, 8:72]).cpu(), x[:, 8:72].double().sum(0).cpu()) < 1e-6

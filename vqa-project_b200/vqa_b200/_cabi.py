@@ -35,6 +35,7 @@ SIGNATURES = {
                        _f, _i, _i, _i, _i, _p, _i, _p],
     "vqa_dropout_f32": [_p, _p, _ll, _f, _u64, _u64, _p, _p],
     "vqa_weight_norm_fwd_f32": [_p, _p, _p, _i, _i, _p],
+    "vqa_weight_norm_split_f32": [_p, _p, _i, _i, _i, _i, _p, _p, _ll, _p],
     "vqa_weight_norm_bwd_f32": [_p, _p, _p, _p, _p, _i, _i, _p],
     "vqa_colsum_f32": [_p, _ll, _p, _p, _ll, _i, _p],
     "vqa_segment_sum_f32": [_p, _p, _i, _i, _i, _p],

@@ -219,6 +219,19 @@ def weight_norm_fwd(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
     return w
 
 
+def weight_norm_split(v: torch.Tensor, g: torch.Tensor, c0: int = 0, c1: Optional[int] = None, with_lo: bool = True) -> "SplitT":
+    """Planes of columns [c0, c1) of the weight-normed matrix v * g / ||v|| (no fp32 intermediate)."""
+    v = _chk(v, "weight_norm v").contiguous(); g = _chk(g, "weight_norm g").contiguous()
+    rows, cols = v.shape
+    c1 = cols if c1 is None else c1
+    if cols % 4 or c0 % 4 or v.data_ptr() % 16:            # rows not 16-byte aligned: two kernels instead of one
+        w = weight_norm_fwd(v, g)
+        return split(w[:, c0:c1] if (c0, c1) == (0, cols) else w[:, c0:c1].contiguous(), with_lo)
+    out = empty_split(rows, c1 - c0, v.device, with_lo)
+    _call("vqa_weight_norm_split_f32", v.data_ptr(), g.data_ptr(), rows, cols, c0, c1, out.hi.data_ptr(), _ptr(out.lo), out.ld, _stream())
+    return out
+
+
 def weight_norm_bwd(dw: torch.Tensor, v: torch.Tensor, g: torch.Tensor, out=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """``out``: optional (dv, dg) destinations (contiguous, e.g. views of a flat gradient buffer)."""
     dw = _chk(dw, "weight_norm dw").contiguous(); v = v.contiguous(); g = g.contiguous()

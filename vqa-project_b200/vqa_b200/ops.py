@@ -183,20 +183,23 @@ class ConditionedGraphFn(torch.autograd.Function):
         else:
             Xs = kn.split(img2)
 
-        # weight-norm effective weights (layers.py:171-172, sparse_graph_model.py:88-89)
-        W1 = kn.weight_norm_fwd(v1, g1)
-        W2 = kn.weight_norm_fwd(v2, g2)
-        Wo1 = kn.weight_norm_fwd(vo1, go1)
-        Wo2 = kn.weight_norm_fwd(vo2, go2)
+        # weight-norm effective weights (layers.py:171-172, sparse_graph_model.py:88-89), written directly as operand planes
         Wc1 = flat_weight(conv_ws[:nk])
         Wc2 = flat_weight(conv_ws[nk:])
-        W1q = W1[:, F:].contiguous()
-        W1xs, W1qs, W2s = kn.split(W1[:, :F]), kn.split(W1q), kn.split(W2)
-        Wo1s, Wo2s, Wc1s, Wc2s = (_split(w) for w in (Wo1, Wo2, Wc1, Wc2))
+        lo3 = _PASSES == 3
+        if _GL_STRICT:
+            W1 = kn.weight_norm_fwd(v1, g1)
+            W2 = kn.weight_norm_fwd(v2, g2)
+            W1xs, W1qs, W2s = kn.split(W1[:, :F]), kn.split(W1[:, F:].contiguous()), kn.split(W2)
+        else:
+            W1xs, W1qs = kn.weight_norm_split(v1, g1, 0, F), kn.weight_norm_split(v1, g1, F, F + H)
+            W2s = kn.weight_norm_split(v2, g2)
+        Wo1s, Wo2s = kn.weight_norm_split(vo1, go1, with_lo=lo3), kn.weight_norm_split(vo2, go2, with_lo=lo3)
+        Wc1s, Wc2s = _split(Wc1), _split(Wc2)
         qs = kn.split(qenc)
 
         # graph learner: [X || q] W1^T = X W1[:, :F]^T + (q W1[:, F:]^T) broadcast over the K nodes  (no concat/repeat)
-        h1s = kn.empty_split(B * K, W1.shape[0], dev, True)
+        h1s = kn.empty_split(B * K, v1.shape[0], dev, True)
         if _GL_STRICT:
             X2 = Xs.float()
             qt = _gemm_gl(qenc, W1[:, F:])
