@@ -20,7 +20,7 @@ extern "C" {
 
 typedef struct CUstream_st* vqa_stream_t; /* cudaStream_t */
 
-#define VQA_ABI_VERSION 4
+#define VQA_ABI_VERSION 5
 
 /* GEMM precision modes */
 #define VQA_PREC_TF32X3 0 /* 3-pass split TF32 on tcgen05: fp32-grade results (parity mode)      */
@@ -95,8 +95,10 @@ int vqa_weight_norm_split_f32(const float* v, const float* g, int rows, int cols
 int vqa_weight_norm_bwd_f32(const float* dw, const float* v, const float* g, float* dv, float* dg, int rows,
                             int cols, vqa_stream_t stream);
 
-/* out[c] = sum_r x[r,c]  (bias gradients; deterministic two-stage reduction, `scratch` >= 256*cols floats) */
-int vqa_colsum_f32(const float* x, long long ldx, float* out, float* scratch, long long rows, int cols,
+/* out[c] = sum_r x[r,c]  (bias gradients; deterministic two-stage reduction, `scratch` >= 256*cols floats).
+ * counters (optional): >= ceil(cols/256) ints that are ZERO on entry and are left zero - the last row block of every column
+ * block then adds the partial sums itself (one launch instead of two, same summation order). */
+int vqa_colsum_f32(const float* x, long long ldx, float* out, float* scratch, long long rows, int cols, int* counters,
                    vqa_stream_t stream);
 /* out[s,c] = sum_{i<seg_len} x[s*seg_len+i, c]  (gradient of the per-image broadcast question term) */
 int vqa_segment_sum_f32(const float* x, float* out, int segments, int seg_len, int cols, vqa_stream_t stream);

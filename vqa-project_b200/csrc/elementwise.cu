@@ -93,6 +93,82 @@ __global__ void __launch_bounds__(256) weight_norm_split_kernel(const float* __r
   }
 }
 
+// One CTA per row, the row (and dw) held in registers: v and dw are read ONCE.  NV float4 per thread: cols <= 1024 * NV.
+__device__ __forceinline__ float block_sum_256(float x, float* sh) {
+  x = warp_sum(x);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += sh[w];                  // fixed order: deterministic
+  __syncthreads();
+  return t;
+}
+template <int NV>
+__global__ void __launch_bounds__(256) weight_norm_bwd_row_kernel(const float* __restrict__ dw, const float* __restrict__ v,
+                                                                 const float* __restrict__ g, float* __restrict__ dv,
+                                                                 float* __restrict__ dg, int cols) {
+  __shared__ float sh[8];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const float* vr = v + (long long)row * cols;
+  const float* dr = dw + (long long)row * cols;
+  float4 a[NV], d[NV];
+  float ss = 0.f, dot = 0.f;
+#pragma unroll
+  for (int u = 0; u < NV; ++u) {
+    const int c = (u * 256 + tid) * 4;
+    if (c < cols) { a[u] = *reinterpret_cast<const float4*>(vr + c); d[u] = *reinterpret_cast<const float4*>(dr + c); }
+    else { a[u] = make_float4(0.f, 0.f, 0.f, 0.f); d[u] = a[u]; }
+    ss += (a[u].x * a[u].x + a[u].y * a[u].y) + (a[u].z * a[u].z + a[u].w * a[u].w);
+    dot += (d[u].x * a[u].x + d[u].y * a[u].y) + (d[u].z * a[u].z + d[u].w * a[u].w);
+  }
+  ss = block_sum_256(ss, sh);
+  dot = block_sum_256(dot, sh);
+  const float norm = sqrtf(ss), gr = g[row];
+  if (tid == 0) dg[row] = dot / norm;
+  const float ca = gr / norm, cb = gr * dot / (norm * ss);   // dv = g/||v|| * dw - g*dot/||v||^3 * v
+  float* o = dv + (long long)row * cols;
+#pragma unroll
+  for (int u = 0; u < NV; ++u) {
+    const int c = (u * 256 + tid) * 4;
+    if (c < cols) *reinterpret_cast<float4*>(o + c) = make_float4(ca * d[u].x - cb * a[u].x, ca * d[u].y - cb * a[u].y, ca * d[u].z - cb * a[u].z, ca * d[u].w - cb * a[u].w);
+  }
+}
+template <int NV>
+__global__ void __launch_bounds__(256) weight_norm_split_row_kernel(const float* __restrict__ v, const float* __restrict__ g, int cols, int c0,
+                                                                   int c1, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                                   long long ldp) {
+  __shared__ float sh[8];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const float* vr = v + (long long)row * cols;
+  float4 a[NV];
+  float ss = 0.f;
+#pragma unroll
+  for (int u = 0; u < NV; ++u) {
+    const int c = (u * 256 + tid) * 4;
+    a[u] = c < cols ? *reinterpret_cast<const float4*>(vr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ss += (a[u].x * a[u].x + a[u].y * a[u].y) + (a[u].z * a[u].z + a[u].w * a[u].w);
+  }
+  ss = block_sum_256(ss, sh);
+  const float s = g[row] / sqrtf(ss);
+  __nv_bfloat16* hr = hi + (long long)row * ldp;
+  __nv_bfloat16* lr = lo ? lo + (long long)row * ldp : nullptr;
+  const int n8 = (c1 - c0 + 7) & ~7;                        // plane columns incl. zero padding; (c1 - c0) % 4 == 0 and c0 % 4 == 0
+#pragma unroll
+  for (int u = 0; u < NV; ++u) {
+    const int c = (u * 256 + tid) * 4;                       // column of v; plane column c - c0
+    if (c >= c0 && c < c1) {
+      const uint32_t h0 = pack2_bf16(a[u].x * s, a[u].y * s), h1 = pack2_bf16(a[u].z * s, a[u].w * s);
+      *reinterpret_cast<uint2*>(hr + (c - c0)) = make_uint2(h0, h1);
+      if (lr) *reinterpret_cast<uint2*>(lr + (c - c0)) = make_uint2(pack2_bf16(a[u].x * s - __uint_as_float(h0 << 16), a[u].y * s - __uint_as_float(h0 & 0xFFFF0000u)),
+                                                                    pack2_bf16(a[u].z * s - __uint_as_float(h1 << 16), a[u].w * s - __uint_as_float(h1 & 0xFFFF0000u)));
+    } else if (c >= c1 && c - c0 < n8) {                   // the padding quad of the last 8-column group stays zero (TMA reads it)
+      *reinterpret_cast<uint2*>(hr + (c - c0)) = make_uint2(0u, 0u);
+      if (lr) *reinterpret_cast<uint2*>(lr + (c - c0)) = make_uint2(0u, 0u);
+    }
+  }
+}
+
 template <bool VEC>   // VEC: rows are 16-byte aligned (cols % 4 == 0) -> float4 accesses
 __global__ void __launch_bounds__(256) weight_norm_bwd_kernel(const float* __restrict__ dw, const float* __restrict__ v,
                                                              const float* __restrict__ g, float* __restrict__ dv,
@@ -144,7 +220,8 @@ __global__ void __launch_bounds__(256) colsum_stage1(const float* __restrict__ x
 // vector variant: 64 column quads x 4 row lanes per block, float4 loads, 4 independent accumulators per thread; the four row
 // lanes are combined in a fixed order through shared memory (deterministic, like stage 2)
 __global__ void __launch_bounds__(256) colsum_stage1_v4(const float* __restrict__ x, long long ldx, float* __restrict__ scratch,
-                                                       long long rows, int cols, long long rpb) {
+                                                       long long rows, int cols, long long rpb, float* __restrict__ out,
+                                                       int* __restrict__ counters) {
   __shared__ float4 part[4][64];
   const int cq = blockIdx.x * 64 + threadIdx.x, ry = threadIdx.y;
   const long long r0 = blockIdx.y * rpb, r1 = min(rows, r0 + rpb);
@@ -171,6 +248,27 @@ __global__ void __launch_bounds__(256) colsum_stage1_v4(const float* __restrict_
     const float4 p0 = part[0][threadIdx.x], p1 = part[1][threadIdx.x], p2 = part[2][threadIdx.x], p3 = part[3][threadIdx.x];
     *reinterpret_cast<float4*>(scratch + (long long)blockIdx.y * cols + cq * 4) =
         make_float4((p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y), (p0.z + p1.z) + (p2.z + p3.z), (p0.w + p1.w) + (p2.w + p3.w));
+  }
+  if (counters == nullptr) return;                          // two-kernel mode: colsum_stage2 follows
+  // single-kernel mode: the LAST row block of this column block to finish adds the partials, in block order (deterministic)
+  __shared__ int last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0 && ry == 0) {
+    const int ticket = atomicAdd(&counters[blockIdx.x], 1);
+    last = ticket == (int)gridDim.y - 1;
+    if (last) counters[blockIdx.x] = 0;                     // self-resetting: the buffer stays zero between launches
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (ry == 0 && cq * 4 < cols) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < (int)gridDim.y; ++b) {
+      const float4 t = __ldcg(reinterpret_cast<const float4*>(scratch + (long long)b * cols + cq * 4));
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    *reinterpret_cast<float4*>(out + cq * 4) = acc;
   }
 }
 __global__ void __launch_bounds__(256) colsum_stage2(const float* __restrict__ scratch, float* __restrict__ out, int nblk, int cols) {
@@ -227,8 +325,13 @@ extern "C" int vqa_weight_norm_split_f32(const float* v, const float* g, int row
   VQA_CHECK_ARG(v && g && hi && rows > 0 && cols > 0 && 0 <= c0 && c0 < c1 && c1 <= cols, "vqa_weight_norm_split_f32: bad arguments");
   VQA_CHECK_ARG((cols & 3) == 0 && (c0 & 3) == 0 && aligned16(v), "vqa_weight_norm_split_f32: v needs 16-byte aligned rows (cols %% 4 == 0) and c0 %% 4 == 0");
   VQA_CHECK_ARG((ldp & 7) == 0 && ldp >= ((c1 - c0 + 7) & ~7) && aligned16(hi) && (!lo || aligned16(lo)), "vqa_weight_norm_split_f32: planes need ld %% 8 == 0 and ld >= round8(c1 - c0)");
-  weight_norm_split_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(v, g, rows, cols, c0, c1, reinterpret_cast<__nv_bfloat16*>(hi),
-                                                              reinterpret_cast<__nv_bfloat16*>(lo), ldp);
+  __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(hi);
+  __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(lo);
+  const bool rowk = ((c1 - c0) & 3) == 0 || c1 == cols;     // quads never straddle c1
+  if (rowk && cols > 256 && cols <= 1024) weight_norm_split_row_kernel<1><<<rows, 256, 0, stream>>>(v, g, cols, c0, c1, ph, pl, ldp);
+  else if (rowk && cols > 1024 && cols <= 2048) weight_norm_split_row_kernel<2><<<rows, 256, 0, stream>>>(v, g, cols, c0, c1, ph, pl, ldp);
+  else if (rowk && cols > 2048 && cols <= 4096) weight_norm_split_row_kernel<4><<<rows, 256, 0, stream>>>(v, g, cols, c0, c1, ph, pl, ldp);
+  else weight_norm_split_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(v, g, rows, cols, c0, c1, ph, pl, ldp);
   VQA_LAUNCH_CHECK("weight_norm_split_kernel");
   return VQA_OK;
 }
@@ -236,7 +339,14 @@ extern "C" int vqa_weight_norm_split_f32(const float* v, const float* g, int row
 extern "C" int vqa_weight_norm_bwd_f32(const float* dw, const float* v, const float* g, float* dv, float* dg, int rows,
                                        int cols, cudaStream_t stream) {
   VQA_CHECK_ARG(dw && v && g && dv && dg && rows > 0 && cols > 0, "vqa_weight_norm_bwd_f32: bad arguments");
-  if ((cols & 3) == 0 && aligned16(dw) && aligned16(v) && aligned16(dv))
+  const bool vec = (cols & 3) == 0 && aligned16(dw) && aligned16(v) && aligned16(dv);
+  if (vec && cols > 256 && cols <= 1024)
+    weight_norm_bwd_row_kernel<1><<<rows, 256, 0, stream>>>(dw, v, g, dv, dg, cols);
+  else if (vec && cols > 1024 && cols <= 2048)
+    weight_norm_bwd_row_kernel<2><<<rows, 256, 0, stream>>>(dw, v, g, dv, dg, cols);
+  else if (vec && cols > 2048 && cols <= 4096)
+    weight_norm_bwd_row_kernel<4><<<rows, 256, 0, stream>>>(dw, v, g, dv, dg, cols);
+  else if (vec)
     weight_norm_bwd_kernel<true><<<(rows + 7) / 8, 256, 0, stream>>>(dw, v, g, dv, dg, rows, cols);
   else
     weight_norm_bwd_kernel<false><<<(rows + 7) / 8, 256, 0, stream>>>(dw, v, g, dv, dg, rows, cols);
@@ -245,13 +355,16 @@ extern "C" int vqa_weight_norm_bwd_f32(const float* dw, const float* v, const fl
 }
 
 extern "C" int vqa_colsum_f32(const float* x, long long ldx, float* out, float* scratch, long long rows, int cols,
-                              cudaStream_t stream) {
+                              int* counters, cudaStream_t stream) {
   VQA_CHECK_ARG(x && out && scratch && rows > 0 && cols > 0 && ldx >= cols, "vqa_colsum_f32: bad arguments");
   const int nblk = (int)min(256LL, (rows + 63) / 64);
   const long long rpb = (rows + nblk - 1) / nblk;
   if ((cols & 3) == 0 && (ldx & 3) == 0 && aligned16(x) && aligned16(scratch)) {
     dim3 grid((cols / 4 + 63) / 64, nblk), block(64, 4);
-    colsum_stage1_v4<<<grid, block, 0, stream>>>(x, ldx, scratch, rows, cols, rpb);
+    const bool fused = counters != nullptr && aligned16(out);
+    colsum_stage1_v4<<<grid, block, 0, stream>>>(x, ldx, scratch, rows, cols, rpb, out, fused ? counters : nullptr);
+    VQA_LAUNCH_CHECK("colsum_stage1_v4");
+    if (fused) return VQA_OK;
   } else {
     dim3 grid((cols + 255) / 256, nblk);
     colsum_stage1<<<grid, 256, 0, stream>>>(x, ldx, scratch, rows, cols, rpb);

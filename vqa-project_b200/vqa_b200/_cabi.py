@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqa_sm100.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 PREC_TF32X3 = 0
 PREC_TF32 = 1
 PREC_TF32X3_HP = 2
@@ -37,7 +37,7 @@ SIGNATURES = {
     "vqa_weight_norm_fwd_f32": [_p, _p, _p, _i, _i, _p],
     "vqa_weight_norm_split_f32": [_p, _p, _i, _i, _i, _i, _p, _p, _ll, _p],
     "vqa_weight_norm_bwd_f32": [_p, _p, _p, _p, _p, _i, _i, _p],
-    "vqa_colsum_f32": [_p, _ll, _p, _p, _ll, _i, _p],
+    "vqa_colsum_f32": [_p, _ll, _p, _p, _ll, _i, _p, _p],
     "vqa_segment_sum_f32": [_p, _p, _i, _i, _i, _p],
     "vqa_adjacency_topk_fwd_f32": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     "vqa_topk_softmax_f32": [_p, _p, _p, _i, _i, _i, _p],

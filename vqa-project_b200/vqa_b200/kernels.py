@@ -14,7 +14,7 @@ from . import _cabi
 from ._cabi import PREC_TF32, PREC_TF32X3, PREC_TF32X3_HP, GEMM_RELU, GEMM_ACCUMULATE, GEMM_NO_CLUSTER, GC_RELU
 
 LAUNCHES = 0
-_LAUNCH_COST = {"vqa_colsum_f32": 2}
+_LAUNCH_COST = {}          # every entry point is one launch (the column sum became a single kernel)
 
 
 def _stream() -> int:
@@ -246,6 +246,18 @@ def weight_norm_bwd(dw: torch.Tensor, v: torch.Tensor, g: torch.Tensor, out=None
     return dv, dg
 
 
+_COLSUM_COUNTERS = {}
+
+
+def _colsum_counters(device: torch.device) -> torch.Tensor:
+    """Persistent zero-initialised ticket counters of the single-launch column sum (the kernel leaves them zero)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    buf = _COLSUM_COUNTERS.get(key)
+    if buf is None:
+        buf = _COLSUM_COUNTERS[key] = torch.zeros(4096, device=device, dtype=torch.int32)
+    return buf
+
+
 def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     x, ldx = _rows_view(_chk(x, "colsum x"), "colsum x")
     if out is None:
@@ -253,7 +265,8 @@ def colsum(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     elif out.numel() != x.shape[1] or not out.is_contiguous():
         raise RuntimeError("colsum: out must be a contiguous tensor with one element per column")
     scratch = torch.empty(256 * x.shape[1], device=x.device, dtype=torch.float32)
-    _call("vqa_colsum_f32", x.data_ptr(), ldx, out.data_ptr(), scratch.data_ptr(), x.shape[0], x.shape[1], _stream())
+    cnt = _colsum_counters(x.device) if x.shape[1] <= 4096 * 256 else None
+    _call("vqa_colsum_f32", x.data_ptr(), ldx, out.data_ptr(), scratch.data_ptr(), x.shape[0], x.shape[1], _ptr(cnt), _stream())
     return out
 
 
