@@ -23,6 +23,7 @@
 #include <cuda_bf16.h>
 #include <mutex>
 #include <cstring>
+#include <cstdlib>
 
 #include "../../include/vqa_b200.h"
 
@@ -344,6 +345,186 @@ gemm_bf16s_kernel(const __grid_constant__ Maps tm, const Params p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------ persistent variant
+// Same tile maths, operands and epilogue; what changes is the schedule.  One CTA (or CTA pair) per SM walks the output tiles
+// unit = cluster + i * #clusters (n fastest, so concurrently running CTAs share their A rows in L2) with TWO TMEM
+// accumulators: the epilogue of tile i (TMEM -> registers -> HBM, up to ~10 us with a mask and split-plane output) runs
+// while the producer and the MMA issuer are already inside tile i+1, and barrier setup / TMEM allocation / descriptor
+// prefetch happen once per CTA instead of once per tile.  With one tile per CTA the epilogue and the prologue were serial:
+// 54 % of the tensor peak on dG1 (K = 1024, mask + planes), 30-35 % on the short-K products (K = 300 / 512).
+struct PSched { int tiles_n, tiles_m, units_m, splits, units, nclusters; };
+
+template <int BN, int PASSES, int CL>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_bf16s_persistent_kernel(const __grid_constant__ Maps tm, const Params p, const PSched sc) {
+  using C = Cfg<BN, PASSES>;
+  constexpr int S = C::S;
+  const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * C::STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + S;
+  uint64_t* acc_full = bars + 2 * S;          // [2]
+  uint64_t* acc_empty = bars + 2 * S + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cluster = blockIdx.x / CL;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm.a_hi); tma_prefetch_desc(&tm.b_hi);
+    if (PASSES == 3) { tma_prefetch_desc(&tm.a_lo); tma_prefetch_desc(&tm.b_lo); }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CL == 2) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // unit -> (split z, row tile(s), column tile); every role decodes the same sequence
+  auto decode = [&](int u, int& n0, int& m0, int& kb_begin, int& nkb, bool& live) {
+    const int tn = u % sc.tiles_n, r = u / sc.tiles_n, um = r % sc.units_m, z = r / sc.units_m;
+    const int mt = um * CL + (int)crank;
+    n0 = tn * BN; m0 = mt * BM;
+    kb_begin = z * p.kb_per_split;
+    nkb = min(p.num_kb, kb_begin + p.kb_per_split) - kb_begin;
+    live = !(CL == 1 && p.tile_gate != nullptr && p.tile_gate[mt] <= p.gate_t);   // row-tile gate: skipped by every role alike
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int u = cluster; u < sc.units; u += sc.nclusters) {
+        int n0, m0, kb_begin, nkb; bool live;
+        decode(u, n0, m0, kb_begin, nkb, live);
+        if (!live) continue;
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], C::STAGE);
+          const int k0 = (kb_begin + i) * BK;
+#pragma unroll
+          for (int pl = 0; pl < C::PLANES; ++pl) {
+            uint8_t* a_dst = smem + s * C::STAGE + pl * C::PLANE;
+            uint8_t* b_dst = a_dst + A_TILE;
+            const CUtensorMap* ma = pl ? &tm.a_lo : &tm.a_hi;
+            const CUtensorMap* mb = pl ? &tm.b_lo : &tm.b_hi;
+            if (!p.a_mn) {
+              tma_load_2d(a_dst, ma, &full[s], k0, m0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BM / 64; ++c) tma_load_2d(a_dst + c * 8192, ma, &full[s], m0 + c * 64, k0);
+            }
+            if (CL == 2) {
+              if (!p.b_mn) {
+                tma_load_2d_mc(b_dst + crank * (BN / 2) * 128, mb, &full[s], k0, n0 + (int)crank * (BN / 2), (uint16_t)3);
+              } else {
+#pragma unroll
+                for (int c = 0; c < BN / 128; ++c) {
+                  const int cc = (int)crank * (BN / 128) + c;
+                  tma_load_2d_mc(b_dst + cc * 8192, mb, &full[s], n0 + cc * 64, k0, (uint16_t)3);
+                }
+              }
+            } else if (!p.b_mn) {
+              tma_load_2d(b_dst, mb, &full[s], k0, n0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BN / 64; ++c) tma_load_2d(b_dst + c * 8192, mb, &full[s], n0 + c * 64, k0);
+            }
+          }
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one thread), accumulator t & 1 for the t-th live tile
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t a_step = p.a_mn ? 2048 : 32, b_step = p.b_mn ? 2048 : 32;   // bytes per K = 16
+      int s = 0, t = 0; uint32_t ph = 0;
+      for (int u = cluster; u < sc.units; u += sc.nclusters) {
+        int n0, m0, kb_begin, nkb; bool live;
+        decode(u, n0, m0, kb_begin, nkb, live);
+        if (!live) continue;
+        const int acc = t & 1;
+        mbar_wait(&acc_empty[acc], ((t >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator (tile t - 2)
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int i = 0; i < nkb; ++i) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + s * C::STAGE), b_hi = a_hi + A_TILE;
+          const uint32_t a_lo = a_hi + C::PLANE, b_lo = a_lo + A_TILE;
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            const uint64_t dah = umma_desc16(a_hi + ks * a_step, p.a_mn), dbh = umma_desc16(b_hi + ks * b_step, p.b_mn);
+            const uint32_t accum = (i > 0 || ks > 0) ? 1u : 0u;
+            if (PASSES == 3) {
+              const uint64_t dal = umma_desc16(a_lo + ks * a_step, p.a_mn), dbl = umma_desc16(b_lo + ks * b_step, p.b_mn);
+              tc_mma<1>(d_tmem, dal, dbh, idesc, accum);   // small terms first
+              tc_mma<1>(d_tmem, dah, dbl, idesc, 1u);
+              tc_mma<1>(d_tmem, dah, dbh, idesc, 1u);
+            } else {
+              tc_mma<1>(d_tmem, dah, dbh, idesc, accum);
+            }
+          }
+          if (CL == 2) tc_commit_mc(&empty[s], (uint16_t)3);
+          else tc_commit(&empty[s]);
+          if (i == nkb - 1) tc_commit(&acc_full[acc]);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+        ++t;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ warps 2-5: epilogue of tile t while tile t + 1 is being accumulated
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    int t = 0;
+    for (int u = cluster; u < sc.units; u += sc.nclusters) {
+      int n0, m0, kb_begin, nkb; bool live;
+      decode(u, n0, m0, kb_begin, nkb, live);
+      if (!live) continue;
+      const int acc = t & 1;
+      if (lane == 0) mbar_wait(&acc_full[acc], (t >> 1) & 1);
+      __syncwarp();
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const Epi epi(p, row_ok ? row : 0);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= p.N) break;            // warp-uniform
+        uint32_t r[32];
+        tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        tc_wait_ld();
+        if (row_ok) epi.store32(n0 + c0, reinterpret_cast<const float*>(r));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      ++t;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CL == 2) cluster_sync_all();          // no CTA leaves while its peer may still multicast into it or arrive on its barriers
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN));
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -376,13 +557,36 @@ static int make_map(CUtensorMap* tm, const void* ptr, long long ld, int mn_exten
 template <int BN, int PASSES, int CL>
 static int launch(const Maps& tm, const Params& p, int splits, cudaStream_t st) {
   using C = Cfg<BN, PASSES>;
+  int mt = (p.M + BM - 1) / BM;
+  if (CL == 2) mt = (mt + 1) & ~1;                 // pairs of vertically adjacent tiles; a padding tile only sees zero-filled rows
+  static const bool one_tile_per_cta = getenv("VQA_GEMM_ONE_TILE_PER_CTA") != nullptr;   // A/B switch for measurements
+  PSched sc;
+  sc.tiles_n = (p.N + BN - 1) / BN; sc.tiles_m = mt; sc.units_m = mt / CL; sc.splits = splits;
+  sc.units = sc.tiles_n * sc.units_m * splits;
+  const int cap = kNumSMs / CL;                    // one CTA per SM (the double-buffered accumulator takes 2 * BN TMEM columns)
+  sc.nclusters = sc.units < cap ? sc.units : cap;
+  if (!one_tile_per_cta && BN >= 128 && sc.units > sc.nclusters) {   // more tiles than SMs: walk them persistently, epilogue overlapped
+    // (BN = 64 is the small-problem tile: two co-resident CTAs per SM with shallow rings already overlap each other)
+    static bool attr_set_p = false;
+    if (!attr_set_p) {
+      VQA_CUDA(cudaFuncSetAttribute(gemm_bf16s_persistent_kernel<BN, PASSES, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+      attr_set_p = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sc.nclusters * CL); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    VQA_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16s_persistent_kernel<BN, PASSES, CL>, tm, p, sc));
+    VQA_LAUNCH_CHECK("gemm_bf16s_persistent_kernel");
+    return VQA_OK;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     VQA_CUDA(cudaFuncSetAttribute(gemm_bf16s_kernel<BN, PASSES, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr_set = true;
   }
-  int mt = (p.M + BM - 1) / BM;
-  if (CL == 2) mt = (mt + 1) & ~1;                 // pairs of vertically adjacent tiles; a padding tile only sees zero-filled rows
   dim3 grid((p.N + BN - 1) / BN, mt, splits);
   if (CL == 1) {
     gemm_bf16s_kernel<BN, PASSES, CL><<<grid, THREADS, C::SMEM, st>>>(tm, p);
