@@ -67,6 +67,25 @@ def _gemm_s(a, b, **kw):
     return kn.gemm_s(a, b, passes=_PASSES, **kw)
 
 
+def _plan(M: int, N: int, K: int, plain: bool = True) -> dict:
+    """Tile width / split-K for the products the library's own heuristic serves badly (measured sweep, tools/gemm_small_sweep.py):
+    few row tiles (M = batch) or a long contraction with a narrow output.  128-wide tiles keep ~100 CTAs busy without the L2
+    re-read cost of 64-wide ones; plain-epilogue products additionally split the contraction to fill / balance the 148 SMs."""
+    mt, kb = (M + 127) // 128, (K + 63) // 64
+    if mt * ((N + 255) // 256) >= 120 and not (plain and kb >= 24 and mt * ((N + 127) // 128) < 296):
+        return {}                                             # plenty of 256-wide tiles: leave it to the library
+    tiles = mt * ((N + 127) // 128)
+    out = {"tile_n": 128} if tiles >= 48 or N > 128 else {}
+    if plain and kb >= 16:
+        if tiles <= 148:
+            sk = max(1, min(148 // tiles, kb // 8))
+        else:
+            sk = 3 if tiles < 296 and kb >= 24 else 1         # 1-2 waves of long tiles: cut them into thirds to balance
+        if sk > 1:
+            out["split_k"] = sk
+    return out
+
+
 def _split_for(out_rows: int, out_cols: int, contraction: int) -> int:
     """Split-K factor for dW = dY^T X products whose output has too few tiles to fill 148 SMs."""
     tiles = ((out_rows + 127) // 128) * ((out_cols + 255) // 256)
@@ -244,12 +263,12 @@ class ConditionedGraphFn(torch.autograd.Function):
 
         # classifier
         hqs = _split(hq)
-        o1 = _gemm_s(hqs, Wo1s, bias=bo1, relu=True)
+        o1 = _gemm_s(hqs, Wo1s, bias=bo1, relu=True, **_plan(B, Wo1s.rows, H, plain=False))
         if drop:
             seed, off, step = next_philox(dev)
             o1 = kn.dropout(o1, p_drop, seed, off, step)
         o1s = _split(o1)
-        logits = _gemm_s(o1s, Wo2s, bias=bo2)
+        logits = _gemm_s(o1s, Wo2s, bias=bo2, **_plan(B, Wo2s.rows, Wo2s.cols, plain=False))
 
         ctx.cfg = dict(B=B, K=K, F=F, H=H, nk=nk, nb=nb, scale=scale, mma1=mma1, mma2=mma2)
         ctx.prm = (b1, b2, bo1, bo2, (mr1, pr1, mt1, pt1), (mr2, pr2, mt2, pt2), conv_ws)   # identities for the gradient sink
@@ -276,10 +295,11 @@ class ConditionedGraphFn(torch.autograd.Function):
         dbo2 = kn.colsum(dlogits, out=_sink(bo2_))
         dWo2 = _gemm_s(dls, o1s, a_mn=True, b_mn=True)
         do1s = kn.empty_split(o1s.rows, o1s.cols, dev, with_lo)
-        do1 = _gemm_s(dls, Wo2s, b_mn=True, aux=o1s, aux_scale=scale, out_split=do1s)   # ReLU + dropout mask from the stored output
+        do1 = _gemm_s(dls, Wo2s, b_mn=True, aux=o1s, aux_scale=scale, out_split=do1s,   # ReLU + dropout mask from the stored output
+                      **_plan(dls.rows, Wo2s.cols, Wo2s.rows, plain=False))
         dbo1 = kn.colsum(do1, out=_sink(bo1_))
         dWo1 = _gemm_s(do1s, hqs, a_mn=True, b_mn=True)
-        dhq = _gemm_s(do1s, Wo1s, b_mn=True)
+        dhq = _gemm_s(do1s, Wo1s, b_mn=True, **_plan(do1s.rows, Wo1s.cols, Wo1s.rows))
         dpooled, dq = kn.gate_bwd(dhq, qenc, pooled)
 
         # graph convolution 2: max-pool scatter by argmax is done inside the kernel
@@ -402,16 +422,17 @@ class QuestionEncoderFn(torch.autograd.Function):
         TB = T * B
 
         def wgrad(a, b, prm):
-            sk = _split_for(a.cols, b.cols, TB)
+            plan = _plan(a.cols, b.cols, TB)
+            plan.setdefault("split_k", _split_for(a.cols, b.cols, TB))
             out = _sink(prm)
-            if out is not None and sk > 1:
+            if out is not None and plan["split_k"] > 1:
                 out.zero_()
-            return kn.gemm_s(a, b, a_mn=True, b_mn=True, split_k=sk, out=out)
+            return kn.gemm_s(a, b, a_mn=True, b_mn=True, out=out, **plan)
         dW_ih = wgrad(dGIs, Es, w_ih_)
         dW_hh = wgrad(dGHs, Hs.rows_slice(0, TB), w_hh_)
         dwemb = None
         if ctx.needs_input_grad[3]:
-            dE = kn.gemm_s(dGIs, Wihs, b_mn=True)                             # (T*B, E)
+            dE = kn.gemm_s(dGIs, Wihs, b_mn=True, **_plan(TB, Wihs.cols, Wihs.rows))   # (T*B, E)
             dwemb = _sink(wemb)
             if dwemb is None:
                 dwemb = torch.zeros_like(wemb)
