@@ -104,7 +104,8 @@ def run_reference(args, workload):
 
 
 def config_dict(w, args, world):
-    return {"workload": f"{w.name}: VQA2 conditioned-graph train step, per-GPU batch {w.batch}, K={w.n_obj} boxes x {w.feat_dim}-d, "
+    family = "medical-VQA (ImageCLEF/MIMIC feature shapes)" if w.name.startswith("med") else "VQA2"
+    return {"workload": f"{w.name}: {family} conditioned-graph train step, per-GPU batch {w.batch}, K={w.n_obj} boxes x {w.feat_dim}-d, "
                         f"<= {w.max_qlen}-token questions, top-k={w.neighbourhood}, {w.n_kernels} Gaussian kernels, {w.out_dim} answers, dropout {w.dropout}",
             "global_batch": w.batch * world, "step": "zero_grad+forward+MultiLabelSoftMarginLoss+backward+allreduce+Adam, " + ("eager launches" if args.no_graph else "one CUDA-graph replay per step (vqa_b200.engine.TrainStep)"),
             "parallelism": f"dp{world}", "gru": "padded masked recurrence on split-bf16 x3 tcgen05 GEMMs (fp32-grade)", "gemm_precision": {"fp32": "split-bf16 x3 passes (fp32-grade, rel err ~1e-5)", "fp32_strict": "split-bf16 x3 passes + chunk-promoted 3xTF32 graph-learner forward",

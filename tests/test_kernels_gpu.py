@@ -520,7 +520,7 @@ def test_graphconv_pool_bwd_data(kn, B, K, nb, nk, out_dim, with_lo):
 
 
 # ---- tensor-core aggregate on split planes (graphconv_mma.cu) -----------------------------------------------------
-MMA_CASES = [(4, 36, 16, 8, 2048), (3, 36, 16, 8, 1024), (2, 51, 19, 4, 512), (2, 100, 32, 8, 1024), (3, 12, 5, 2, 256), (2, 7, 7, 2, 256)]
+MMA_CASES = [(4, 36, 16, 8, 2048), (3, 36, 16, 8, 1024), (2, 51, 19, 4, 512), (3, 51, 19, 8, 1024), (2, 51, 19, 8, 2048), (2, 100, 32, 8, 1024), (3, 12, 5, 2, 256), (2, 7, 7, 2, 256)]
 
 
 @pytest.mark.parametrize("B,K,nb,nk,out_dim", MMA_CASES)

@@ -461,7 +461,7 @@ constexpr int P_CH = 5, P_MAXKC = 4;                   // builder: edges per thr
 struct Agg2Params {
   const float* coef; const unsigned* eoff;
   const float* q; float* pooled; long long* argmax; float* hq;
-  int B, K, KP, nb, nk, out_dim, D, nkc, tpk, slabs, nitems, nstage, nacc, rpg, flags, with_lo;
+  int B, K, KP, nb, nk, out_dim, D, nkc, tpk, slabs, nitems, nstage, nacc, ni, rpg, flags, with_lo;
   float drop_scale; unsigned drop_thresh16; unsigned long long seed, offset; const unsigned long long* step_ptr;
   int off_coef, coef_plane, coef_buf, off_stage, stage_bytes, off_out, out_plane, off_pool, off_bars, tmem_cols;
 };
@@ -498,7 +498,7 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
       for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
       for (int a = 0; a < 8; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], P_EPI / 32); }
       for (int a = 0; a < 2; ++a) {
-        mbar_init(&cfull[a], 1); mbar_init(&cempty[a], P_NI);
+        mbar_init(&cfull[a], 1); mbar_init(&cempty[a], p.ni);
         mbar_init(&sfull[a], P_EPI / 32); mbar_init(&sempty[a], 1);
       }
       fence_barrier_init();
@@ -563,7 +563,9 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
     }
   } else if (warp <= P_NI) {
     // ------------------------------------------------------------ MMA issuers (one thread per warp runs the whole loop)
-    if (lane == 0) {
+    // p.ni <= P_NI issuers are active and p.ni <= #stages: with several consumers on one ring, the issuer of tile g may only wait on
+    // full[g % S] once tile g - S has been loaded (else the parity test is one phase off); its own previous tile g - ni guarantees that
+    if (lane == 0 && warp - 1 < p.ni) {
       uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
       const uint32_t lbo = (uint32_t)KP * 128;
       const int me = warp - 1;
@@ -571,7 +573,7 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
       auto next_tile = [&]() {
         if (++s == S) { s = 0; sph ^= 1; }
         if (++acc == NACC) { acc = 0; aph ^= 1; }
-        if (++owner == P_NI) owner = 0;
+        if (++owner == p.ni) owner = 0;
       };
       for (int it = it0; it < it1; ++it, ++n) {
         const int cb = n & 1;
@@ -602,7 +604,7 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
           }
           tc_commit(&empty[s]);
           tc_commit(&tfull[acc]);
-          mine = t + P_NI >= tiles_per_item;                        // my last tile of this item
+          mine = t + p.ni >= tiles_per_item;                        // my last tile of this item
           if (mine) tc_commit(&cempty[cb]);                          // coefficient buffer free once every issuer's MMAs of the item retire
         }
         if (!mine) mbar_arrive(&cempty[cb]);                        // no tile of this item was mine
@@ -1156,6 +1158,7 @@ static int agg_launch(const void* in_hi, const void* in_lo, long long ldin, void
     if (S2 >= 2) {
       if (S2 > 8) S2 = 8;
       a.nstage = S2;
+      a.ni = S2 < P_NI ? S2 : P_NI;
       int o2 = 0;
       a.off_coef = o2; o2 += 2 * a.coef_buf; o2 = (o2 + 1023) & ~1023;
       a.off_stage = o2; o2 += S2 * p.stage_bytes;
