@@ -168,10 +168,25 @@ def run_b200(args, workload):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line (the JSON): libraries that write to fd 1 on their own (NCCL prints its version banner
+    # there on the first communicator) are pointed at stderr, the JSON line goes to the saved descriptor
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device: the vqa_b200 path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = "unbound"
+    try:        # run this rank (and first-touch its pinned batches) on the CPUs next to its GPU: 8 ranks x 158 MB of H2D per step
+        import pynvml                                      # otherwise all cross one socket link
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else local
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+        numa = f"nvml cpu affinity of gpu {phys}: {len(os.sched_getaffinity(0))} cpus"
+    except Exception as e:                                 # pragma: no cover - affinity is an optimisation, never a requirement
+        numa = f"unbound ({type(e).__name__})"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ops.set_precision(args.precision)
@@ -395,7 +410,8 @@ def run_b200(args, workload):
         "roofline": roof, "roofline_other_kernels": extra, "roofline_gemm": roof_gemm, "cpu_baseline": cpu,
         "clocks": sampler.summary(), "final_loss": final_loss, "bf16_mode": bf16_mode,
     }
-    print(json.dumps(line), flush=True)
+    line["config"]["host_affinity"] = numa
+    print(json.dumps(line), file=json_out, flush=True)
     leave()
 
 
