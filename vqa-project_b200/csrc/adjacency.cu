@@ -25,32 +25,36 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // One warp per row, <= 4 entries per lane (K <= 128).  rank(j) = #{j' : A[j'] > A[j] or (A[j'] == A[j] and j' < j)};
 // entry j is selected iff rank < nb and is emitted at slot rank -> output is in descending-value order, ties go to
 // the lower index.  The reference's topk(sorted=False) order is unspecified; callers compare index SETS.
-__device__ void topk_softmax_rows(const float* As, int KP, int K, int nb, int* __restrict__ idx_out,
-                                  float* __restrict__ alpha_out) {
+// NE = ceil(K / 32) entries per lane: the rank loop costs K * NE compare-and-count steps per row, so it is instantiated per NE
+template <int NE>
+__device__ __forceinline__ void topk_softmax_rows_ne(const float* As, int KP, int K, int nb, int* __restrict__ idx_out,
+                                                     float* __restrict__ alpha_out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = warp; i < K; i += ADJ_WARPS) {
     const float* row = As + i * KP;
-    float x[4];
-    int rank[4] = {0, 0, 0, 0};
+    float x[NE];
+    int rank[NE];
     float mx = -INFINITY;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < NE; ++e) {
       const int j = lane + 32 * e;
       x[e] = j < K ? row[j] : -INFINITY;
+      rank[e] = 0;
       mx = fmaxf(mx, x[e]);
     }
     mx = warp_max(mx);
+#pragma unroll 4
     for (int jj = 0; jj < K; ++jj) {
       const float y = row[jj];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < NE; ++e) {
         const int j = lane + 32 * e;
         rank[e] += (y > x[e] || (y == x[e] && jj < j)) ? 1 : 0;
       }
     }
-    float ex[4], s = 0.f;
+    float ex[NE], s = 0.f;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < NE; ++e) {
       const int j = lane + 32 * e;
       const bool sel = j < K && rank[e] < nb;
       ex[e] = sel ? expf(x[e] - mx) : 0.f;
@@ -58,7 +62,7 @@ __device__ void topk_softmax_rows(const float* As, int KP, int K, int nb, int* _
     }
     s = warp_sum(s);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < NE; ++e) {
       const int j = lane + 32 * e;
       if (j < K && rank[e] < nb) {
         idx_out[i * nb + rank[e]] = j;
@@ -66,6 +70,13 @@ __device__ void topk_softmax_rows(const float* As, int KP, int K, int nb, int* _
       }
     }
   }
+}
+__device__ void topk_softmax_rows(const float* As, int KP, int K, int nb, int* __restrict__ idx_out,
+                                  float* __restrict__ alpha_out) {
+  if (K <= 32) topk_softmax_rows_ne<1>(As, KP, K, nb, idx_out, alpha_out);
+  else if (K <= 64) topk_softmax_rows_ne<2>(As, KP, K, nb, idx_out, alpha_out);
+  else if (K <= 96) topk_softmax_rows_ne<3>(As, KP, K, nb, idx_out, alpha_out);
+  else topk_softmax_rows_ne<4>(As, KP, K, nb, idx_out, alpha_out);
 }
 
 // MAXT: upper-triangle 4x4 tiles owned per thread (1 for K <= 64 incl. the split-C groups, up to 3 for K <= 128)
