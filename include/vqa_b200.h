@@ -20,7 +20,7 @@ extern "C" {
 
 typedef struct CUstream_st* vqa_stream_t; /* cudaStream_t */
 
-#define VQA_ABI_VERSION 5
+#define VQA_ABI_VERSION 6
 
 /* GEMM precision modes */
 #define VQA_PREC_TF32X3 0 /* 3-pass split TF32 on tcgen05: fp32-grade results (parity mode)      */
@@ -213,6 +213,15 @@ int vqa_embed_scatter_add_f32(const float* dE, long long ldd, const long long* q
 int vqa_gru_cell_fwd_f32(const float* gi, long long ldgi, const float* gh, const float* b_hh, const float* h_prev,
                          const int* len, int t, float* h_out, void* h_hi, void* h_lo, long long ldp, float* gates, int B,
                          int H, vqa_stream_t stream);
+/* The same step as ONE kernel: gh = h_{t-1} W_hh^T on the tensor cores (3-pass split-bf16) with the cell evaluated straight
+ * out of TMEM - no (B,3H) gh round trip, no separate cell launch.  Whh planes (3H,H), gi (B,3H; includes b_ih) and b_hh (3H)
+ * are given in UNIT-BLOCK order: block u = rows/columns [r | z | n] of hidden units 32u..32u+31 (row u*96 + g*32 + i <-
+ * original row g*H + u*32 + i); h_t, its planes and the gates are written in the original layouts.  tile_gate (optional, one
+ * int per 128 batch rows): row tiles with tile_gate[m] <= t are skipped, their outputs are NOT written.  H % 32 == 0. */
+int vqa_gru_step_fused(const void* hprev_hi, const void* hprev_lo, long long ldh, const void* Whh_hi, const void* Whh_lo,
+                       long long ldw, const float* gi, long long ldgi, const float* b_hh, const float* h_prev, const int* len,
+                       int t, float* h_out, void* hout_hi, void* hout_lo, long long ldp, float* gates, const int* tile_gate,
+                       int B, int H, vqa_stream_t stream);
 /* Backward of one step: dh (B,H) -> dgi, dgh (B,3H; fp32 and split planes, ld = ldp) and dh_part (B,H), the direct
  * part of dL/dh_{t-1}; the caller adds dgh W_hh. */
 int vqa_gru_cell_bwd_f32(const float* dh, const float* gates, const float* h_prev, const int* len, int t, float* dgi,

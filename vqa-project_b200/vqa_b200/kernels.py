@@ -134,6 +134,12 @@ def empty_split(rows: int, cols: int, device, with_lo: bool = True) -> SplitT:
     return SplitT(buf[0], buf[1] if with_lo else None, rows, cols, ld)
 
 
+def zeros_split(rows: int, cols: int, device, with_lo: bool = True) -> SplitT:
+    ld = (cols + 7) // 8 * 8
+    buf = torch.zeros((2 if with_lo else 1, rows, ld), device=device, dtype=torch.bfloat16)
+    return SplitT(buf[0], buf[1] if with_lo else None, rows, cols, ld)
+
+
 def split(x: torch.Tensor, with_lo: bool = True) -> SplitT:
     """fp32 (rows, cols) -> bf16 planes hi = bf16(x), lo = bf16(x - hi)."""
     x, ldx = _rows_view(_chk(x, "split x"), "split x")
@@ -510,6 +516,16 @@ def gru_cell_fwd(gi, gh, b_hh, h_prev, qlen, t, h_out, h_split: SplitT, gates):
     B, H = h_out.shape
     _call("vqa_gru_cell_fwd_f32", gi.data_ptr(), ldgi, _ptr(gh), b_hh.data_ptr(), _ptr(h_prev), qlen.data_ptr(), t, h_out.data_ptr(),
           h_split.hi.data_ptr(), _ptr(h_split.lo), h_split.ld, gates.data_ptr(), B, H, _stream())
+
+
+def gru_step_fused(hprev: "SplitT", Whh_ub: "SplitT", gi_ub: torch.Tensor, b_hh_ub: torch.Tensor, h_prev: torch.Tensor, qlen: torch.Tensor,
+                   t: int, h_out: torch.Tensor, hout: "SplitT", gates: torch.Tensor, tile_len: Optional[torch.Tensor] = None) -> None:
+    """One GRU step as one kernel (product + cell).  ``Whh_ub`` / ``gi_ub`` / ``b_hh_ub`` in unit-block order (see the header)."""
+    B, H = h_prev.shape
+    gi_ub, ldgi = _rows_view(_chk(gi_ub, "gru gi"), "gru gi")
+    _call("vqa_gru_step_fused", hprev.hi.data_ptr(), hprev.lo.data_ptr(), hprev.ld, Whh_ub.hi.data_ptr(), Whh_ub.lo.data_ptr(), Whh_ub.ld,
+          gi_ub.data_ptr(), ldgi, b_hh_ub.data_ptr(), h_prev.data_ptr(), qlen.data_ptr(), int(t), h_out.data_ptr(), hout.hi.data_ptr(),
+          hout.lo.data_ptr(), hout.ld, gates.data_ptr(), _ptr(tile_len), B, H, _stream())
 
 
 def gru_cell_bwd(dh, gates, h_prev, qlen, t, dgi, dgh, dgi_s: SplitT, dgh_s: SplitT, dh_part):

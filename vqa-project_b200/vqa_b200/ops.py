@@ -355,6 +355,23 @@ class ConditionedGraphFn(torch.autograd.Function):
                 dvo1, dgo1, dbo1, dvo2, dgo2, dbo2, *conv_grads)
 
 
+# One kernel per forward step (product + cell out of TMEM, kernels.gru_step_fused) instead of product and cell as two launches.
+# Correct and tested both ways; measured at B=512, H=1024: 3.92 ms/step fused vs 3.86 ms unfused, so it is OFF.  Either way a
+# step moves ~100 MB of operands from L2 to the SMs (every CTA re-reads its 512 KB slice of h and of W_hh: 17-24 us at L2
+# bandwidth against ~5 us of tensor time) - the fusion removes the 6 MB gh round trip and a launch, not that.  What will:
+# cluster multicast of the h tile along N and of the W_hh tile along M.
+GRU_FUSED = False
+_UB_PERM = {}
+
+
+def _unit_block_perm(H: int, device) -> torch.Tensor:
+    """Row permutation of the (3H, .) GRU weights into unit-block order: new row u*96 + g*32 + i <- old row g*H + u*32 + i."""
+    key = (H, str(device))
+    if key not in _UB_PERM:
+        _UB_PERM[key] = torch.arange(3 * H, device=device).view(3, H // 32, 32).permute(1, 0, 2).reshape(-1).contiguous()
+    return _UB_PERM[key]
+
+
 class QuestionEncoderFn(torch.autograd.Function):
     """(question tokens, lengths, embedding + GRU parameters) -> final GRU state per question (B, H).
 
@@ -371,27 +388,43 @@ class QuestionEncoderFn(torch.autograd.Function):
         Wihs, Whhs = kn.split(w_ih), kn.split(w_hh)
         b_ih = b_ih.contiguous()
         b_hh = b_hh.contiguous()
-        GI = kn.gemm_s(Es, Wihs, bias=b_ih)                                   # (T*B, 3H), all steps at once
         Hall = torch.empty((T + 1, B, H), device=dev, dtype=torch.float32)     # Hall[t+1] = h_t, Hall[0] = 0
-        Hs = kn.empty_split((T + 1) * B, H, dev)
-        Hall[0].zero_(); Hs.hi[:B].zero_(); Hs.lo[:B].zero_()
         gates = torch.empty((T, B, 4 * H), device=dev, dtype=torch.float32)
-        # per-step product h W_hh^T: L2-bandwidth bound at M = B rows (measured sweep, tools/gru_gemm_sweep.py): 128-wide tiles, no split
-        tile = 128 if B <= 1024 else 0
         # longest question per 128-row tile: the per-step products skip row tiles whose sequences have all ended (the reference's
         # collate_fn sorts a batch by descending length, so the active rows are a shrinking prefix; any order stays correct)
         pad = (-B) % 128
         tile_len = torch.nn.functional.pad(qlen.to(torch.int32), (0, pad)).view(-1, 128).amax(dim=1).to(torch.int32).contiguous()
-        for t in range(T):
-            GH = kn.gemm_s(Hs.rows_slice(t * B, (t + 1) * B), Whhs, tile_n=tile, row_gate=(tile_len, t)) if t > 0 else None
-            kn.gru_cell_fwd(GI[t * B:(t + 1) * B], GH, b_hh, Hall[t] if t > 0 else None, qlen, t, Hall[t + 1],
-                            Hs.rows_slice((t + 1) * B, (t + 2) * B), gates[t])
+        if GRU_FUSED and H % 32 == 0:
+            # one kernel per step: product + cell out of TMEM.  Weights / input projections in unit-block order
+            # (block u = [r | z | n] of units 32u..32u+31) so that one 128 x 96 accumulator holds all gates of its units
+            perm = _unit_block_perm(H, dev)
+            Wih_ub, Whh_ub = kn.split(w_ih.index_select(0, perm)), kn.split(w_hh.index_select(0, perm))
+            GI = kn.gemm_s(Es, Wih_ub, bias=b_ih.index_select(0, perm))        # (T*B, 3H) in unit-block column order
+            b_hh_ub = b_hh.index_select(0, perm)
+            Hs = kn.zeros_split((T + 1) * B, H, dev)                           # skipped row tiles stay zero (dW_hh reads all rows)
+            Hall[0].zero_()
+            for t in range(T):
+                kn.gru_step_fused(Hs.rows_slice(t * B, (t + 1) * B), Whh_ub, GI[t * B:(t + 1) * B], b_hh_ub, Hall[t], qlen, t, Hall[t + 1],
+                                  Hs.rows_slice((t + 1) * B, (t + 2) * B), gates[t], tile_len)
+            # every question's state at its OWN last step (rows of skipped tiles are not carried forward)
+            out = Hall[qlen.to(torch.int64).clamp(min=0, max=T), torch.arange(B, device=dev)]
+        else:
+            GI = kn.gemm_s(Es, Wihs, bias=b_ih)                                   # (T*B, 3H), all steps at once
+            Hs = kn.empty_split((T + 1) * B, H, dev)
+            Hall[0].zero_(); Hs.hi[:B].zero_(); Hs.lo[:B].zero_()
+            # per-step product h W_hh^T: L2-bandwidth bound at M = B rows (measured sweep, tools/gru_gemm_sweep.py): 128-wide tiles, no split
+            tile = 128 if B <= 1024 else 0
+            for t in range(T):
+                GH = kn.gemm_s(Hs.rows_slice(t * B, (t + 1) * B), Whhs, tile_n=tile, row_gate=(tile_len, t)) if t > 0 else None
+                kn.gru_cell_fwd(GI[t * B:(t + 1) * B], GH, b_hh, Hall[t] if t > 0 else None, qlen, t, Hall[t + 1],
+                                Hs.rows_slice((t + 1) * B, (t + 2) * B), gates[t])
+            out = Hall[T]
         ctx.T = T
         ctx.prm = (w_ih, w_hh, b_ih, b_hh)
         ctx.tile_len = tile_len
         ctx.splits = (Es, Wihs, Whhs, Hs)
         ctx.save_for_backward(question, qlen, wemb, Hall, gates)
-        return Hall[T]
+        return out
 
     @staticmethod
     def backward(ctx, dq):
