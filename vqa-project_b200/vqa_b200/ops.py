@@ -356,10 +356,10 @@ class ConditionedGraphFn(torch.autograd.Function):
 
 
 # One kernel per forward step (product + cell out of TMEM, kernels.gru_step_fused) instead of product and cell as two launches.
-# Correct and tested both ways; measured at B=512, H=1024: 3.92 ms/step fused vs 3.86 ms unfused, so it is OFF.  Either way a
-# step moves ~100 MB of operands from L2 to the SMs (every CTA re-reads its 512 KB slice of h and of W_hh: 17-24 us at L2
-# bandwidth against ~5 us of tensor time) - the fusion removes the 6 MB gh round trip and a launch, not that.  What will:
-# cluster multicast of the h tile along N and of the W_hh tile along M.
+# Correct and tested both ways; measured at B=512, H=1024: 3.92 ms/step fused vs 3.86 ms unfused, so it is OFF.  Either way every
+# CTA of a step streams ~64 KB of operand planes per k-block into its SM (~1000 cycles per k-block against ~770 of tensor
+# time, 16 k-blocks, plus launch / prologue / epilogue): the fusion removes the 6 MB gh round trip and a launch, not that.
+# Multicasting the shared A tile between horizontally adjacent CTAs was tried too (same bytes arrive in every SM): no gain.
 GRU_FUSED = False
 _UB_PERM = {}
 
