@@ -20,7 +20,7 @@ extern "C" {
 
 typedef struct CUstream_st* vqa_stream_t; /* cudaStream_t */
 
-#define VQA_ABI_VERSION 6
+#define VQA_ABI_VERSION 7
 
 /* GEMM precision modes */
 #define VQA_PREC_TF32X3 0 /* 3-pass split TF32 on tcgen05: fp32-grade results (parity mode)      */
@@ -222,6 +222,13 @@ int vqa_gru_step_fused(const void* hprev_hi, const void* hprev_lo, long long ldh
                        long long ldw, const float* gi, long long ldgi, const float* b_hh, const float* h_prev, const int* len,
                        int t, float* h_out, void* hout_hi, void* hout_lo, long long ldp, float* gates, const int* tile_gate,
                        int B, int H, vqa_stream_t stream);
+/* All T steps in ONE cooperative launch (grid barrier between steps instead of kernel boundaries; needs H/32 * ceil(B/128)
+ * <= 148 CTAs, else VQA_ERR_UNSUPPORTED).  H planes: ((T+1)*B, H) with rows [0,B) = h_{-1} = 0 supplied by the caller, rows
+ * (t+1)*B.. receive h_t; Hall: (T+1, B, H) fp32 likewise; gi: (T*B, 3H) and Whh / b_hh in unit-block order; gates: (T, B, 4H);
+ * counter: one device word used by the grid barrier (zeroed by this call). */
+int vqa_gru_seq_fused(const void* H_hi, const void* H_lo, long long ldh, const void* Whh_hi, const void* Whh_lo, long long ldw,
+                      const float* gi, long long ldgi, const float* b_hh, float* Hall, const int* len, float* gates,
+                      const int* tile_gate, unsigned* counter, int T, int B, int H, vqa_stream_t stream);
 /* Backward of one step: dh (B,H) -> dgi, dgh (B,3H; fp32 and split planes, ld = ldp) and dh_part (B,H), the direct
  * part of dL/dh_{t-1}; the caller adds dgh W_hh. */
 int vqa_gru_cell_bwd_f32(const float* dh, const float* gates, const float* h_prev, const int* len, int t, float* dgi,

@@ -226,7 +226,7 @@ def test_gemm_split_bf16_accumulate_and_auto_tile(kn):
 # --------------------------------------------------------------------------------------------- question encoder
 @pytest.mark.parametrize("B,T,H,V,E,sort", [(9, 7, 64, 50, 300, False), (33, 14, 128, 200, 300, False), (4, 3, 32, 11, 24, False),
                                             (300, 12, 64, 40, 24, True), (260, 9, 32, 40, 24, False)])
-@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("fused", ["seq", "step", "off"])
 def test_question_encoder_matches_packed_gru(B, T, H, V, E, sort, fused, monkeypatch):
     """ops.QuestionEncoderFn (padded, masked recurrence on our kernels) vs nn.Embedding + pack_padded_sequence + nn.GRU
     in fp64 on the CPU (the reference's construction, sparse_graph_model.py:117-121), forward and every gradient.
@@ -234,7 +234,8 @@ def test_question_encoder_matches_packed_gru(B, T, H, V, E, sort, fused, monkeyp
     unsorted: tiles stay alive as long as any of their rows is)."""
     from torch.nn.utils.rnn import pack_padded_sequence
     from vqa_b200 import ops
-    monkeypatch.setattr(ops, "GRU_FUSED", fused)          # one kernel per step (product + cell out of TMEM) vs two launches
+    monkeypatch.setattr(ops, "GRU_FUSED_SEQ", "1" if fused == "seq" else "0")     # all steps in one cooperative launch (grid barrier between steps)
+    monkeypatch.setattr(ops, "GRU_FUSED", fused == "step")        # one kernel per step (product + cell out of TMEM); "off": two launches per step
     g = torch.Generator().manual_seed(B * 100 + T)
     lens = torch.randint(1, T + 1, (B,), generator=g)
     lens[0] = T

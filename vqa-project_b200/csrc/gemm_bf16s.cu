@@ -544,6 +544,75 @@ struct GruParams {
 };
 __device__ __forceinline__ float gru_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
 
+// The cell for the 128 x 96 accumulator of CTA (u, row tile m0): shared by the per-step and the whole-sequence kernels.
+__device__ __forceinline__ void gru_cell_from_tmem(const GruParams& p, uint32_t tmem_base, uint64_t* acc_full, uint32_t acc_parity, int warp,
+                                                   int lane, int u, int m0) {
+    // ------------------------------------------------------------ warps 2-5: the cell, one batch row per thread.  The row's input
+    // projections and previous state (128 floats) are fetched into registers WHILE the product is being accumulated.
+    const int q = warp & 3, b = m0 + q * 32 + lane;
+    const bool row_ok = b < p.B;
+    const int H = p.H, j0 = u * 32;
+    const long long br_ = row_ok ? b : 0;
+    const bool active = row_ok && p.t < p.len[br_];
+    const float* gib = p.gi + br_ * p.ldgi + u * G_BN;
+    const float* bh = p.b_hh + u * G_BN;
+    float4 gi4[24], hp4[8];
+#pragma unroll
+    for (int v = 0; v < 24; ++v) gi4[v] = *reinterpret_cast<const float4*>(gib + v * 4);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) hp4[v] = *reinterpret_cast<const float4*>(p.h_prev + br_ * H + j0 + v * 4);
+    if (lane == 0) mbar_wait(acc_full, acc_parity);
+    __syncwarp();
+    tc_fence_after();
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+    for (int c = 0; c < 32; c += 8) {
+      uint32_t ar[8], az[8], an[8];
+      tc_ld_32x8(lane_base + (uint32_t)c, ar);
+      tc_ld_32x8(lane_base + (uint32_t)(32 + c), az);
+      tc_ld_32x8(lane_base + (uint32_t)(64 + c), an);
+      tc_wait_ld();
+      float hv[8], rr[8], zz[8], nn[8], mm[8];
+#pragma unroll
+      for (int e = 0; e < 8; e += 4) {
+        const float4 ir = gi4[(c + e) >> 2], iz = gi4[8 + ((c + e) >> 2)], in_ = gi4[16 + ((c + e) >> 2)], h4 = hp4[(c + e) >> 2];
+        const float4 br = __ldg(reinterpret_cast<const float4*>(bh + c + e)), bz = __ldg(reinterpret_cast<const float4*>(bh + 32 + c + e)),
+                     bn = __ldg(reinterpret_cast<const float4*>(bh + 64 + c + e));
+        const float air[4] = {ir.x, ir.y, ir.z, ir.w}, aiz[4] = {iz.x, iz.y, iz.z, iz.w}, ain[4] = {in_.x, in_.y, in_.z, in_.w};
+        const float abr[4] = {br.x, br.y, br.z, br.w}, abz[4] = {bz.x, bz.y, bz.z, bz.w}, abn[4] = {bn.x, bn.y, bn.z, bn.w};
+        const float ahp[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const float ghr = __uint_as_float(ar[e + w]) + abr[w], ghz = __uint_as_float(az[e + w]) + abz[w], ghn = __uint_as_float(an[e + w]) + abn[w];
+          const float r = gru_sigmoid(air[w] + ghr), z = gru_sigmoid(aiz[w] + ghz);
+          const float n = tanhf(ain[w] + r * ghn);
+          const float hnew = (1.f - z) * n + z * ahp[w];
+          hv[e + w] = active ? hnew : ahp[w];
+          rr[e + w] = r; zz[e + w] = z; nn[e + w] = n; mm[e + w] = ghn;
+        }
+      }
+      if (row_ok) {
+        float* ho = p.h_out + (long long)b * H + j0 + c;
+        *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+        uint32_t hh[4], ll[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          hh[e] = pack_bf16(hv[2 * e], hv[2 * e + 1]);
+          ll[e] = pack_bf16(hv[2 * e] - __uint_as_float(hh[e] << 16), hv[2 * e + 1] - __uint_as_float(hh[e] & 0xFFFF0000u));
+        }
+        const long long po = (long long)b * p.ldp + j0 + c;
+        *reinterpret_cast<uint4*>(p.hout_hi + po) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+        *reinterpret_cast<uint4*>(p.hout_lo + po) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+        float* g = p.gates + (long long)b * 4 * H + j0 + c;
+        *reinterpret_cast<float4*>(g) = make_float4(rr[0], rr[1], rr[2], rr[3]);          *reinterpret_cast<float4*>(g + 4) = make_float4(rr[4], rr[5], rr[6], rr[7]);
+        *reinterpret_cast<float4*>(g + H) = make_float4(zz[0], zz[1], zz[2], zz[3]);      *reinterpret_cast<float4*>(g + H + 4) = make_float4(zz[4], zz[5], zz[6], zz[7]);
+        *reinterpret_cast<float4*>(g + 2 * H) = make_float4(nn[0], nn[1], nn[2], nn[3]);  *reinterpret_cast<float4*>(g + 2 * H + 4) = make_float4(nn[4], nn[5], nn[6], nn[7]);
+        *reinterpret_cast<float4*>(g + 3 * H) = make_float4(mm[0], mm[1], mm[2], mm[3]);  *reinterpret_cast<float4*>(g + 3 * H + 4) = make_float4(mm[4], mm[5], mm[6], mm[7]);
+      }
+    }
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 gru_step_kernel(const __grid_constant__ Maps tm, const GruParams p) {
   constexpr int S = G_S, PLANE = A_TILE + G_BN * 128;
@@ -610,70 +679,115 @@ gru_step_kernel(const __grid_constant__ Maps tm, const GruParams p) {
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------ warps 2-5: the cell, one batch row per thread.  The row's input
-    // projections and previous state (128 floats) are fetched into registers WHILE the product is being accumulated.
-    const int q = warp & 3, b = m0 + q * 32 + lane;
-    const bool row_ok = b < p.B;
-    const int H = p.H, j0 = u * 32;
-    const long long br_ = row_ok ? b : 0;
-    const bool active = row_ok && p.t < p.len[br_];
-    const float* gib = p.gi + br_ * p.ldgi + u * G_BN;
-    const float* bh = p.b_hh + u * G_BN;
-    float4 gi4[24], hp4[8];
-#pragma unroll
-    for (int v = 0; v < 24; ++v) gi4[v] = *reinterpret_cast<const float4*>(gib + v * 4);
-#pragma unroll
-    for (int v = 0; v < 8; ++v) hp4[v] = *reinterpret_cast<const float4*>(p.h_prev + br_ * H + j0 + v * 4);
-    if (lane == 0) mbar_wait(acc_full, 0);
+    gru_cell_from_tmem(p, tmem_base, acc_full, 0u, warp, lane, u, m0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128));
+  }
+}
+
+// The whole recurrence in ONE launch: the step kernel's body inside a loop over t, barriers / TMEM set up once, a grid-wide
+// barrier (monotonic counter, cooperative launch: all CTAs are co-resident) between steps instead of a kernel boundary.
+struct GruSeq { int T; unsigned* counter; long long gi_step, hp_step, ho_step, hpl_step, gates_step; };
+
+__global__ void __launch_bounds__(THREADS, 1)
+gru_seq_kernel(const __grid_constant__ Maps tm, const GruParams p0, const GruSeq sq) {
+  constexpr int S = G_S, PLANE = A_TILE + G_BN * 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * G_STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + S;
+  uint64_t* acc_full = bars + 2 * S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u = blockIdx.x, m0 = blockIdx.y * BM;
+  const unsigned nctas = gridDim.x * gridDim.y;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm.a_hi); tma_prefetch_desc(&tm.b_hi); tma_prefetch_desc(&tm.a_lo); tma_prefetch_desc(&tm.b_lo); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      mbar_init(acc_full, 1);
+      fence_barrier_init();
+    }
     __syncwarp();
-    tc_fence_after();
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int gate = p0.tile_gate ? p0.tile_gate[blockIdx.y] : 0x7fffffff;   // this row tile is live while t < gate (a prefix of the steps)
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(G_BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  int it = 0;                                              // k-blocks issued / consumed so far (ring position), per role
+
+  for (int t = 0; t < sq.T; ++t) {
+    if (t < gate) {
+      if (warp == 0) {
+        if (lane == 0) {
+          asm volatile("fence.proxy.async.global;" ::: "memory");   // h_{t-1} planes were written with generic stores by other CTAs
+          for (int i = 0; i < p0.num_kb; ++i, ++it) {
+            const int s = it % S, ph = (it / S) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full[s], G_STAGE);
 #pragma unroll
-    for (int c = 0; c < 32; c += 8) {
-      uint32_t ar[8], az[8], an[8];
-      tc_ld_32x8(lane_base + (uint32_t)c, ar);
-      tc_ld_32x8(lane_base + (uint32_t)(32 + c), az);
-      tc_ld_32x8(lane_base + (uint32_t)(64 + c), an);
-      tc_wait_ld();
-      float hv[8], rr[8], zz[8], nn[8], mm[8];
-#pragma unroll
-      for (int e = 0; e < 8; e += 4) {
-        const float4 ir = gi4[(c + e) >> 2], iz = gi4[8 + ((c + e) >> 2)], in_ = gi4[16 + ((c + e) >> 2)], h4 = hp4[(c + e) >> 2];
-        const float4 br = __ldg(reinterpret_cast<const float4*>(bh + c + e)), bz = __ldg(reinterpret_cast<const float4*>(bh + 32 + c + e)),
-                     bn = __ldg(reinterpret_cast<const float4*>(bh + 64 + c + e));
-        const float air[4] = {ir.x, ir.y, ir.z, ir.w}, aiz[4] = {iz.x, iz.y, iz.z, iz.w}, ain[4] = {in_.x, in_.y, in_.z, in_.w};
-        const float abr[4] = {br.x, br.y, br.z, br.w}, abz[4] = {bz.x, bz.y, bz.z, bz.w}, abn[4] = {bn.x, bn.y, bn.z, bn.w};
-        const float ahp[4] = {h4.x, h4.y, h4.z, h4.w};
-#pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          const float ghr = __uint_as_float(ar[e + w]) + abr[w], ghz = __uint_as_float(az[e + w]) + abz[w], ghn = __uint_as_float(an[e + w]) + abn[w];
-          const float r = gru_sigmoid(air[w] + ghr), z = gru_sigmoid(aiz[w] + ghz);
-          const float n = tanhf(ain[w] + r * ghn);
-          const float hnew = (1.f - z) * n + z * ahp[w];
-          hv[e + w] = active ? hnew : ahp[w];
-          rr[e + w] = r; zz[e + w] = z; nn[e + w] = n; mm[e + w] = ghn;
+            for (int pl = 0; pl < 2; ++pl) {
+              uint8_t* a_dst = smem + s * G_STAGE + pl * PLANE;
+              tma_load_2d(a_dst, pl ? &tm.a_lo : &tm.a_hi, &full[s], i * BK, t * p0.B + m0);   // A map covers all (T+1)*B rows of the h planes
+              tma_load_2d(a_dst + A_TILE, pl ? &tm.b_lo : &tm.b_hi, &full[s], i * BK, u * G_BN);
+            }
+          }
         }
-      }
-      if (row_ok) {
-        float* ho = p.h_out + (long long)b * H + j0 + c;
-        *reinterpret_cast<float4*>(ho) = make_float4(hv[0], hv[1], hv[2], hv[3]);
-        *reinterpret_cast<float4*>(ho + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
-        uint32_t hh[4], ll[4];
+      } else if (warp == 1) {
+        if (lane == 0) {
+          for (int i = 0; i < p0.num_kb; ++i, ++it) {
+            const int s = it % S, ph = (it / S) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(smem + s * G_STAGE), b_hi = a_hi + A_TILE;
+            const uint32_t a_lo = a_hi + PLANE, b_lo = a_lo + A_TILE;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          hh[e] = pack_bf16(hv[2 * e], hv[2 * e + 1]);
-          ll[e] = pack_bf16(hv[2 * e] - __uint_as_float(hh[e] << 16), hv[2 * e + 1] - __uint_as_float(hh[e] & 0xFFFF0000u));
+            for (int ks = 0; ks < BK / 16; ++ks) {
+              const uint64_t dah = umma_desc16(a_hi + ks * 32, 0), dbh = umma_desc16(b_hi + ks * 32, 0);
+              const uint64_t dal = umma_desc16(a_lo + ks * 32, 0), dbl = umma_desc16(b_lo + ks * 32, 0);
+              tc_mma<1>(tmem_base, dal, dbh, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+              tc_mma<1>(tmem_base, dah, dbl, idesc, 1u);
+              tc_mma<1>(tmem_base, dah, dbh, idesc, 1u);
+            }
+            tc_commit(&empty[s]);
+            if (i == p0.num_kb - 1) tc_commit(acc_full);
+          }
         }
-        const long long po = (long long)b * p.ldp + j0 + c;
-        *reinterpret_cast<uint4*>(p.hout_hi + po) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-        *reinterpret_cast<uint4*>(p.hout_lo + po) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-        float* g = p.gates + (long long)b * 4 * H + j0 + c;
-        *reinterpret_cast<float4*>(g) = make_float4(rr[0], rr[1], rr[2], rr[3]);          *reinterpret_cast<float4*>(g + 4) = make_float4(rr[4], rr[5], rr[6], rr[7]);
-        *reinterpret_cast<float4*>(g + H) = make_float4(zz[0], zz[1], zz[2], zz[3]);      *reinterpret_cast<float4*>(g + H + 4) = make_float4(zz[4], zz[5], zz[6], zz[7]);
-        *reinterpret_cast<float4*>(g + 2 * H) = make_float4(nn[0], nn[1], nn[2], nn[3]);  *reinterpret_cast<float4*>(g + 2 * H + 4) = make_float4(nn[4], nn[5], nn[6], nn[7]);
-        *reinterpret_cast<float4*>(g + 3 * H) = make_float4(mm[0], mm[1], mm[2], mm[3]);  *reinterpret_cast<float4*>(g + 3 * H + 4) = make_float4(mm[4], mm[5], mm[6], mm[7]);
+        __syncwarp();
+      } else {
+        GruParams pt = p0;                                   // this step's slices
+        pt.t = t;
+        pt.gi = p0.gi + (long long)t * sq.gi_step;
+        pt.h_prev = p0.h_prev + (long long)t * sq.hp_step;
+        pt.h_out = p0.h_out + (long long)t * sq.ho_step;
+        pt.hout_hi = p0.hout_hi + (long long)t * sq.hpl_step;
+        pt.hout_lo = p0.hout_lo + (long long)t * sq.hpl_step;
+        pt.gates = p0.gates + (long long)t * sq.gates_step;
+        gru_cell_from_tmem(pt, tmem_base, acc_full, (uint32_t)(t & 1), warp, lane, u, m0);   // live steps are a prefix: t-th use of acc_full
+        tc_fence_before();
       }
     }
+    // ---- grid-wide barrier: every CTA (live or not) has finished step t, its h_t rows are visible device-wide
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      atomicAdd(sq.counter, 1u);
+      const unsigned target = (unsigned)(t + 1) * nctas;
+      const long long t0 = clock64();
+      while (*reinterpret_cast<volatile unsigned*>(sq.counter) < target)
+        if (clock64() - t0 > 4000000000LL) { printf("vqa_b200: GRU grid barrier timed out (block %d,%d step %d)\n", blockIdx.x, blockIdx.y, t); __trap(); }
+      __threadfence();
+    }
+    __syncthreads();
+    tc_fence_after();
   }
   tc_fence_before();
   __syncthreads();
@@ -944,5 +1058,46 @@ extern "C" int vqa_gru_step_fused(const void* hprev_hi, const void* hprev_lo, lo
   dim3 grid(H / 32, (B + sb::BM - 1) / sb::BM);
   sb::gru_step_kernel<<<grid, sb::THREADS, sb::G_SMEM, stream>>>(tm, p);
   VQA_LAUNCH_CHECK("gru_step_kernel");
+  return VQA_OK;
+}
+
+extern "C" int vqa_gru_seq_fused(const void* H_hi, const void* H_lo, long long ldh, const void* Whh_hi, const void* Whh_lo, long long ldw,
+                                 const float* gi, long long ldgi, const float* b_hh, float* Hall, const int* len, float* gates,
+                                 const int* tile_gate, unsigned* counter, int T, int B, int H, cudaStream_t stream) {
+  const char* who = "vqa_gru_seq_fused";
+  VQA_CHECK_ARG(H_hi && H_lo && Whh_hi && Whh_lo && gi && b_hh && Hall && len && gates && counter, "%s: null pointer", who);
+  VQA_CHECK_ARG(T > 0 && B > 0 && H > 0 && H % 32 == 0, "%s: H must be a multiple of 32 (H=%d)", who, H);
+  VQA_CHECK_ARG((ldh & 7) == 0 && (ldw & 7) == 0 && ldh >= H && ldw >= H && (ldgi & 3) == 0 && ldgi >= 3 * H, "%s: bad leading dimensions", who);
+  VQA_CHECK_ARG(aligned16(H_hi) && aligned16(H_lo) && aligned16(Whh_hi) && aligned16(Whh_lo) && aligned16(gi) && aligned16(b_hh) && aligned16(Hall) && aligned16(gates),
+                "%s: pointers must be 16-byte aligned", who);
+  dim3 grid(H / 32, (B + sb::BM - 1) / sb::BM);
+  if ((long long)grid.x * grid.y > kNumSMs)
+    return vqa_fail(VQA_ERR_UNSUPPORTED, "%s: %u x %u CTAs cannot be co-resident on %d SMs (the grid barrier needs that): launch the steps one by one", who, grid.x, grid.y, kNumSMs);
+  sb::Maps tm;
+  memset(&tm, 0, sizeof(tm));
+  int rc = sb::make_map(&tm.a_hi, H_hi, ldh, (T + 1) * B, H, 0, sb::BM);      // rows t*B .. : h_{t-1}; rows (t+1)*B .. : h_t
+  if (!rc) rc = sb::make_map(&tm.a_lo, H_lo, ldh, (T + 1) * B, H, 0, sb::BM);
+  if (!rc) rc = sb::make_map(&tm.b_hi, Whh_hi, ldw, 3 * H, H, 0, sb::G_BN);
+  if (!rc) rc = sb::make_map(&tm.b_lo, Whh_lo, ldw, 3 * H, H, 0, sb::G_BN);
+  if (rc) return rc;
+  __nv_bfloat16* hh = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(H_hi));
+  __nv_bfloat16* hl = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(H_lo));
+  sb::GruParams p{gi, ldgi, b_hh, Hall, len, 0, Hall + (long long)B * H, hh + (long long)B * ldh, hl + (long long)B * ldh, ldh, gates, tile_gate,
+                  B, H, (H + sb::BK - 1) / sb::BK};
+  sb::GruSeq sq{T, counter, (long long)B * ldgi, (long long)B * H, (long long)B * H, (long long)B * ldh, (long long)B * 4 * H};
+  static bool attr_set = false;
+  if (!attr_set) {
+    VQA_CUDA(cudaFuncSetAttribute(sb::gru_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sb::G_SMEM));
+    attr_set = true;
+  }
+  VQA_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned), stream));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(sb::THREADS); cfg.dynamicSmemBytes = sb::G_SMEM; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  VQA_CUDA(cudaLaunchKernelEx(&cfg, sb::gru_seq_kernel, tm, p, sq));
+  VQA_LAUNCH_CHECK("gru_seq_kernel");
   return VQA_OK;
 }

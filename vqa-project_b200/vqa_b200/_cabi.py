@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqa_sm100.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 PREC_TF32X3 = 0
 PREC_TF32 = 1
 PREC_TF32X3_HP = 2
@@ -58,6 +58,7 @@ SIGNATURES = {
     "vqa_embed_scatter_add_f32": [_p, _ll, _p, _ll, _p, _p, _ll, _i, _i, _i, _p],
     "vqa_gru_cell_fwd_f32": [_p, _ll, _p, _p, _p, _p, _i, _p, _p, _p, _ll, _p, _i, _i, _p],
     "vqa_gru_step_fused": [_p, _p, _ll, _p, _p, _ll, _p, _ll, _p, _p, _p, _i, _p, _p, _p, _ll, _p, _p, _i, _i, _p],
+    "vqa_gru_seq_fused": [_p, _p, _ll, _p, _p, _ll, _p, _ll, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "vqa_gru_cell_bwd_f32": [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _ll, _p, _i, _i, _p],
     "vqa_gate_bwd_f32": [_p, _p, _p, _p, _p, _ll, _p],
 }

@@ -528,6 +528,28 @@ def gru_step_fused(hprev: "SplitT", Whh_ub: "SplitT", gi_ub: torch.Tensor, b_hh_
           hout.lo.data_ptr(), hout.ld, gates.data_ptr(), _ptr(tile_len), B, H, _stream())
 
 
+_GRID_COUNTERS = {}
+
+
+def gru_seq_supported(B: int, H: int) -> bool:
+    """The whole-sequence kernel synchronises its CTAs with a grid barrier: all of them must fit on the 148 SMs at once."""
+    return H % 32 == 0 and (H // 32) * ((B + 127) // 128) <= 148
+
+
+def gru_seq_fused(Hs: "SplitT", Whh_ub: "SplitT", gi_ub: torch.Tensor, b_hh_ub: torch.Tensor, Hall: torch.Tensor, qlen: torch.Tensor,
+                  gates: torch.Tensor, tile_len: Optional[torch.Tensor], T: int) -> None:
+    """All T GRU steps in one cooperative launch.  Hs rows [0,B) and Hall[0] must hold h_{-1} = 0."""
+    _, B, H = Hall.shape
+    gi_ub, ldgi = _rows_view(_chk(gi_ub, "gru gi"), "gru gi")
+    key = Hall.device.index if Hall.device.index is not None else torch.cuda.current_device()
+    cnt = _GRID_COUNTERS.get(key)
+    if cnt is None:
+        cnt = _GRID_COUNTERS[key] = torch.zeros(4, device=Hall.device, dtype=torch.int32)
+    _call("vqa_gru_seq_fused", Hs.hi.data_ptr(), Hs.lo.data_ptr(), Hs.ld, Whh_ub.hi.data_ptr(), Whh_ub.lo.data_ptr(), Whh_ub.ld,
+          gi_ub.data_ptr(), ldgi, b_hh_ub.data_ptr(), Hall.data_ptr(), qlen.data_ptr(), gates.data_ptr(), _ptr(tile_len), cnt.data_ptr(),
+          int(T), B, H, _stream())
+
+
 def gru_cell_bwd(dh, gates, h_prev, qlen, t, dgi, dgh, dgi_s: SplitT, dgh_s: SplitT, dh_part):
     B, H = dh.shape
     _call("vqa_gru_cell_bwd_f32", dh.data_ptr(), gates.data_ptr(), _ptr(h_prev), qlen.data_ptr(), t, dgi.data_ptr(), dgh.data_ptr(),

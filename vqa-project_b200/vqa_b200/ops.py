@@ -13,6 +13,8 @@ module API (``layers.GraphLearner`` / ``layers.NeighbourhoodGraphConvolution``).
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional, Sequence
 
 import torch
@@ -361,6 +363,11 @@ class ConditionedGraphFn(torch.autograd.Function):
 # time, 16 k-blocks, plus launch / prologue / epilogue): the fusion removes the 6 MB gh round trip and a launch, not that.
 # Multicasting the shared A tile between horizontally adjacent CTAs was tried too (same bytes arrive in every SM): no gain.
 GRU_FUSED = False
+# The same fused step for ALL steps in one cooperative launch (grid barrier between steps, kernels.gru_seq_fused; needs
+# H/32 * ceil(B/128) <= 148 CTAs).  Also correct and tested, also slower inside the captured step: 3.93 vs 3.89 ms at B=512
+# and 1.33 vs 1.22 ms at B=8 - a graph replay has no launch overhead left to save, and inside one kernel the cell of step t
+# cannot overlap the product of step t+1.  "1" enables it, "0" (default) keeps product and cell as two launches per step.
+GRU_FUSED_SEQ = os.environ.get("VQA_GRU_SEQ", "0")
 _UB_PERM = {}
 
 
@@ -394,7 +401,8 @@ class QuestionEncoderFn(torch.autograd.Function):
         # collate_fn sorts a batch by descending length, so the active rows are a shrinking prefix; any order stays correct)
         pad = (-B) % 128
         tile_len = torch.nn.functional.pad(qlen.to(torch.int32), (0, pad)).view(-1, 128).amax(dim=1).to(torch.int32).contiguous()
-        if GRU_FUSED and H % 32 == 0:
+        fused_seq = kn.gru_seq_supported(B, H) and GRU_FUSED_SEQ in ("1", True)
+        if fused_seq or (GRU_FUSED and H % 32 == 0):
             # one kernel per step: product + cell out of TMEM.  Weights / input projections in unit-block order
             # (block u = [r | z | n] of units 32u..32u+31) so that one 128 x 96 accumulator holds all gates of its units
             perm = _unit_block_perm(H, dev)
@@ -403,9 +411,12 @@ class QuestionEncoderFn(torch.autograd.Function):
             b_hh_ub = b_hh.index_select(0, perm)
             Hs = kn.zeros_split((T + 1) * B, H, dev)                           # skipped row tiles stay zero (dW_hh reads all rows)
             Hall[0].zero_()
-            for t in range(T):
-                kn.gru_step_fused(Hs.rows_slice(t * B, (t + 1) * B), Whh_ub, GI[t * B:(t + 1) * B], b_hh_ub, Hall[t], qlen, t, Hall[t + 1],
-                                  Hs.rows_slice((t + 1) * B, (t + 2) * B), gates[t], tile_len)
+            if fused_seq:
+                kn.gru_seq_fused(Hs, Whh_ub, GI, b_hh_ub, Hall, qlen, gates, tile_len, T)
+            else:
+                for t in range(T):
+                    kn.gru_step_fused(Hs.rows_slice(t * B, (t + 1) * B), Whh_ub, GI[t * B:(t + 1) * B], b_hh_ub, Hall[t], qlen, t, Hall[t + 1],
+                                      Hs.rows_slice((t + 1) * B, (t + 2) * B), gates[t], tile_len)
             # every question's state at its OWN last step (rows of skipped tiles are not carried forward)
             out = Hall[qlen.to(torch.int64).clamp(min=0, max=T), torch.arange(B, device=dev)]
         else:
