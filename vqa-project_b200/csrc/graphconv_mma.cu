@@ -20,6 +20,12 @@
 //   B = M_k, K-major (j contiguous), written by the prologue threads in the same swizzled layout, hi and lo planes;
 //   D in TMEM: lane = column c, TMEM column = node i  ->  the epilogue thread of lane c owns one output column for all
 //       nodes: ReLU / dropout / max-pool + gate are per-thread, and a warp writes 32 consecutive columns of a node row.
+//
+// Kernels in this file: edge_coef_kernel (everything that depends only on the selected edges, once per layer and step),
+// agg_persistent_kernel (the streaming aggregate, forward / pooled forward / transposed backward: one warp-specialised CTA
+// per SM), agg_kernel (the same per (image, slab) CTA, used when no precomputed edge coefficients are passed or the shapes do
+// not fit the persistent kernel's shared-memory plan), pool_bwd_data_kernel (backward data path of the max-pooled layer),
+// edge_p_kernel (edge products + edge finish of the backward).
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
