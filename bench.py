@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp32_strict", "bf16"],
                     help="fp32: split-bf16 3-pass tcgen05 GEMMs (fp32-grade, the parity mode); bf16: 1-pass bf16 tensor-core GEMMs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bucket-mb", type=int, default=32, help="gradient all-reduce bucket size (N > 1)")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--cpu-sample", type=int, default=64, help="questions per CPU step (bounded sample of the workload)")
     return ap.parse_args()
@@ -200,7 +201,7 @@ def run_b200(args, workload):
     _dbg("parameters broadcast")
     model.train()
     criterion = torch.nn.MultiLabelSoftMarginLoss()
-    reducer = GradReducer(model.parameters())
+    reducer = GradReducer(model.parameters(), bucket_bytes=args.bucket_mb << 20)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=not args.no_graph)
     torch.manual_seed(1234 + rank)       # rank-offset dropout streams
     step = TrainStep(model, opt, criterion, reducer=reducer, use_graph=not args.no_graph, seed=1234 + rank)

@@ -127,3 +127,46 @@ def test_sink_views_are_adopted_by_autograd_without_a_copy():
         assert lin.weight.grad.data_ptr() == red.flat.data_ptr() + lin.weight._vqa_flat_off * 4
         assert torch.allclose(lin.weight.grad, torch.ones(3, 5).t() @ x)
     red.remove()
+
+
+def test_mark_ready_launches_a_bucket_before_the_node_returns_and_is_not_counted_twice():
+    """Fused operators are single autograd nodes: they report finished parameter gradients themselves (mark_ready), so a bucket's
+    all-reduce can start inside their backward; the post-accumulate hook that fires later for the same parameter must not count again."""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "vqa-project_b200")]
+    from vqa_b200.ddp import GradReducer
+    a = torch.nn.Parameter(torch.randn(300, 10)); b = torch.nn.Parameter(torch.randn(10))
+    red = GradReducer([a, b], bucket_bytes=4096)           # two buckets: {b} is not enough alone -> buckets from the end: {b, a}? sizes decide
+    seen = []
+
+    class F(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, wa, wb):
+            ctx.save_for_backward(x, wa, wb)
+            return x @ wa + wb
+
+        @staticmethod
+        def backward(ctx, g):
+            x, wa, wb = ctx.saved_tensors
+            ga, gb = red.sink(wa), red.sink(wb)
+            torch.mm(x.t(), g, out=ga)
+            red.mark_ready(wa)
+            seen.append(("after a", red.launched, list(red._ready)))
+            torch.sum(g, dim=0, out=gb)
+            red.mark_ready(wb)
+            red.mark_ready(wb)                               # idempotent
+            seen.append(("after b", red.launched, list(red._ready)))
+            return None, ga, gb
+
+    x = torch.randn(7, 300)
+    for _ in range(2):
+        red.zero_grad()
+        launched0 = red.launched
+        seen.clear()
+        F.apply(x, a, b).sum().backward()
+        red.finish()
+        nb = len(red.bucket_size)
+        assert red.launched - launched0 == nb               # every bucket exactly once, hooks did not recount
+        assert seen[-1][1] - launched0 == nb                 # ... and all of them already inside backward
+        assert torch.allclose(a.grad, x.t() @ torch.ones(7, 10)) and torch.allclose(b.grad, torch.full((10,), 7.0))
+        assert a.grad.data_ptr() == red.flat.data_ptr() + a._vqa_flat_off * 4
+    red.remove()

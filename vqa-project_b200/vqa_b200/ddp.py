@@ -47,8 +47,13 @@ class GradReducer:
         end, nbytes, count = total, 0, 0
         for i in reversed(range(len(self.params))):
             p = self.params[i]
+            pbytes = p.numel() * p.element_size()
+            if count and pbytes >= bucket_bytes // 2:     # a large tensor never drags small, later-finishing neighbours into its bucket
+                self.bucket_slices.append(slice(self.params[i + 1]._vqa_flat_off, end))
+                self.bucket_size.append(count)
+                end, nbytes, count = self.params[i + 1]._vqa_flat_off, 0, 0
             self.bucket_of[i] = len(self.bucket_slices)
-            nbytes += p.numel() * p.element_size()
+            nbytes += pbytes
             count += 1
             if nbytes >= bucket_bytes or i == 0:
                 self.bucket_slices.append(slice(p._vqa_flat_off, end))
@@ -60,12 +65,14 @@ class GradReducer:
         for p in self.params:
             p.grad = self._view(p)
         self._ready = [0] * len(self.bucket_size)
+        self._done = [False] * len(self.params)           # counted towards its bucket in this step (by mark_ready or by the hook)
+        self._index = {p.data_ptr(): i for i, p in enumerate(self.params)}
         self._handles = []
         self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
         self.launched = 0
         try:                                              # the fused operators write their parameter gradients through the sink
             from . import ops
-            ops.set_grad_sink(self.sink)
+            ops.set_grad_sink(self.sink, self.mark_ready)
         except Exception:                                 # pragma: no cover - CPU-only use of the reducer (tests)
             pass
 
@@ -80,18 +87,33 @@ class GradReducer:
             return None
         return self._view(p)
 
-    def _make_hook(self, i: int):
+    def _count(self, i: int) -> None:
+        if self._done[i]:
+            return
+        self._done[i] = True
         b = self.bucket_of[i]
+        self._ready[b] += 1
+        if self._ready[b] == self.bucket_size[b]:
+            self._launch(b)
 
+    def mark_ready(self, t: torch.Tensor) -> None:
+        """The operator that wrote this parameter's gradient into its sink view says so the moment its last kernel is enqueued.
+        The fused operators are single autograd nodes: without this, the hooks of ALL their parameters would fire together when
+        the node returns, and the classifier's 36 MB bucket could not start its all-reduce under the rest of backward."""
+        i = self._index.get(t.data_ptr())
+        if i is not None and self.params[i].grad is None:  # (.grad exists: accumulation mode, the hook does the counting)
+            self._count(i)
+
+    def _make_hook(self, i: int):
         def hook(param):
             g = param.grad
             if g is not None and g.data_ptr() != self.flat.data_ptr() + param._vqa_flat_off * self.flat.element_size():
+                if self._done[i]:
+                    raise RuntimeError("GradReducer: a gradient marked ready through the sink was replaced by another tensor")
                 v = self._view(param)                     # produced outside the sink: move it into the flat buffer
                 v.copy_(g)
                 param.grad = v
-            self._ready[b] += 1
-            if self._ready[b] == self.bucket_size[b]:
-                self._launch(b)
+            self._count(i)
         return hook
 
     def _launch(self, b: int) -> None:
@@ -112,6 +134,7 @@ class GradReducer:
                 if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + p._vqa_flat_off * self.flat.element_size():
                     p.grad = self._view(p)
         self._ready = [0] * len(self.bucket_size)
+        self._done = [False] * len(self.params)
 
     def finish(self) -> None:
         """Wait for the in-flight buckets (launching any whose parameters received no gradient) and average."""
@@ -132,7 +155,7 @@ class GradReducer:
         try:
             from . import ops
             if ops._GRAD_SINK == self.sink:
-                ops.set_grad_sink(None)
+                ops.set_grad_sink(None, None)
         except Exception:                                 # pragma: no cover
             pass
 
