@@ -37,6 +37,8 @@ def parse():
                     help="fp32: split-bf16 3-pass tcgen05 GEMMs (fp32-grade, the parity mode); bf16: 1-pass bf16 tensor-core GEMMs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bucket-mb", type=int, default=32, help="gradient all-reduce bucket size (N > 1)")
+    ap.add_argument("--tail", default="fused", choices=["fused", "torch"],
+                    help="criterion + optimiser: our single-launch kernels (vqa_b200.loss / vqa_b200.optim) or torch's modules")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying the captured CUDA graph")
     ap.add_argument("--cpu-sample", type=int, default=64, help="questions per CPU step (bounded sample of the workload)")
     return ap.parse_args()
@@ -108,7 +110,7 @@ def config_dict(w, args, world):
     family = "medical-VQA (ImageCLEF/MIMIC feature shapes)" if w.name.startswith("med") else "VQA2"
     return {"workload": f"{w.name}: {family} conditioned-graph train step, per-GPU batch {w.batch}, K={w.n_obj} boxes x {w.feat_dim}-d, "
                         f"<= {w.max_qlen}-token questions, top-k={w.neighbourhood}, {w.n_kernels} Gaussian kernels, {w.out_dim} answers, dropout {w.dropout}",
-            "global_batch": w.batch * world, "step": "zero_grad+forward+MultiLabelSoftMarginLoss+backward+allreduce+Adam, " + ("eager launches" if args.no_graph else "one CUDA-graph replay per step (vqa_b200.engine.TrainStep)"),
+            "global_batch": w.batch * world, "step": "zero_grad+forward+MultiLabelSoftMarginLoss+backward+allreduce+Adam (" + ("criterion and Adam as single kernels of libvqa_sm100.so" if args.tail == "fused" else "torch criterion and fused Adam") + "), " + ("eager launches" if args.no_graph else "one CUDA-graph replay per step (vqa_b200.engine.TrainStep)"),
             "parallelism": f"dp{world}", "gru": "padded masked recurrence on split-bf16 x3 tcgen05 GEMMs (fp32-grade)", "gemm_precision": {"fp32": "split-bf16 x3 passes (fp32-grade, rel err ~1e-5)", "fp32_strict": "split-bf16 x3 passes + chunk-promoted 3xTF32 graph-learner forward",
                                    "bf16": "bf16 x1 pass (graph-learner forward x3 passes)"}[args.precision],
             "l2_policy": "inputs larger than L2 (image batch 151 MB > 126 MB), 3 rotating batches"}
@@ -200,9 +202,15 @@ def run_b200(args, workload):
     broadcast_parameters(model)
     _dbg("parameters broadcast")
     model.train()
-    criterion = torch.nn.MultiLabelSoftMarginLoss()
     reducer = GradReducer(model.parameters(), bucket_bytes=args.bucket_mb << 20)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=not args.no_graph)
+    if args.tail == "fused":             # criterion and optimiser of run.py:382,392 as our own kernels (csrc/train_step.cu)
+        from vqa_b200.loss import MultiLabelSoftMarginLoss
+        from vqa_b200.optim import FlatAdam
+        criterion = MultiLabelSoftMarginLoss()
+        opt = FlatAdam(reducer, lr=1e-4)
+    else:                                # torch's modules on the same flat gradient buffer (A/B)
+        criterion = torch.nn.MultiLabelSoftMarginLoss()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True, capturable=not args.no_graph)
     torch.manual_seed(1234 + rank)       # rank-offset dropout streams
     step = TrainStep(model, opt, criterion, reducer=reducer, use_graph=not args.no_graph, seed=1234 + rank)
 

@@ -20,7 +20,7 @@ extern "C" {
 
 typedef struct CUstream_st* vqa_stream_t; /* cudaStream_t */
 
-#define VQA_ABI_VERSION 7
+#define VQA_ABI_VERSION 8
 
 /* GEMM precision modes */
 #define VQA_PREC_TF32X3 0 /* 3-pass split TF32 on tcgen05: fp32-grade results (parity mode)      */
@@ -239,6 +239,28 @@ int vqa_gru_cell_bwd_f32(const float* dh, const float* gates, const float* h_pre
  * sparse_graph_model.py:150-151 (autograd of max + relu*mul). */
 int vqa_gate_bwd_f32(const float* dhq, const float* q, const float* pooled, float* dpooled, float* dq, long long n,
                      vqa_stream_t stream);
+
+/* ---- tail of the training step (the reference drivers' criterion and optimiser) ----
+ * nn.MultiLabelSoftMarginLoss(logits, target) of run.py:382,431 (run_imageclef.py / run_mimic.py alike) over n = B*A contiguous
+ * elements: *loss = scale * sum_i -( y_i logsigmoid(x_i) + (1 - y_i) logsigmoid(-x_i) ), scale = 1/(B*A) for reduction='mean'.
+ * partial: >= vqa_mlsm_loss_blocks(n) floats of scratch; counter: one int that is ZERO on entry and is left zero (the last
+ * block adds the partial sums in block order, so the result does not depend on scheduling). */
+int vqa_mlsm_loss_blocks(long long n);
+int vqa_mlsm_loss_fwd_f32(const float* logits, const float* target, long long n, float scale, float* partial, int* counter,
+                          float* loss, vqa_stream_t stream);
+/* dlogits_i = (sigmoid(x_i) - y_i) * scale * (*grad_out)   (grad_out: device scalar, NULL == 1). */
+int vqa_mlsm_loss_bwd_f32(const float* logits, const float* target, const float* grad_out, float* dlogits, long long n,
+                          float scale, vqa_stream_t stream);
+
+/* torch.optim.Adam (run.py:392,435; amsgrad=False, maximize=False) for every parameter tensor in ONE launch.
+ * chunks: device table of nchunks x {int64 address of the parameter elements, int64 element offset into grad / exp_avg /
+ * exp_avg_sq, int64 count}; grad is the flat gradient buffer (vqa_b200.ddp.GradReducer), exp_avg / exp_avg_sq have its layout.
+ * g = grad * grad_scale (+ weight_decay * p); grad_scale = 1/world folds the data-parallel average into this pass.
+ * lr: device float (so a CUDA-graph replay sees a scheduler's new rate).  state: two device ints, {steps taken, 0}; the
+ * launch applies step state[0]+1 (bias corrections in double) and its last block stores the new count. */
+int vqa_adam_flat_f32(const long long* chunks, int nchunks, const float* grad, float* exp_avg, float* exp_avg_sq,
+                      const float* lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, int* state,
+                      vqa_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -78,3 +78,24 @@ def test_drop_in_state_dict_contract():
     model.load_state_dict({k: torch.from_numpy(g["param." + k]) for k in ref_keys})   # reference checkpoints load
     lst = model.graph_convolution_1.conv_weight_list()
     assert all(x.data_ptr() == lst[0].data_ptr() + i * x.numel() * 4 for i, x in enumerate(lst))
+
+
+def test_conv_weights_are_rejoined_by_module_conversions():
+    """``.to()/.double()`` split the per-kernel weights into storages of their own; the layer re-joins them inside ``_apply`` so the
+    addresses a gradient reducer / optimiser records right after ``model.cuda()`` stay valid."""
+    import torch
+    import layers
+    gc = layers.NeighbourhoodGraphConvolution(12, 8, 4, 2)
+
+    def consecutive(m):
+        ws = [lin.weight for lin in m.conv_weights]
+        step = ws[0].numel() * ws[0].element_size()
+        return all(w.data_ptr() == ws[0].data_ptr() + i * step for i, w in enumerate(ws))
+
+    assert consecutive(gc)
+    before = [w.detach().clone() for w in (lin.weight for lin in gc.conv_weights)]
+    gc = gc.double()
+    assert consecutive(gc) and gc.conv_weights[0].weight.dtype == torch.float64
+    gc = torch.nn.Sequential(gc).float()[0]               # through a parent module's recursion
+    assert consecutive(gc)
+    assert all(torch.equal(a, lin.weight) for a, lin in zip(before, gc.conv_weights))

@@ -170,3 +170,23 @@ def test_mark_ready_launches_a_bucket_before_the_node_returns_and_is_not_counted
         assert torch.allclose(a.grad, x.t() @ torch.ones(7, 10)) and torch.allclose(b.grad, torch.full((10,), 7.0))
         assert a.grad.data_ptr() == red.flat.data_ptr() + a._vqa_flat_off * 4
     red.remove()
+
+
+def test_reducer_average_flag_leaves_the_sum_for_an_optimiser_that_scales_itself():
+    """optim.FlatAdam clears ``average`` and folds 1/world into its own pass; with one process finish() never scales."""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "vqa-project_b200")]
+    from vqa_b200.ddp import GradReducer
+    net = torch.nn.Linear(4, 2)
+    red = GradReducer(net.parameters())
+    assert red.average is True
+    red.world, red.average = 2, False                     # pretend: the buffer holds a two-rank SUM
+    red._launch = lambda b: None                          # no process group in this test
+    red.zero_grad()
+    net(torch.ones(1, 4)).sum().backward()
+    before = red.flat.clone()
+    red.finish()
+    assert torch.equal(red.flat, before)
+    red.average = True
+    red.finish()
+    assert torch.allclose(red.flat, before * 0.5)
+    red.remove()

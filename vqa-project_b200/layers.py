@@ -105,6 +105,13 @@ class NeighbourhoodGraphConvolution(nn.Module):
             for i, w in enumerate(ws):
                 w.data = flat[i * d:(i + 1) * d]
 
+    def _apply(self, fn, *args, **kwargs):
+        """``.to()/.cuda()/.float()`` give every Parameter storage of its own: re-join them at once, so their addresses are final
+        before a gradient reducer / optimiser records them."""
+        out = super()._apply(fn, *args, **kwargs)
+        self.flatten_parameters()
+        return out
+
     def conv_weight_list(self):
         self.flatten_parameters()
         return [lin.weight for lin in self.conv_weights]

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqa_sm100.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 PREC_TF32X3 = 0
 PREC_TF32 = 1
 PREC_TF32X3_HP = 2
@@ -61,6 +61,10 @@ SIGNATURES = {
     "vqa_gru_seq_fused": [_p, _p, _ll, _p, _p, _ll, _p, _ll, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "vqa_gru_cell_bwd_f32": [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _ll, _p, _i, _i, _p],
     "vqa_gate_bwd_f32": [_p, _p, _p, _p, _p, _ll, _p],
+    "vqa_mlsm_loss_blocks": [_ll],
+    "vqa_mlsm_loss_fwd_f32": [_p, _p, _ll, _f, _p, _p, _p, _p],
+    "vqa_mlsm_loss_bwd_f32": [_p, _p, _p, _p, _ll, _f, _p],
+    "vqa_adam_flat_f32": [_p, _i, _p, _p, _p, _p, _f, _f, _f, _f, _f, _p, _p],
 }
 EXPORTS = ["vqa_last_error", "vqa_abi_version"] + list(SIGNATURES)
 

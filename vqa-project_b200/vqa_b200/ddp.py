@@ -70,6 +70,7 @@ class GradReducer:
         self._handles = []
         self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
         self.launched = 0
+        self.average = True                               # finish() scales by 1/world; optim.FlatAdam folds the factor into its pass instead
         try:                                              # the fused operators write their parameter gradients through the sink
             from . import ops
             ops.set_grad_sink(self.sink, self.mark_ready)
@@ -137,7 +138,8 @@ class GradReducer:
         self._done = [False] * len(self.params)
 
     def finish(self) -> None:
-        """Wait for the in-flight buckets (launching any whose parameters received no gradient) and average."""
+        """Wait for the in-flight buckets (launching any whose parameters received no gradient) and average (unless
+        ``average`` was cleared by an optimiser that applies 1/world itself: the buffer then holds the SUM over ranks)."""
         for b in range(len(self.bucket_size)):
             if self._ready[b] != self.bucket_size[b]:
                 self._ready[b] = self.bucket_size[b]
@@ -145,7 +147,7 @@ class GradReducer:
         for h in self._handles:
             h.wait()
         self._handles.clear()
-        if self.world > 1:
+        if self.world > 1 and self.average:
             self.flat.mul_(1.0 / self.world)
 
     def remove(self) -> None:

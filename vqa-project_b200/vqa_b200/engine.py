@@ -135,6 +135,8 @@ class TrainStep:
         if not self.filled[s]:
             self._fill(s, question, image, K, _as_len_tensor(qlen, self.device), target, self.copy_stream)
         torch.cuda.current_stream().wait_event(self.ready[s])
+        if hasattr(self.opt, "sync_lr"):
+            self.opt.sync_lr()                                        # a scheduler's new rate reaches the captured Adam launch
         if self.use_graph:
             self.graphs[s].replay()
             loss = self.losses[s]

@@ -554,3 +554,54 @@ def gru_cell_bwd(dh, gates, h_prev, qlen, t, dgi, dgh, dgi_s: SplitT, dgh_s: Spl
     B, H = dh.shape
     _call("vqa_gru_cell_bwd_f32", dh.data_ptr(), gates.data_ptr(), _ptr(h_prev), qlen.data_ptr(), t, dgi.data_ptr(), dgh.data_ptr(),
           dgi_s.hi.data_ptr(), _ptr(dgi_s.lo), dgh_s.hi.data_ptr(), _ptr(dgh_s.lo), dgi_s.ld, dh_part.data_ptr(), B, H, _stream())
+
+
+# ------------------------------------------------------------------------------------------- criterion / optimiser (train_step.cu)
+_LOSS_SCRATCH = {}
+
+
+def _loss_scratch(device: torch.device, blocks: int):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    ent = _LOSS_SCRATCH.get(key)
+    if ent is None or ent[0].numel() < blocks:
+        ent = _LOSS_SCRATCH[key] = (torch.empty(max(blocks, 1024), device=device, dtype=torch.float32),
+                                    torch.zeros(1, device=device, dtype=torch.int32))
+    return ent
+
+
+def mlsm_loss_fwd(logits: torch.Tensor, target: torch.Tensor, scale: float) -> torch.Tensor:
+    """0-d loss = scale * sum -(y logsigmoid(x) + (1-y) logsigmoid(-x)) over contiguous (B, A) tensors, one launch."""
+    _chk(logits, "mlsm_loss logits"); _chk(target, "mlsm_loss target")
+    if logits.shape != target.shape or not logits.is_contiguous() or not target.is_contiguous():
+        raise RuntimeError(f"mlsm_loss: logits {tuple(logits.shape)} and target {tuple(target.shape)} must be contiguous and of one shape")
+    n = logits.numel()
+    partial, counter = _loss_scratch(logits.device, _cabi.load().vqa_mlsm_loss_blocks(n))
+    loss = torch.empty((), device=logits.device, dtype=torch.float32)
+    _call("vqa_mlsm_loss_fwd_f32", logits.data_ptr(), target.data_ptr(), n, float(scale), partial.data_ptr(), counter.data_ptr(),
+          loss.data_ptr(), _stream())
+    return loss
+
+
+def mlsm_loss_bwd(logits: torch.Tensor, target: torch.Tensor, grad_out: Optional[torch.Tensor], scale: float) -> torch.Tensor:
+    """dlogits = (sigmoid(x) - y) * scale * grad_out (a device scalar; None == 1), one launch."""
+    if grad_out is not None:
+        _chk(grad_out, "mlsm_loss grad_out")
+        if grad_out.numel() != 1:
+            raise RuntimeError("mlsm_loss: grad_out must be a scalar")
+    d = torch.empty_like(logits)
+    _call("vqa_mlsm_loss_bwd_f32", logits.data_ptr(), target.data_ptr(), _ptr(grad_out), d.data_ptr(), logits.numel(), float(scale),
+          _stream())
+    return d
+
+
+def adam_flat(chunks: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, lr: torch.Tensor,
+              beta1: float, beta2: float, eps: float, weight_decay: float, grad_scale: float, state: torch.Tensor) -> None:
+    """One Adam step of every parameter named by the (nchunks, 3) int64 chunk table, one launch (see include/vqa_b200.h)."""
+    _chk(chunks, "adam chunks", torch.int64); _chk(grad, "adam grad"); _chk(exp_avg, "adam exp_avg"); _chk(exp_avg_sq, "adam exp_avg_sq")
+    _chk(lr, "adam lr"); _chk(state, "adam state", torch.int32)
+    if chunks.dim() != 2 or chunks.shape[1] != 3 or not chunks.is_contiguous():
+        raise RuntimeError("adam_flat: chunk table must be a contiguous (nchunks, 3) int64 tensor")
+    if exp_avg.numel() != grad.numel() or exp_avg_sq.numel() != grad.numel() or state.numel() < 2:
+        raise RuntimeError("adam_flat: exp_avg / exp_avg_sq must have the flat gradient buffer's size, state two ints")
+    _call("vqa_adam_flat_f32", chunks.data_ptr(), chunks.shape[0], grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+          lr.data_ptr(), float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale), state.data_ptr(), _stream())
