@@ -20,7 +20,7 @@ extern "C" {
 
 typedef struct CUstream_st* vqa_stream_t; /* cudaStream_t */
 
-#define VQA_ABI_VERSION 8
+#define VQA_ABI_VERSION 9
 
 /* GEMM precision modes */
 #define VQA_PREC_TF32X3 0 /* 3-pass split TF32 on tcgen05: fp32-grade results (parity mode)      */
@@ -261,6 +261,19 @@ int vqa_mlsm_loss_bwd_f32(const float* logits, const float* target, const float*
 int vqa_adam_flat_f32(const long long* chunks, int nchunks, const float* grad, float* exp_avg, float* exp_avg_sq,
                       const float* lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, int* state,
                       vqa_stream_t stream);
+
+/* ---- batch assembly on the device (input side of the path; replaces the per-question host work of torch_dataset.py:105-164
+ * and most of the H2D copy of utils.py:22-31).  The feature table lives in HBM (or in pinned host memory for the rows of one
+ * batch): features (n_rows, K, D) fp32 or bf16 (features_bf16 != 0), boxes (n_rows, K, 4) fp32 xyxy already divided by the
+ * image size (torch_dataset.py:148-154).  image[b] = [ features[rows[b]] | boxes[rows[b]] ] as (B, K, D+4) fp32, the layout
+ * Model.forward takes.  A row index outside [0, n_rows) writes zeros and sets *err_flag = 1 (never reads outside the table). */
+int vqa_gather_image_f32(const void* features, int features_bf16, const float* boxes, const long long* rows, long long n_rows,
+                         float* image, int B, int K, int D, int* err_flag, vqa_stream_t stream);
+/* Dense (B, A) rows from CSR triplets: out[b, ids[e]] = vals[e] for e in [ptr[b], ptr[b+1]), zero elsewhere; entries are
+ * applied in order (a repeated id keeps the last value, as the assignment loops of torch_dataset.py:117-130 do).  An id
+ * outside [0, A) is skipped and sets *err_flag = 2. */
+int vqa_scatter_targets_f32(const long long* ptr, const int* ids, const float* vals, float* out, int B, int A, int* err_flag,
+                            vqa_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,118 @@
+"""Host side of the shard pipeline (vqa_b200/shards.py) against a restatement of the reference's dataset code (shard_fixture.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import shard_fixture as SF  # noqa: E402
+from vqa_b200 import shards  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ds():
+    return SF.make_dataset()
+
+
+def _convert(ds, path, dtype="f32", q_width=100):
+    return shards.from_reference_records(ds["records"], ds["q_wtoi"], ds["a_wtoi"], ds["i_feat"], ds["bbox"], ds["sizes"], str(path),
+                                         n_answers=ds["n_answers"], n_obj=ds["K"], q_width=q_width, feature_dtype=dtype)
+
+
+def test_fp32_shards_reproduce_every_reference_item_bit_for_bit(ds, tmp_path):
+    meta = _convert(ds, tmp_path)
+    s = shards.ShardSet(str(tmp_path))
+    assert meta["n_questions"] == len(ds["records"]) == len(s) and meta["feat_dim"] == ds["D"] + 4
+    assert s.n_images == len({r["image_id"] for r in ds["records"]})
+    for n in range(len(s)):
+        ref, got = SF.reference_item(ds, n), s.dense_item(n)
+        for j, (r, g) in enumerate(zip(ref, got)):
+            if isinstance(r, np.ndarray):
+                assert r.shape == g.shape and np.array_equal(r, g), (n, j)
+            else:
+                assert r == g, (n, j)
+        assert got[4].dtype == np.float32 and got[0].dtype == np.int64
+
+
+def test_bf16_shards_round_features_only(ds, tmp_path):
+    _convert(ds, tmp_path, "bf16")
+    s = shards.ShardSet(str(tmp_path))
+    assert s.bf16 and s.features.dtype == np.uint16
+    for n in range(len(s)):
+        ref, got = SF.reference_item(ds, n), s.dense_item(n)
+        D = ds["D"]
+        want = torch.from_numpy(ref[4][:, :D].copy()).to(torch.bfloat16).float().numpy()
+        assert np.array_equal(got[4][:, :D], want)
+        assert np.array_equal(got[4][:, D:], ref[4][:, D:])            # boxes stay fp32
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+
+
+def test_csr_rows_in_batch_order(ds, tmp_path):
+    _convert(ds, tmp_path)
+    s = shards.ShardSet(str(tmp_path))
+    idx = np.array([5, 0, 22, 7, 7 + 1], dtype=np.int64)
+    for which, col in (("ans", 1), ("vote", 2)):
+        ptr, ids, val = s.csr_rows(which, idx)
+        assert ptr.dtype == np.int64 and ids.dtype == np.int32 and val.dtype == np.float32 and ptr[0] == 0
+        for b, n in enumerate(idx):
+            dense = np.zeros(s.n_answers, dtype=np.float32)
+            for e in range(ptr[b], ptr[b + 1]):
+                dense[ids[e]] = val[e]
+            assert np.array_equal(dense, SF.reference_item(ds, int(n))[col])
+
+
+def test_epoch_batches_partition_the_epoch_across_ranks():
+    n, bs, world = 103, 8, 3
+    seen = []
+    for rank in range(world):
+        bl = shards.epoch_batches(n, bs, epoch=2, seed=5, rank=rank, world=world)
+        assert all(len(b) == len(bl[0]) for b in bl[:-1]) and len(bl[0]) == bs
+        seen.append(bl)
+    assert len({len(b) for b in seen}) == 1                            # same number of steps on every rank (no hung collective)
+    for step in zip(*seen):
+        assert len({len(b) for b in step}) == 1                        # and the same batch size per step
+    flat = np.concatenate([np.concatenate(b) for b in seen])
+    assert len(np.unique(flat)) == len(flat) and len(flat) >= n - (n % (bs * world)) and len(flat) <= n
+    again = shards.epoch_batches(n, bs, epoch=2, seed=5, rank=1, world=world)
+    assert all(np.array_equal(a, b) for a, b in zip(again, seen[1]))
+    other = shards.epoch_batches(n, bs, epoch=3, seed=5, rank=1, world=world)
+    assert not all(np.array_equal(a, b) for a, b in zip(other, seen[1]))
+    full = shards.epoch_batches(n, bs, shuffle=False, drop_last=True)
+    assert len(full) == n // bs and np.array_equal(np.concatenate(full), np.arange(n // bs * bs))
+    assert sum(len(b) for b in shards.epoch_batches(n, bs, shuffle=False)) == n
+
+
+def test_in_batch_order_modes(ds):
+    qlen = np.array([len(r["question_toked"]) for r in ds["records"]], dtype=np.int32)
+    idx = np.array([3, 17, 9, 0, 21, 12], dtype=np.int64)
+    ref = SF.reference_collate([SF.reference_item(ds, int(n)) for n in idx])
+    assert np.array_equal(shards.order_batch(idx, qlen, "reference"), ref[7].numpy())      # collate_fn sorts by the LAST element: idx
+    byq = shards.order_batch(idx, qlen, "qlen")
+    assert sorted(byq.tolist()) == sorted(idx.tolist()) and np.all(np.diff(qlen[byq]) <= 0)
+    for a, b in zip(byq[:-1], byq[1:]):                                # stable: ties keep the sampling order
+        if qlen[a] == qlen[b]:
+            assert list(idx).index(a) < list(idx).index(b)
+    assert np.array_equal(shards.order_batch(idx, qlen, "none"), idx)
+    with pytest.raises(ValueError):
+        shards.order_batch(idx, qlen, "random")
+
+
+def test_writer_rejects_bad_input(tmp_path):
+    ok = dict(features=np.zeros((2, 3, 8), np.float32), boxes=np.zeros((2, 3, 4), np.float32), questions=np.zeros((1, 10), np.int32),
+              qlen=[1], image_row=[0], qid=[1], answers=[[(1, 0.5)]], votes=[[(1, 3.0)]], n_answers=4)
+    shards.write_shards(str(tmp_path / "ok"), **ok)
+    bad = dict(ok, features=np.full((2, 3, 8), np.nan, np.float32))
+    with pytest.raises(ValueError, match="non-finite"):
+        shards.write_shards(str(tmp_path / "a"), **bad)
+    with pytest.raises(ValueError, match="image_row"):
+        shards.write_shards(str(tmp_path / "b"), **dict(ok, image_row=[2]))
+    with pytest.raises(ValueError, match="answer id"):
+        shards.write_shards(str(tmp_path / "c"), **dict(ok, answers=[[(4, 1.0)]]))
+    with pytest.raises(ValueError, match="multiple of 8"):
+        shards.write_shards(str(tmp_path / "d"), **dict(ok, features=np.zeros((2, 3, 12), np.float32)))
+    with pytest.raises(ValueError, match="feature_dtype"):
+        shards.write_shards(str(tmp_path / "e"), **dict(ok, feature_dtype="fp16"))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        shards.ShardLoader(str(tmp_path / "ok"), 1, device="cpu")

@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvqa_sm100.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 PREC_TF32X3 = 0
 PREC_TF32 = 1
 PREC_TF32X3_HP = 2
@@ -65,6 +65,8 @@ SIGNATURES = {
     "vqa_mlsm_loss_fwd_f32": [_p, _p, _ll, _f, _p, _p, _p, _p],
     "vqa_mlsm_loss_bwd_f32": [_p, _p, _p, _p, _ll, _f, _p],
     "vqa_adam_flat_f32": [_p, _i, _p, _p, _p, _p, _f, _f, _f, _f, _f, _p, _p],
+    "vqa_gather_image_f32": [_p, _i, _p, _p, _ll, _p, _i, _i, _i, _p, _p],
+    "vqa_scatter_targets_f32": [_p, _p, _p, _p, _i, _i, _p, _p],
 }
 EXPORTS = ["vqa_last_error", "vqa_abi_version"] + list(SIGNATURES)
 

@@ -605,3 +605,32 @@ def adam_flat(chunks: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, e
         raise RuntimeError("adam_flat: exp_avg / exp_avg_sq must have the flat gradient buffer's size, state two ints")
     _call("vqa_adam_flat_f32", chunks.data_ptr(), chunks.shape[0], grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
           lr.data_ptr(), float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale), state.data_ptr(), _stream())
+
+
+# ------------------------------------------------------------------------------------------- batch assembly (loader.cu)
+def gather_image(features: torch.Tensor, boxes: torch.Tensor, rows: torch.Tensor, err: torch.Tensor) -> torch.Tensor:
+    """image (B, K, D+4) fp32 = [features[rows] | boxes[rows]] from a (n, K, D) fp32/bf16 table and (n, K, 4) fp32 boxes."""
+    if features.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError(f"gather_image: features must be fp32 or bf16, got {features.dtype}")
+    _chk(features, "gather_image features", features.dtype); _chk(boxes, "gather_image boxes"); _chk(rows, "gather_image rows", torch.int64)
+    _chk(err, "gather_image err", torch.int32)
+    if features.dim() != 3 or boxes.shape != (features.shape[0], features.shape[1], 4) or not features.is_contiguous() or not boxes.is_contiguous():
+        raise RuntimeError(f"gather_image: need contiguous features (n,K,D) and boxes (n,K,4), got {tuple(features.shape)} / {tuple(boxes.shape)}")
+    n, K, D = features.shape
+    rows = rows.contiguous().reshape(-1)
+    B = rows.numel()
+    out = torch.empty((B, K, D + 4), device=features.device, dtype=torch.float32)
+    _call("vqa_gather_image_f32", features.data_ptr(), int(features.dtype == torch.bfloat16), boxes.data_ptr(), rows.data_ptr(), n,
+          out.data_ptr(), B, K, D, err.data_ptr(), _stream())
+    return out
+
+
+def scatter_targets(ptr: torch.Tensor, ids: torch.Tensor, vals: torch.Tensor, B: int, A: int, err: torch.Tensor) -> torch.Tensor:
+    """Dense (B, A) fp32 rows from CSR triplets (ptr int64 (B+1,), ids int32, vals fp32)."""
+    _chk(ptr, "scatter_targets ptr", torch.int64); _chk(ids, "scatter_targets ids", torch.int32); _chk(vals, "scatter_targets vals")
+    _chk(err, "scatter_targets err", torch.int32)
+    if ptr.numel() != B + 1 or ids.numel() != vals.numel():
+        raise RuntimeError("scatter_targets: ptr must have B+1 entries and ids / vals one entry per triplet")
+    out = torch.empty((B, A), device=ptr.device, dtype=torch.float32)
+    _call("vqa_scatter_targets_f32", ptr.data_ptr(), ids.data_ptr(), vals.data_ptr(), out.data_ptr(), B, A, err.data_ptr(), _stream())
+    return out
