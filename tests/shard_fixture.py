@@ -1,8 +1,13 @@
-"""A miniature dataset in the shape ``VQA_Dataset.__init__`` loads it (torch_dataset.py:35-75) plus a restatement of
-``__getitem__`` / ``collate_fn`` (:27-31, :105-164) used ONLY as the checker of vqa_b200.shards."""
+"""A miniature dataset in the shape ``VQA_Dataset.__init__`` loads it (torch_dataset.py:35-75): question records, word/answer
+dictionaries, per-image features, boxes and sizes keyed by ``str(image_id)``.  Deterministic in its arguments; shared by the shard
+tests and by ``tests/golden/make_dataset_golden.py``.  The checker that turns it into items/batches is ``oracle/dataset_oracle.py``."""
+import os
+import sys
+
 import numpy as np
-import torch
-from torch.utils.data import dataloader
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle.dataset_oracle import reference_collate, reference_item  # noqa: E402,F401  (re-exported for the tests)
 
 
 def make_dataset(n_images=7, n_questions=23, K=6, D=16, n_answers=11, seed=3):
@@ -31,49 +36,3 @@ def make_dataset(n_images=7, n_questions=23, K=6, D=16, n_answers=11, seed=3):
                             answers_w_scores=[(p, round(float(rng.rand()), 3)) for p in picks],
                             answers=[(p, float(rng.randint(1, 11))) for p in picks]))
     return dict(records=records, q_wtoi=q_wtoi, a_wtoi=a_wtoi, i_feat=i_feat, bbox=bbox, sizes=sizes, n_answers=n_answers, K=K, D=D)
-
-
-def reference_item(ds, idx, q_width=100):
-    """torch_dataset.py:105-164, statement by statement (k = number of boxes of the fixture)."""
-    rec = ds["records"][idx]
-    qlen = len(rec["question_toked"])
-    q = [0] * q_width
-    for i, w in enumerate(rec["question_toked"]):
-        try:
-            q[i] = ds["q_wtoi"][w]
-        except KeyError:
-            q[i] = 0
-    a = np.zeros(ds["n_answers"], dtype=np.float32)
-    for w, c in rec["answers_w_scores"]:
-        try:
-            a[ds["a_wtoi"][w]] = c
-        except KeyError:
-            continue
-    n_votes = np.zeros(ds["n_answers"], dtype=np.float32)
-    for w, c in rec["answers"]:
-        try:
-            n_votes[ds["a_wtoi"][w]] = c
-        except KeyError:
-            continue
-    qid = rec["question_id"]
-    iid = rec["image_id"]
-    img = ds["i_feat"][str(iid)]
-    bboxes = np.array(ds["bbox"][str(iid)])                             # (zarr reads return fresh arrays)
-    imsize = ds["sizes"][str(iid)]
-    if np.logical_not(np.isfinite(img)).sum() > 0:
-        raise ValueError
-    k = ds["K"]
-    for i in range(k):
-        bb = bboxes[i]
-        bb[0] /= imsize[0]
-        bb[1] /= imsize[1]
-        bb[2] /= imsize[0]
-        bb[3] /= imsize[1]
-        bboxes[i] = bb
-    return (np.asarray(q), np.asarray(a).reshape(-1), np.asarray(n_votes).reshape(-1), np.asarray(qid).reshape(-1),
-            np.concatenate([img, bboxes], axis=1), np.asarray(k).reshape(1), qlen, idx)
-
-
-def reference_collate(batch):
-    batch.sort(key=lambda x: x[-1], reverse=True)                       # torch_dataset.py:27-31
-    return dataloader.default_collate(batch)

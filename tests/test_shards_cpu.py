@@ -116,3 +116,47 @@ def test_writer_rejects_bad_input(tmp_path):
         shards.write_shards(str(tmp_path / "e"), **dict(ok, feature_dtype="fp16"))
     with pytest.raises(RuntimeError, match="CUDA"):
         shards.ShardLoader(str(tmp_path / "ok"), 1, device="cpu")
+
+
+# ---------------------------------------------------------------------------------------------- pinned to the reference's own code
+GOLDEN_ARGS = dict(n_images=5, n_questions=19, K=36, D=16, n_answers=11, seed=3)      # as tests/golden/make_dataset_golden.py
+NAMES = ("q", "a", "n_votes", "qid", "i", "k", "qlen", "idx")
+
+
+def _golden():
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dataset_small.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def test_dataset_oracle_matches_reference_golden():
+    """oracle/dataset_oracle.py against what the unmodified torch_dataset.py returned for the same miniature dataset."""
+    g, ds = _golden(), SF.make_dataset(**GOLDEN_ARGS)
+    assert g["item.i"].dtype == np.float32 and g["item.q"].dtype == np.int64 and g["item.a"].dtype == np.float32
+    for n in range(len(ds["records"])):
+        it = SF.reference_item(ds, n)
+        for j, name in enumerate(NAMES):
+            want = g["item." + name][n]
+            got = np.asarray(it[j])
+            assert got.shape == want.shape and np.array_equal(got, want), (n, name)
+            assert got.dtype == want.dtype or name in ("qlen", "idx"), (n, name, got.dtype, want.dtype)
+    for b, idx in enumerate(([3, 17, 9, 0, 12], [18, 1, 2, 7])):
+        col = SF.reference_collate([SF.reference_item(ds, n) for n in idx])
+        for j, name in enumerate(NAMES):
+            want = g[f"batch{b}.{name}"]
+            assert tuple(col[j].shape) == want.shape and np.array_equal(col[j].numpy(), want), (b, name)
+            assert col[j].numpy().dtype == want.dtype, (b, name)
+        assert list(g[f"batch{b}.idx"]) == sorted(idx, reverse=True)     # the reference sorts by index, not by length
+
+
+def test_shards_reproduce_the_reference_golden_items(tmp_path):
+    """The converter + shard reader against the reference's own __getitem__ outputs (K = 36, the reference's hard-coded box count)."""
+    g, ds = _golden(), SF.make_dataset(**GOLDEN_ARGS)
+    _convert(ds, tmp_path)
+    s = shards.ShardSet(str(tmp_path))
+    for n in range(len(s)):
+        it = s.dense_item(n)
+        for j, name in enumerate(NAMES):
+            assert np.array_equal(np.asarray(it[j]), g["item." + name][n]), (n, name)
+    for b in range(2):
+        idx = g[f"batch{b}.idx"]
+        assert np.array_equal(shards.order_batch(np.array(sorted(idx.tolist())), s.qlen, "reference"), idx)

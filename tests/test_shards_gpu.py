@@ -139,3 +139,20 @@ def test_loader_batch_drives_the_model_like_the_reference_loop(tmp_path):
         perm = torch.tensor([inv[int(n)] for n in batch[7]], device=DEV)
         assert torch.allclose(logits, ref_logits[perm], rtol=1e-5, atol=1e-6)
         assert U.total_vqa_score(logits, n_votes) == pytest.approx(U.total_vqa_score(ref_logits, rv), abs=1e-5)
+
+
+def test_loader_reproduces_the_reference_golden_batches(tmp_path):
+    """Device-assembled batches against tests/golden/dataset_small.npz - the outputs of the unmodified torch_dataset.py
+    (__getitem__ + collate_fn) on the same miniature dataset (tests/golden/make_dataset_golden.py)."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dataset_small.npz"))
+    ds = SF.make_dataset(n_images=5, n_questions=19, K=36, D=16, n_answers=11, seed=3)
+    _convert(ds, tmp_path)
+    ld = shards.ShardLoader(str(tmp_path), 5, DEV, order="reference")
+    names = ("q", "a", "n_votes", "qid", "i", "k", "qlen", "idx")
+    for b in range(2):
+        idx = shards.order_batch(np.sort(z[f"batch{b}.idx"]), ld.set.qlen, "reference")
+        batch = ld.assemble(idx)
+        for j, name in enumerate(names):
+            want = torch.from_numpy(z[f"batch{b}.{name}"])
+            assert batch[j].dtype == want.dtype and batch[j].shape == want.shape and torch.equal(batch[j].cpu(), want), (b, name)
+    ld.check_errors()
