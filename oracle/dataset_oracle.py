@@ -59,6 +59,49 @@ def reference_item(ds, idx, q_width=100):
             np.concatenate([img, bboxes], axis=1), np.asarray(k).reshape(1), qlen, idx)
 
 
+def reference_item_medical(ds, idx, q_width=100, variant="imageclef"):
+    """``ImageclefDataset.__getitem__`` (``torch_dataset.py:236-291``) and ``MimicDataset.__getitem__`` (``:356-417``): as above
+    except that every box of the image is used and the last element is the image key; ImageCLEF keys images by
+    ``image_id + '.jpg'`` (``:268``) and iterates ``answers`` as a dict (``:258``), MIMIC does neither (``:375,385``)."""
+    clef = variant == "imageclef"
+    rec = ds["records"][idx]
+    qlen = len(rec["question_toked"])
+    q = [0] * q_width
+    for i, w in enumerate(rec["question_toked"]):
+        try:
+            q[i] = ds["q_wtoi"][w]
+        except KeyError:
+            q[i] = 0
+    a = np.zeros(ds["n_answers"], dtype=np.float32)
+    for w, c in rec["answers_w_scores"]:
+        try:
+            a[ds["a_wtoi"][w]] = c
+        except KeyError:
+            continue
+    n_votes = np.zeros(ds["n_answers"], dtype=np.float32)
+    for w, c in (rec["answers"].items() if clef else rec["answers"]):   # :258 a dict (ImageCLEF) / :375 pairs (MIMIC)
+        try:
+            n_votes[ds["a_wtoi"][w]] = c
+        except KeyError:
+            continue
+    qid = rec["question_id"]
+    iid = rec["image_id"] + ".jpg" if clef else rec["image_id"]         # :268 / :385
+    img = ds["i_feat"][str(iid)]
+    bboxes = np.array(ds["bbox"][str(iid)])
+    imsize = ds["sizes"][str(iid)]
+    if np.logical_not(np.isfinite(img)).sum() > 0:
+        raise ValueError
+    for i in range(bboxes.shape[0]):                                    # :279-285 every box
+        bb = bboxes[i]
+        bb[0] /= imsize[0]
+        bb[1] /= imsize[1]
+        bb[2] /= imsize[0]
+        bb[3] /= imsize[1]
+        bboxes[i] = bb
+    return (np.asarray(q), np.asarray(a).reshape(-1), np.asarray(n_votes).reshape(-1), np.asarray(qid).reshape(-1),
+            np.concatenate([img, bboxes], axis=1), np.asarray(bboxes.shape[0]).reshape(1), qlen, iid)
+
+
 def reference_collate(batch):
     """``torch_dataset.py:27-31``: sorts by the LAST tuple element - the dataset index (``:164``), not the question length its comment
     speaks of - in descending order, then ``default_collate``."""

@@ -9,7 +9,8 @@ empty stand-in module satisfies the import.  A ``VQA_Dataset`` is created withou
 files) and given the attributes ``__getitem__`` reads - ``vqa``, ``q_wtoi``, ``a_wtoi``, ``n_answers``, ``i_feat``, ``bbox`` (dicts
 of arrays standing in for the zarr groups) and ``sizes`` (a pandas DataFrame with one column per image id, as ``pd.read_csv`` of
 the size table gives) - from the miniature dataset of ``tests/shard_fixture.py`` with K = 36 boxes (the reference hard-codes 36).
-Every item and two collated batches (the reference's own ``collate_fn``) are stored; ``oracle/dataset_oracle.py`` is pinned to them.
+Every item and two collated batches (the reference's own ``collate_fn``) are stored, and the same for ``ImageclefDataset`` and
+``MimicDataset`` (K = 51 boxes, string image keys); ``oracle/dataset_oracle.py`` is pinned to them.
 """
 import os
 import sys
@@ -24,7 +25,9 @@ import shard_fixture as SF  # noqa: E402
 
 REF = "/root/reference"
 GOLDEN_ARGS = dict(n_images=5, n_questions=19, K=36, D=16, n_answers=11, seed=3)
+MEDICAL_ARGS = dict(n_images=6, n_questions=17, K=51, D=16, n_answers=9, seed=5)
 BATCHES = ([3, 17, 9, 0, 12], [18, 1, 2, 7])
+MEDICAL_BATCHES = ([3, 16, 9, 0, 12, 5], [1, 2, 7])
 
 
 def main():
@@ -56,6 +59,29 @@ def main():
         col = T.collate_fn(batch)
         for j, name in enumerate(names):
             out[f"batch{b}.{name}"] = col[j].numpy()
+    # ---- the medical datasets: ImageclefDataset.__getitem__ and MimicDataset.__getitem__ (its own override), same construction
+    for variant, cls in (("imageclef", T.ImageclefDataset), ("mimic", T.MimicDataset)):
+        ds = SF.make_medical_dataset(variant=variant, **MEDICAL_ARGS)
+        obj = cls.__new__(cls)
+        obj.vqa, obj.q_wtoi, obj.a_wtoi, obj.n_answers = ds["records"], ds["q_wtoi"], ds["a_wtoi"], ds["n_answers"]
+        obj.i_feat = ds["i_feat"]
+        obj.sizes = pd.DataFrame({k: v for k, v in ds["sizes"].items()})
+        obj.n_questions = len(ds["records"])
+
+        def med_item(n):
+            obj.bbox = {k: v.copy() for k, v in ds["bbox"].items()}
+            return obj[n]
+
+        items = [med_item(n) for n in range(len(obj))]
+        for j, name in enumerate(names[:-1]):
+            out[f"{variant}.item.{name}"] = np.stack([np.asarray(it[j]) for it in items])
+        out[f"{variant}.item.iid"] = np.array([it[7] for it in items])
+        for b, idx in enumerate(MEDICAL_BATCHES):
+            col = T.collate_fn([med_item(n) for n in idx])
+            for j, name in enumerate(names[:-1]):
+                out[f"{variant}.batch{b}.{name}"] = col[j].numpy()
+            out[f"{variant}.batch{b}.iid"] = np.array(col[7])
+            out[f"{variant}.batch{b}.src"] = np.array(idx)
     np.savez_compressed(os.path.join(HERE, "dataset_small.npz"), **out)
     print("wrote dataset_small.npz:", {k: v.shape for k, v in out.items() if k.startswith("item.")})
 

@@ -7,7 +7,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle.dataset_oracle import reference_collate, reference_item  # noqa: E402,F401  (re-exported for the tests)
+from oracle.dataset_oracle import reference_collate, reference_item, reference_item_medical  # noqa: E402,F401  (re-exported for the tests)
 
 
 def make_dataset(n_images=7, n_questions=23, K=6, D=16, n_answers=11, seed=3):
@@ -36,3 +36,20 @@ def make_dataset(n_images=7, n_questions=23, K=6, D=16, n_answers=11, seed=3):
                             answers_w_scores=[(p, round(float(rng.rand()), 3)) for p in picks],
                             answers=[(p, float(rng.randint(1, 11))) for p in picks]))
     return dict(records=records, q_wtoi=q_wtoi, a_wtoi=a_wtoi, i_feat=i_feat, bbox=bbox, sizes=sizes, n_answers=n_answers, K=K, D=D)
+
+
+def make_medical_dataset(n_images=6, n_questions=17, K=51, D=16, n_answers=9, seed=5, variant="imageclef"):
+    """The same in the shape ``ImageclefDataset`` (string image ids keyed as ``id + '.jpg'``, ``answers`` a dict of vote counts) or
+    ``MimicDataset`` (string ids used as they are, ``answers`` a list of pairs) load it; K boxes per image, all used."""
+    ds = make_dataset(n_images=n_images, n_questions=n_questions, K=K, D=D, n_answers=n_answers, seed=seed)
+    ren = {}
+    for j, old in enumerate(sorted(ds["i_feat"], key=int)):
+        ren[old] = f"synpic{(j * 7919) % 1000:03d}"
+    suffix = ".jpg" if variant == "imageclef" else ""
+    for name in ("i_feat", "bbox", "sizes"):
+        ds[name] = {ren[k] + suffix: v for k, v in ds[name].items()}
+    for r in ds["records"]:
+        r["image_id"] = ren[str(r["image_id"])]
+        if variant == "imageclef":
+            r["answers"] = {w: c for w, c in r["answers"]}
+    return ds

@@ -160,3 +160,47 @@ def test_shards_reproduce_the_reference_golden_items(tmp_path):
     for b in range(2):
         idx = g[f"batch{b}.idx"]
         assert np.array_equal(shards.order_batch(np.array(sorted(idx.tolist())), s.qlen, "reference"), idx)
+
+
+MEDICAL_ARGS = dict(n_images=6, n_questions=17, K=51, D=16, n_answers=9, seed=5)
+
+
+@pytest.mark.parametrize("variant", ["imageclef", "mimic"])
+def test_medical_variants_match_reference_golden(tmp_path, variant):
+    """ImageclefDataset / MimicDataset items (string image key last, every box used, ImageCLEF's dict answers and '.jpg' keys):
+    the oracle restatement, the converter + shard reader and the in-batch order against the unmodified reference's outputs."""
+    g = _golden()
+    ds = SF.make_medical_dataset(variant=variant, **MEDICAL_ARGS)
+    meta = shards.from_reference_records(ds["records"], ds["q_wtoi"], ds["a_wtoi"], ds["i_feat"], ds["bbox"], ds["sizes"], str(tmp_path),
+                                         n_answers=ds["n_answers"], n_obj=None, variant=variant)
+    assert meta["n_obj"] == 51 and meta["variant"] == variant
+    s = shards.ShardSet(str(tmp_path))
+    for n in range(len(s)):
+        ref, got = SF.reference_item_medical(ds, n, variant=variant), s.dense_item(n)
+        for j, name in enumerate(NAMES[:-1]):
+            want = g[f"{variant}.item.{name}"][n]
+            assert np.array_equal(np.asarray(ref[j]), want) and np.array_equal(np.asarray(got[j]), want), (n, name)
+        assert ref[7] == got[7] == str(g[f"{variant}.item.iid"][n])
+    for b in range(2):
+        src = g[f"{variant}.batch{b}.src"]
+        col = SF.reference_collate([SF.reference_item_medical(ds, int(n), variant=variant) for n in src])
+        assert list(col[7]) == list(g[f"{variant}.batch{b}.iid"])                     # sorted by the key string, descending, stable
+        assert np.array_equal(col[4].numpy(), g[f"{variant}.batch{b}.i"]) and np.array_equal(col[0].numpy(), g[f"{variant}.batch{b}.q"])
+        keys = [s.last_element(int(n)) for n in src]
+        order = shards.order_batch(np.asarray(src, dtype=np.int64), s.qlen, "reference", keys)
+        assert [s.last_element(int(n)) for n in order] == list(g[f"{variant}.batch{b}.iid"])
+        assert np.array_equal(np.stack([s.dense_item(int(n))[4] for n in order]), g[f"{variant}.batch{b}.i"])
+        assert np.array_equal(np.stack([s.dense_item(int(n))[1] for n in order]), g[f"{variant}.batch{b}.a"])
+        assert np.array_equal(np.stack([s.dense_item(int(n))[2] for n in order]), g[f"{variant}.batch{b}.n_votes"])
+
+
+def test_medical_converter_rejects_ragged_box_counts(tmp_path):
+    ds = SF.make_medical_dataset(variant="mimic", **MEDICAL_ARGS)
+    k = next(iter(ds["bbox"]))
+    ds["bbox"][k] = ds["bbox"][k][:40]
+    ds["i_feat"][k] = ds["i_feat"][k][:40]
+    with pytest.raises(ValueError, match="boxes"):
+        shards.from_reference_records(ds["records"], ds["q_wtoi"], ds["a_wtoi"], ds["i_feat"], ds["bbox"], ds["sizes"], str(tmp_path),
+                                      n_answers=ds["n_answers"], n_obj=None, variant="mimic")
+    with pytest.raises(ValueError, match="variant"):
+        shards.from_reference_records([], {}, {}, {}, {}, {}, str(tmp_path), n_answers=3, variant="clevr")

@@ -156,3 +156,23 @@ def test_loader_reproduces_the_reference_golden_batches(tmp_path):
             want = torch.from_numpy(z[f"batch{b}.{name}"])
             assert batch[j].dtype == want.dtype and batch[j].shape == want.shape and torch.equal(batch[j].cpu(), want), (b, name)
     ld.check_errors()
+
+
+@pytest.mark.parametrize("variant", ["imageclef", "mimic"])
+def test_medical_loader_reproduces_the_reference_golden_batches(tmp_path, variant):
+    """ImageclefDataset / MimicDataset batches (K = 51 boxes, image key as the last element, collate order by that key) against the
+    unmodified reference's outputs in tests/golden/dataset_small.npz."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dataset_small.npz"))
+    ds = SF.make_medical_dataset(variant=variant, n_images=6, n_questions=17, K=51, D=16, n_answers=9, seed=5)
+    shards.from_reference_records(ds["records"], ds["q_wtoi"], ds["a_wtoi"], ds["i_feat"], ds["bbox"], ds["sizes"], str(tmp_path),
+                                  n_answers=ds["n_answers"], n_obj=None, variant=variant)
+    ld = shards.ShardLoader(str(tmp_path), 6, DEV, order="reference")
+    names = ("q", "a", "n_votes", "qid", "i", "k", "qlen")
+    for b in range(2):
+        src = z[f"{variant}.batch{b}.src"].astype(np.int64)
+        batch = ld.assemble(ld.ordered(src))
+        for j, name in enumerate(names):
+            want = torch.from_numpy(z[f"{variant}.batch{b}.{name}"])
+            assert batch[j].dtype == want.dtype and batch[j].shape == want.shape and torch.equal(batch[j].cpu(), want), (b, name)
+        assert list(batch[7]) == [str(x) for x in z[f"{variant}.batch{b}.iid"]]
+    ld.check_errors()

@@ -34,6 +34,7 @@ import numpy as np
 import torch
 
 FORMAT_VERSION = 1
+VARIANTS = ("vqa2", "imageclef", "mimic")          # VQA_Dataset / ImageclefDataset / MimicDataset of torch_dataset.py
 _NPY = ("questions", "qlen", "image_row", "qid", "ans_ptr", "ans_id", "ans_val", "vote_ptr", "vote_id", "vote_val")
 
 
@@ -55,11 +56,16 @@ def to_bf16_bits(x: np.ndarray) -> np.ndarray:
 
 def write_shards(out_dir: str, *, features: np.ndarray, boxes: np.ndarray, questions: np.ndarray, qlen: np.ndarray,
                  image_row: np.ndarray, qid: np.ndarray, answers: Sequence[Sequence[Tuple[int, float]]],
-                 votes: Sequence[Sequence[Tuple[int, float]]], n_answers: int, feature_dtype: str = "f32") -> Dict:
+                 votes: Sequence[Sequence[Tuple[int, float]]], n_answers: int, feature_dtype: str = "f32",
+                 image_keys: Optional[Sequence[str]] = None, variant: str = "vqa2") -> Dict:
     """Write one shard directory.  ``features`` (n_images, K, D) fp32, ``boxes`` (n_images, K, 4) normalised xyxy,
-    ``questions`` (n_questions, q_width) token ids, ``answers`` / ``votes``: per question a list of (answer id, value)."""
+    ``questions`` (n_questions, q_width) token ids, ``answers`` / ``votes``: per question a list of (answer id, value).
+    ``image_keys`` (one string per image row; the medical datasets return it as the batch's last element) and ``variant``
+    (``"vqa2"`` / ``"imageclef"`` / ``"mimic"``: which reference dataset class the batches mirror) are recorded for the loader."""
     if feature_dtype not in ("f32", "bf16"):
         raise ValueError(f"feature_dtype must be 'f32' or 'bf16', got {feature_dtype!r}")
+    if variant not in VARIANTS:
+        raise ValueError(f"variant must be one of {VARIANTS}, got {variant!r}")
     features = np.asarray(features)
     boxes = np.ascontiguousarray(boxes, dtype=np.float32)
     n_img, K, D = features.shape
@@ -68,6 +74,10 @@ def write_shards(out_dir: str, *, features: np.ndarray, boxes: np.ndarray, quest
         raise ValueError(f"boxes must be {(n_img, K, 4)}, got {boxes.shape}")
     if D % 8:
         raise ValueError(f"feature width must be a multiple of 8 (16-byte rows in either dtype), got {D}")
+    if variant != "vqa2" and image_keys is None:
+        raise ValueError(f"variant={variant!r} needs image_keys (the batches carry the image key as their last element)")
+    if image_keys is not None and len(image_keys) != n_img:
+        raise ValueError("image_keys must have one entry per image row")
     if not (len(qlen) == len(image_row) == len(qid) == len(answers) == len(votes) == nq):
         raise ValueError("questions, qlen, image_row, qid, answers and votes must have one entry per question")
     if not np.isfinite(features).all():
@@ -93,31 +103,51 @@ def write_shards(out_dir: str, *, features: np.ndarray, boxes: np.ndarray, quest
         np.save(os.path.join(out_dir, k + ".npy"), v)
     meta = dict(format=FORMAT_VERSION, n_images=int(n_img), n_obj=int(K), feat_width=int(D), feat_dim=int(D + 4),
                 feature_dtype=feature_dtype, n_questions=int(nq), q_width=int(arrays["questions"].shape[1]) if nq else 0,
-                n_answers=int(n_answers))
+                n_answers=int(n_answers), variant=variant)
+    if image_keys is not None:
+        with open(os.path.join(out_dir, "image_keys.json"), "w") as f:
+            json.dump([str(k) for k in image_keys], f)
     with open(os.path.join(out_dir, "meta.json"), "w") as f:
         json.dump(meta, f, indent=1)
     return meta
 
 
 def from_reference_records(records: Sequence[Mapping], q_wtoi: Mapping[str, int], a_wtoi: Mapping[str, int], i_feat: Mapping,
-                           bbox: Mapping, sizes: Mapping, out_dir: str, *, n_answers: int, n_obj: int = 36, q_width: int = 100,
-                           feature_dtype: str = "f32") -> Dict:
+                           bbox: Mapping, sizes: Mapping, out_dir: str, *, n_answers: int, n_obj: Optional[int] = 36, q_width: int = 100,
+                           feature_dtype: str = "f32", variant: str = "vqa2") -> Dict:
     """Convert what ``VQA_Dataset.__init__`` loads (``torch_dataset.py:35-75``: the question json ``records``, the two word->index
-    dictionaries, the zarr groups ``i_feat`` / ``bbox`` and the image-size table ``sizes``, all indexed by ``str(image_id)``) into
+    dictionaries, the zarr groups ``i_feat`` / ``bbox`` and the image-size table ``sizes``, all indexed by the image key) into
     shards, applying ``__getitem__``'s rules (``:105-164``): unseen question words -> 0, unseen answers skipped, a repeated answer
-    keeps its last value, boxes divided by (w, h, w, h), features must be finite."""
-    image_ids: List = []
-    row_of: Dict = {}
+    keeps its last value, boxes divided by (w, h, w, h), features must be finite.
+
+    ``variant="imageclef"`` / ``"mimic"`` follow ``ImageclefDataset.__getitem__`` (``:236-291``) / ``MimicDataset.__getitem__``
+    (``:356-417``) instead: every box of the image is used (``n_obj=None``: taken from the data; it must be the same for all images -
+    the model reads one K per batch) and the batch's last element is the image key, not the dataset index; ImageCLEF additionally
+    keys images by ``image_id + '.jpg'`` and stores ``answers`` as a dict."""
+    if variant not in VARIANTS:
+        raise ValueError(f"variant must be one of {VARIANTS}, got {variant!r}")
+    medical = variant != "vqa2"
+
+    def key_of(r):
+        return str(r["image_id"]) + ".jpg" if variant == "imageclef" else str(r["image_id"])
+
+    keys: List[str] = []
+    row_of: Dict[str, int] = {}
     for r in records:
-        iid = r["image_id"]
-        if iid not in row_of:
-            row_of[iid] = len(image_ids)
-            image_ids.append(iid)
+        k = key_of(r)
+        if k not in row_of:
+            row_of[k] = len(keys)
+            keys.append(k)
     feats, boxes = [], []
-    for iid in image_ids:
-        f = np.asarray(i_feat[str(iid)], dtype=np.float32)[:n_obj]
-        b = np.array(np.asarray(bbox[str(iid)])[:n_obj], dtype=np.float32)       # a copy: the reference scales in place
-        w, h = (float(x) for x in np.asarray(sizes[str(iid)]).reshape(-1)[:2])
+    for k in keys:
+        f = np.asarray(i_feat[k], dtype=np.float32)
+        b = np.array(np.asarray(bbox[k]), dtype=np.float32)             # a copy: the reference scales in place
+        if medical and n_obj is None:
+            n_obj = b.shape[0]
+        if b.shape[0] < n_obj or f.shape[0] < n_obj or (medical and (b.shape[0] != n_obj or f.shape[0] != n_obj)):
+            raise ValueError(f"image {k}: {b.shape[0]} boxes / {f.shape[0]} feature rows, expected {n_obj}")
+        f, b = f[:n_obj], b[:n_obj]
+        w, h = (float(x) for x in np.asarray(sizes[k]).reshape(-1)[:2])
         b[:, 0] /= w
         b[:, 1] /= h
         b[:, 2] /= w
@@ -132,12 +162,13 @@ def from_reference_records(records: Sequence[Mapping], q_wtoi: Mapping[str, int]
         qlen[n] = len(toks)
         for i, wd in enumerate(toks):
             questions[n, i] = q_wtoi.get(wd, 0)
+        vote_pairs = r["answers"].items() if variant == "imageclef" else r["answers"]
         answers.append([(a_wtoi[wd], float(c)) for wd, c in r["answers_w_scores"] if wd in a_wtoi])
-        votes.append([(a_wtoi[wd], float(c)) for wd, c in r["answers"] if wd in a_wtoi])
+        votes.append([(a_wtoi[wd], float(c)) for wd, c in vote_pairs if wd in a_wtoi])
     return write_shards(out_dir, features=np.stack(feats), boxes=np.stack(boxes), questions=questions, qlen=qlen,
-                        image_row=np.array([row_of[r["image_id"]] for r in records], dtype=np.int64),
+                        image_row=np.array([row_of[key_of(r)] for r in records], dtype=np.int64),
                         qid=np.array([r["question_id"] for r in records], dtype=np.int64), answers=answers, votes=votes,
-                        n_answers=n_answers, feature_dtype=feature_dtype)
+                        n_answers=n_answers, feature_dtype=feature_dtype, image_keys=keys, variant=variant)
 
 
 # ------------------------------------------------------------------------------------------------------ reading
@@ -153,6 +184,14 @@ class ShardSet:
         self.path = path
         self.n_images, self.n_obj, self.feat_width, self.n_answers = m["n_images"], m["n_obj"], m["feat_width"], m["n_answers"]
         self.n_questions, self.q_width, self.bf16 = m["n_questions"], m["q_width"], m["feature_dtype"] == "bf16"
+        self.variant = m.get("variant", "vqa2")
+        kp = os.path.join(path, "image_keys.json")
+        self.image_keys: Optional[List[str]] = None
+        if os.path.exists(kp):
+            with open(kp) as f:
+                self.image_keys = json.load(f)
+        if self.variant not in VARIANTS or (self.variant != "vqa2" and self.image_keys is None):
+            raise ValueError(f"{path}: unknown variant {self.variant!r} or medical shards without image_keys.json")
         shape = (self.n_images, self.n_obj, self.feat_width)
         self.features = np.memmap(os.path.join(path, "features.bin"), dtype=np.uint16 if self.bf16 else np.float32, mode="r", shape=shape)
         self.boxes = np.memmap(os.path.join(path, "boxes.bin"), dtype=np.float32, mode="r", shape=(self.n_images, self.n_obj, 4))
@@ -188,7 +227,12 @@ class ShardSet:
             f = (f.astype(np.uint32) << 16).view(np.float32)
         img = np.concatenate([f, np.asarray(self.boxes[r])], axis=1)
         return (np.asarray(self.questions[n], dtype=np.int64), a, v, np.asarray(self.qid[n]).reshape(-1), img,
-                np.asarray(self.n_obj).reshape(1), int(self.qlen[n]), n)
+                np.asarray(self.n_obj).reshape(1), int(self.qlen[n]), self.last_element(n))
+
+    def last_element(self, n: int):
+        """What the reference item carries last: the dataset index (``torch_dataset.py:164``) or, for the medical datasets, the
+        image key (``:291``) - also the key ``collate_fn`` sorts a batch by."""
+        return self.image_keys[int(self.image_row[n])] if self.variant != "vqa2" else n
 
 
 def epoch_batches(n_questions: int, batch_size: int, *, epoch: int = 0, shuffle: bool = True, seed: int = 1000, rank: int = 0,
@@ -211,11 +255,15 @@ def epoch_batches(n_questions: int, batch_size: int, *, epoch: int = 0, shuffle:
     return out
 
 
-def order_batch(idx: np.ndarray, qlen: np.ndarray, order: str) -> np.ndarray:
+def order_batch(idx: np.ndarray, qlen: np.ndarray, order: str, keys: Optional[Sequence[str]] = None) -> np.ndarray:
     """In-batch order.  ``"reference"``: what ``collate_fn`` does - ``batch.sort(key=lambda x: x[-1], reverse=True)`` with the
     dataset index as the last tuple element (``torch_dataset.py:27-31,164``), i.e. descending INDEX.  ``"qlen"``: descending
-    question length (what that function's comment intends), stable - lets the GRU's row-tile gate skip finished tiles."""
+    question length (what that function's comment intends), stable - lets the GRU's row-tile gate skip finished tiles.
+    ``keys``: per entry of ``idx`` the string the medical datasets carry last (their ``collate_fn`` order is by that string)."""
     if order == "reference":
+        if keys is not None:                                            # medical datasets: the last element is the image key (a str)
+            pos = sorted(range(len(idx)), key=lambda j: keys[j], reverse=True)      # list.sort semantics: stable, also reversed
+            return idx[np.asarray(pos, dtype=np.int64)]
         return idx[np.argsort(-idx, kind="stable")]
     if order == "qlen":
         return idx[np.argsort(-np.asarray(qlen[idx], dtype=np.int64), kind="stable")]
@@ -263,9 +311,14 @@ class ShardLoader:
         self.epoch = epoch
 
     def batches(self) -> List[np.ndarray]:
-        return [order_batch(b, self.set.qlen, self.order) for b in
+        return [self.ordered(b) for b in
                 epoch_batches(len(self.set), self.batch_size, epoch=self.epoch, shuffle=self.shuffle, seed=self.seed,
                               rank=self.rank, world=self.world, drop_last=self.drop_last)]
+
+    def ordered(self, idx: np.ndarray) -> np.ndarray:
+        """``idx`` in this loader's in-batch order (``order_batch``; the medical variant's reference order is by image key)."""
+        keys = [self.set.last_element(int(n)) for n in idx] if self.set.variant != "vqa2" and self.order == "reference" else None
+        return order_batch(idx, self.set.qlen, self.order, keys)
 
     def __len__(self) -> int:
         return len(epoch_batches(len(self.set), self.batch_size, epoch=self.epoch, shuffle=False, rank=self.rank, world=self.world,
@@ -299,7 +352,8 @@ class ShardLoader:
         qid = torch.from_numpy(np.asarray(s.qid[sidx])[back].reshape(B, 1).astype(np.int64))
         k = torch.full((B, 1), s.n_obj, dtype=torch.int64, device=dev)
         qlen = torch.from_numpy(np.asarray(s.qlen[sidx])[back].astype(np.int64))
-        return q, a, n_votes, qid, image, k, qlen, torch.from_numpy(idx.astype(np.int64))
+        last = [s.last_element(int(n)) for n in idx] if s.variant != "vqa2" else torch.from_numpy(idx.astype(np.int64))
+        return q, a, n_votes, qid, image, k, qlen, last
 
     def check_errors(self) -> None:
         """Raise if a kernel met an index outside its table (synchronises; called at the end of every epoch)."""
