@@ -204,3 +204,21 @@ def test_medical_converter_rejects_ragged_box_counts(tmp_path):
                                       n_answers=ds["n_answers"], n_obj=None, variant="mimic")
     with pytest.raises(ValueError, match="variant"):
         shards.from_reference_records([], {}, {}, {}, {}, {}, str(tmp_path), n_answers=3, variant="clevr")
+
+
+def test_convert_dataset_tool_takes_a_loaded_reference_dataset_object(ds, tmp_path):
+    """tools/convert_dataset.py: the attributes VQA_Dataset.__init__ sets (torch_dataset.py:35-102) are all it reads."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("convert_dataset", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                                "tools", "convert_dataset.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    obj = types.SimpleNamespace(vqa=ds["records"], q_wtoi=ds["q_wtoi"], a_wtoi=ds["a_wtoi"], i_feat=ds["i_feat"], bbox=ds["bbox"],
+                                sizes=ds["sizes"], n_answers=ds["n_answers"], pretrained_wemb=np.ones((25, 8), np.float32))
+    with pytest.raises(ValueError):                                    # the fixture has 6 boxes per image, VQA2 needs 36
+        tool.convert(obj, str(tmp_path / "x"), "vqa2")
+    meta = tool.convert(obj, str(tmp_path / "y"), "mimic")
+    assert meta["n_obj"] == ds["K"] and meta["variant"] == "mimic"
+    assert np.load(tmp_path / "y" / "pretrained_wemb.npy").shape == (25, 8)
+    assert len(shards.ShardSet(str(tmp_path / "y"))) == len(ds["records"])
