@@ -222,3 +222,48 @@ def test_convert_dataset_tool_takes_a_loaded_reference_dataset_object(ds, tmp_pa
     assert meta["n_obj"] == ds["K"] and meta["variant"] == "mimic"
     assert np.load(tmp_path / "y" / "pretrained_wemb.npy").shape == (25, 8)
     assert len(shards.ShardSet(str(tmp_path / "y"))) == len(ds["records"])
+
+
+# ---------------------------------------------------------------------------------------------- properties (hypothesis)
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(n=st.integers(1, 400), bs=st.integers(1, 33), world=st.integers(1, 8), epoch=st.integers(0, 3), drop_last=st.booleans())
+def test_epoch_batches_properties(n, bs, world, epoch, drop_last):
+    per_rank = [shards.epoch_batches(n, bs, epoch=epoch, seed=9, rank=r, world=world, drop_last=drop_last) for r in range(world)]
+    steps = len(per_rank[0])
+    assert all(len(b) == steps for b in per_rank)                      # every rank takes the same number of steps ...
+    for t in range(steps):
+        sizes = {len(per_rank[r][t]) for r in range(world)}
+        assert len(sizes) == 1 and 1 <= next(iter(sizes)) <= bs        # ... with the same batch size (collectives stay aligned)
+    flat = np.concatenate([np.concatenate(b) for b in per_rank if b]) if steps else np.zeros(0, dtype=np.int64)
+    assert len(np.unique(flat)) == len(flat) and (flat.size == 0 or (flat.min() >= 0 and flat.max() < n))
+    full = (n // (bs * world)) * bs * world
+    assert len(flat) >= full and (not drop_last or len(flat) == full) and len(flat) > n - max(bs * world, world) - world
+
+
+@settings(max_examples=40, deadline=None)
+@given(data=st.data())
+def test_csr_rows_and_batch_order_properties(data, tmp_path_factory):
+    nq = data.draw(st.integers(1, 30))
+    A = data.draw(st.integers(2, 12))
+    rows = [[(data.draw(st.integers(0, A - 1)), float(data.draw(st.integers(0, 10)))) for _ in range(data.draw(st.integers(0, 4)))]
+            for _ in range(nq)]
+    qlen = np.array([data.draw(st.integers(1, 14)) for _ in range(nq)], dtype=np.int32)
+    path = str(tmp_path_factory.mktemp("prop"))
+    shards.write_shards(path, features=np.zeros((1, 2, 8), np.float32), boxes=np.zeros((1, 2, 4), np.float32),
+                        questions=np.zeros((nq, 4), np.int32), qlen=qlen, image_row=np.zeros(nq, np.int64), qid=np.arange(nq),
+                        answers=rows, votes=rows[::-1], n_answers=A)
+    s = shards.ShardSet(path)
+    idx = np.array(data.draw(st.permutations(list(range(nq))))[:data.draw(st.integers(1, nq))], dtype=np.int64)
+    ptr, ids, val = s.csr_rows("ans", idx)
+    assert ptr[0] == 0 and ptr[-1] == len(ids) == len(val) == sum(len(rows[n]) for n in idx)
+    for b, n in enumerate(idx):
+        assert [(int(i), float(v)) for i, v in zip(ids[ptr[b]:ptr[b + 1]], val[ptr[b]:ptr[b + 1]])] == rows[n]
+    vp, vi, _ = s.csr_rows("vote", idx)
+    assert [int(x) for x in vi[vp[0]:vp[1]]] == [a for a, _ in rows[::-1][idx[0]]]
+    byq = shards.order_batch(idx, s.qlen, "qlen")
+    assert sorted(byq.tolist()) == sorted(idx.tolist()) and np.all(np.diff(qlen[byq]) <= 0)
+    ref = shards.order_batch(idx, s.qlen, "reference")
+    assert ref.tolist() == sorted(idx.tolist(), reverse=True)
