@@ -135,3 +135,66 @@ def test_packed_gru_matches_torch_gru():
     _, hid = gru(packed)
     p = {"q_gru." + k: v.detach() for k, v in gru.state_dict().items()}
     assert rel_err(O.gru_last_hidden(emb, qlen, p), hid[0].detach()) < 1e-6
+
+
+def test_hand_checkable_known_answers():
+    """tests/golden/kat_tiny.json (produced by the unmodified reference, tests/golden/make_kat.py) against closed forms derived with
+    ``math`` alone, and the oracle against both: 4 unit-square nodes, 3 Gaussian kernels, top-2 neighbourhoods."""
+    import json
+    import math
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat_tiny.json")) as f:
+        kat = json.load(f)
+    c = kat["centres"]
+    pi = math.pi
+    # ---- pseudo-coordinates: (rho, theta) of c_i - c_j with theta = atan2(dx, dy)  [x first: sparse_graph_model.py:264-265]
+    hand_theta = [[0.0, -pi / 2, pi, -3 * pi / 4],          # from node 0 (0,0): to (1,0) d=(-1,0); to (0,1) d=(0,-1); to (1,1) d=(-1,-1)
+                  [pi / 2, 0.0, 3 * pi / 4, pi],            # from node 1 (1,0): d=(1,0); -; (1,-1); (0,-1)
+                  [0.0, -pi / 4, 0.0, -pi / 2],             # from node 2 (0,1): d=(0,1); (-1,1); -; (-1,0)
+                  [pi / 4, 0.0, pi / 2, 0.0]]               # from node 3 (1,1): d=(1,1); (0,1); (1,0); -
+    r2 = math.sqrt(2.0)
+    hand_rho = [[0, 1, 1, r2], [1, 0, r2, 1], [1, r2, 0, 1], [r2, 1, 1, 0]]
+    assert np.allclose(kat["rho"], hand_rho, atol=1e-15) and np.allclose(kat["theta"], hand_theta, atol=1e-15)
+    pseudo = O.polar_pseudo_coordinates(torch.tensor([c], dtype=torch.float64))
+    assert np.allclose(pseudo[0, :, :, 0].numpy(), hand_rho, atol=1e-15) and np.allclose(pseudo[0, :, :, 1].numpy(), hand_theta, atol=1e-15)
+
+    # ---- Gaussian patch weights, unit precisions: w_k ~ exp(-(rho - mu_rho_k)^2 / 2) * exp(-ang(theta, mu_theta_k)^2 / 2), normalised over k
+    g = kat["gauss"]
+
+    def hand_w(rho, theta):
+        raw = []
+        for mr, mt in zip(g["mean_rho"], g["mean_theta"]):
+            a = abs(theta - mt)
+            a = min(a, abs(2 * pi - a))                     # wrap-around (layers.py:114-116)
+            raw.append(math.exp(-0.5 * (rho - mr) ** 2) * math.exp(-0.5 * a * a))
+        s = sum(raw)
+        return [x / s for x in raw]
+
+    hand = [[hand_w(hand_rho[i][j], hand_theta[i][j]) for j in range(4)] for i in range(4)]
+    assert np.allclose(kat["gaussian_weights"], hand, rtol=1e-12)
+    # one value spelled out: edge 1 <- 0 has rho = 1, theta = pi/2 -> raw = (e^{-1/2 - pi^2/8}, 1, e^{-pi^2/8})
+    e1, e2 = math.exp(-0.5 - pi * pi / 8), math.exp(-pi * pi / 8)
+    assert np.allclose(kat["gaussian_weights"][1][0], [e1 / (e1 + 1 + e2), 1 / (e1 + 1 + e2), e2 / (e1 + 1 + e2)], rtol=1e-12)
+    # wrap-around: edge 0 <- 3 has theta = -3pi/4; against mu_theta = pi the angle is pi/4, not 7pi/4
+    # (against mu_theta = pi/2 it is 3pi/4, not 5pi/4); both kernels have mu_rho = 1, so w_2 / w_1 = e^{((3pi/4)^2 - (pi/4)^2) / 2} = e^{pi^2/4}
+    assert math.isclose(kat["gaussian_weights"][0][3][2] / kat["gaussian_weights"][0][3][1], math.exp(pi * pi / 4), rel_tol=1e-12)
+    p = {"gc." + k: torch.tensor(v, dtype=torch.float64).view(3, 1) for k, v in g.items()}
+    w = O.gaussian_kernel_weights(pseudo, p, "gc").view(4, 4, 3)
+    assert np.allclose(w.numpy(), hand, rtol=1e-12)
+    for i in range(4):
+        for j in range(4):
+            one = O.np_edge_kernel_weights(np.array(c[i]), np.array(c[j]), np.array(g["mean_rho"]), np.array(g["precision_rho"]),
+                                           np.array(g["mean_theta"]), np.array(g["precision_theta"]))
+            assert np.allclose(one, hand[i][j], rtol=1e-12)
+
+    # ---- top-2 + softmax: rows whose two largest entries differ by ln 2, ln 3, ln 4, ln 1.5 -> (1/3, 2/3), (1/4, 3/4), (1/5, 4/5), (2/5, 3/5)
+    assert kat["topk_index_sets"] == [[1, 3], [0, 2], [1, 3], [0, 1]]
+    hand_alpha = [[1 / 3, 2 / 3], [1 / 4, 3 / 4], [1 / 5, 4 / 5], [3 / 5, 2 / 5]]
+    assert np.allclose(kat["topk_softmax_by_index"], hand_alpha, rtol=1e-12)
+    adj = torch.tensor([kat["adjacency"]], dtype=torch.float64)
+    alpha, idx = O.select_neighbourhood(adj, 2)
+    for i in range(4):
+        pairs = sorted(zip(idx[0, i].tolist(), alpha[0, i].tolist()))
+        assert [a for a, _ in pairs] == kat["topk_index_sets"][i] and np.allclose([v for _, v in pairs], hand_alpha[i], rtol=1e-12)
+        order, sm = O.np_topk_softmax(np.array(kat["adjacency"][i]), 2)
+        assert order.tolist() == kat["topk_index_sets"][i] and np.allclose(sm, hand_alpha[i], rtol=1e-12)
