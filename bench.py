@@ -470,7 +470,7 @@ def run_b200(args, workload):
     if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only
         from vqa_b200.synthetic import WORKLOADS
         cores = os.cpu_count() or 1
-        t, _ = cpu_train_steps(WORKLOADS["vqa2_b64"], args.cpu_sample, 4, 1, cores)
+        t, _ = cpu_train_steps(WORKLOADS["vqa2_b64"], args.cpu_sample, 20, 2, cores)      # ~10 s of host work on the 16-core boxes
         v = args.cpu_sample * len(t) / sum(t)
         cpu = {"value": round(v, 3), "unit": "questions/s", "cores": cores, "kind": "port",
                "sample": f"{len(t)} train steps of {args.cpu_sample} questions (BASELINE config[0] shapes), oracle port, PyTorch CPU"}
