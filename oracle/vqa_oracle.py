@@ -122,7 +122,7 @@ def gru_last_hidden(emb: torch.Tensor, qlen: Sequence[int], p: Params, prefix: s
     b_ih, b_hh = p[prefix + ".bias_ih_l0"], p[prefix + ".bias_hh_l0"]
     hid = w_hh.shape[1]
     bsz = emb.shape[0]
-    lens = torch.as_tensor([int(x) for x in qlen], dtype=torch.long)
+    lens = torch.as_tensor([int(x) for x in qlen], dtype=torch.long, device=emb.device)
     h = emb.new_zeros(bsz, hid)
     for t in range(int(lens.max())):
         gi = emb[:, t] @ w_ih.t() + b_ih
@@ -244,7 +244,7 @@ def forward(
     def drop(x):
         if not training or dropout_p == 0.0:
             return x
-        keep = (torch.rand(x.shape, generator=generator, dtype=x.dtype) >= dropout_p).to(x.dtype)
+        keep = (torch.rand(x.shape, generator=generator, dtype=x.dtype, device=x.device) >= dropout_p).to(x.dtype)
         return x * keep / (1.0 - dropout_p)
 
     centres = box_centres(image)  # from the UN-dropped image (lines 106-108 precede 111)
