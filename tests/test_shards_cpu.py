@@ -267,3 +267,20 @@ def test_csr_rows_and_batch_order_properties(data, tmp_path_factory):
     assert sorted(byq.tolist()) == sorted(idx.tolist()) and np.all(np.diff(qlen[byq]) <= 0)
     ref = shards.order_batch(idx, s.qlen, "reference")
     assert ref.tolist() == sorted(idx.tolist(), reverse=True)
+
+
+def test_writer_streams_images_from_an_iterator(tmp_path):
+    rng = np.random.RandomState(1)
+    feats, boxes = rng.rand(5, 3, 8).astype(np.float32), rng.rand(5, 3, 4).astype(np.float32)
+    common = dict(questions=np.zeros((2, 6), np.int32), qlen=[1, 2], image_row=[4, 0], qid=[7, 8], answers=[[], [(1, 1.0)]],
+                  votes=[[], []], n_answers=3)
+    shards.write_shards(str(tmp_path / "a"), features=feats, boxes=boxes, **common)
+    shards.write_shards(str(tmp_path / "b"), image_iter=((feats[i], boxes[i]) for i in range(5)), **common)
+    a, b = shards.ShardSet(str(tmp_path / "a")), shards.ShardSet(str(tmp_path / "b"))
+    assert a.meta == b.meta and np.array_equal(a.features, b.features) and np.array_equal(a.boxes, b.boxes) and np.array_equal(a.features, feats)
+    with pytest.raises(ValueError, match="either"):
+        shards.write_shards(str(tmp_path / "c"), features=feats, boxes=boxes, image_iter=iter([]), **common)
+    with pytest.raises(ValueError, match="no images"):
+        shards.write_shards(str(tmp_path / "d"), image_iter=iter([]), **common)
+    with pytest.raises(ValueError, match="image row 1"):
+        shards.write_shards(str(tmp_path / "e"), image_iter=iter([(feats[0], boxes[0]), (feats[1][:2], boxes[1][:2])]), **common)

@@ -54,43 +54,57 @@ def to_bf16_bits(x: np.ndarray) -> np.ndarray:
     return t.view(torch.int16).numpy().view(np.uint16)
 
 
-def write_shards(out_dir: str, *, features: np.ndarray, boxes: np.ndarray, questions: np.ndarray, qlen: np.ndarray,
+def write_shards(out_dir: str, *, features: Optional[np.ndarray] = None, boxes: Optional[np.ndarray] = None, questions: np.ndarray, qlen: np.ndarray,
                  image_row: np.ndarray, qid: np.ndarray, answers: Sequence[Sequence[Tuple[int, float]]],
                  votes: Sequence[Sequence[Tuple[int, float]]], n_answers: int, feature_dtype: str = "f32",
-                 image_keys: Optional[Sequence[str]] = None, variant: str = "vqa2") -> Dict:
+                 image_keys: Optional[Sequence[str]] = None, variant: str = "vqa2", image_iter=None) -> Dict:
     """Write one shard directory.  ``features`` (n_images, K, D) fp32, ``boxes`` (n_images, K, 4) normalised xyxy,
     ``questions`` (n_questions, q_width) token ids, ``answers`` / ``votes``: per question a list of (answer id, value).
     ``image_keys`` (one string per image row; the medical datasets return it as the batch's last element) and ``variant``
-    (``"vqa2"`` / ``"imageclef"`` / ``"mimic"``: which reference dataset class the batches mirror) are recorded for the loader."""
+    (``"vqa2"`` / ``"imageclef"`` / ``"mimic"``: which reference dataset class the batches mirror) are recorded for the loader.
+    Large tables: pass ``features=None, boxes=None`` and ``image_iter`` = an iterable of per-image ``(features (K, D), boxes (K, 4))``
+    pairs in row order; they are streamed to disk one image at a time (VQA2 trainval is 36 GB of features)."""
     if feature_dtype not in ("f32", "bf16"):
         raise ValueError(f"feature_dtype must be 'f32' or 'bf16', got {feature_dtype!r}")
     if variant not in VARIANTS:
         raise ValueError(f"variant must be one of {VARIANTS}, got {variant!r}")
-    features = np.asarray(features)
-    boxes = np.ascontiguousarray(boxes, dtype=np.float32)
-    n_img, K, D = features.shape
     nq = len(questions)
-    if boxes.shape != (n_img, K, 4):
-        raise ValueError(f"boxes must be {(n_img, K, 4)}, got {boxes.shape}")
-    if D % 8:
-        raise ValueError(f"feature width must be a multiple of 8 (16-byte rows in either dtype), got {D}")
+    if not (len(qlen) == len(image_row) == len(qid) == len(answers) == len(votes) == nq):
+        raise ValueError("questions, qlen, image_row, qid, answers and votes must have one entry per question")
+    if image_iter is None:
+        features = np.asarray(features)
+        boxes = np.ascontiguousarray(boxes, dtype=np.float32)
+        if features.ndim != 3 or boxes.shape != (features.shape[0], features.shape[1], 4):
+            raise ValueError(f"features must be (n_images, K, D) and boxes (n_images, K, 4), got {features.shape} / {boxes.shape}")
+        image_iter = zip(features, boxes)
+    elif features is not None or boxes is not None:
+        raise ValueError("give either features + boxes or image_iter")
+    os.makedirs(out_dir, exist_ok=True)
+    n_img, K, D = 0, None, None
+    with open(os.path.join(out_dir, "features.bin"), "wb") as ff, open(os.path.join(out_dir, "boxes.bin"), "wb") as fb:
+        for f, b in image_iter:
+            f = np.ascontiguousarray(f, dtype=np.float32)
+            b = np.ascontiguousarray(b, dtype=np.float32)
+            if K is None:
+                K, D = f.shape
+                if D % 8:
+                    raise ValueError(f"feature width must be a multiple of 8 (16-byte rows in either dtype), got {D}")
+            if f.shape != (K, D) or b.shape != (K, 4):
+                raise ValueError(f"image row {n_img}: features {f.shape} / boxes {b.shape}, expected {(K, D)} / {(K, 4)}")
+            if not np.isfinite(f).all():
+                raise ValueError("non-finite image features")        # the reference raises per item (torch_dataset.py:141-142)
+            (to_bf16_bits(f) if feature_dtype == "bf16" else f).tofile(ff)
+            b.tofile(fb)
+            n_img += 1
+    if n_img == 0:
+        raise ValueError("no images")
     if variant != "vqa2" and image_keys is None:
         raise ValueError(f"variant={variant!r} needs image_keys (the batches carry the image key as their last element)")
     if image_keys is not None and len(image_keys) != n_img:
         raise ValueError("image_keys must have one entry per image row")
-    if not (len(qlen) == len(image_row) == len(qid) == len(answers) == len(votes) == nq):
-        raise ValueError("questions, qlen, image_row, qid, answers and votes must have one entry per question")
-    if not np.isfinite(features).all():
-        raise ValueError("non-finite image features")            # the reference raises per item (torch_dataset.py:141-142)
     image_row = np.asarray(image_row, dtype=np.int64)
     if nq and (image_row.min() < 0 or image_row.max() >= n_img):
         raise ValueError("image_row out of range")
-    os.makedirs(out_dir, exist_ok=True)
-    if feature_dtype == "bf16":
-        to_bf16_bits(features).tofile(os.path.join(out_dir, "features.bin"))
-    else:
-        np.ascontiguousarray(features, dtype=np.float32).tofile(os.path.join(out_dir, "features.bin"))
-    boxes.tofile(os.path.join(out_dir, "boxes.bin"))
     ap, ai, av = _csr(answers)
     vp, vi, vv = _csr(votes)
     for ids in (ai, vi):
@@ -138,22 +152,25 @@ def from_reference_records(records: Sequence[Mapping], q_wtoi: Mapping[str, int]
         if k not in row_of:
             row_of[k] = len(keys)
             keys.append(k)
-    feats, boxes = [], []
-    for k in keys:
-        f = np.asarray(i_feat[k], dtype=np.float32)
-        b = np.array(np.asarray(bbox[k]), dtype=np.float32)             # a copy: the reference scales in place
-        if medical and n_obj is None:
-            n_obj = b.shape[0]
-        if b.shape[0] < n_obj or f.shape[0] < n_obj or (medical and (b.shape[0] != n_obj or f.shape[0] != n_obj)):
-            raise ValueError(f"image {k}: {b.shape[0]} boxes / {f.shape[0]} feature rows, expected {n_obj}")
-        f, b = f[:n_obj], b[:n_obj]
-        w, h = (float(x) for x in np.asarray(sizes[k]).reshape(-1)[:2])
-        b[:, 0] /= w
-        b[:, 1] /= h
-        b[:, 2] /= w
-        b[:, 3] /= h
-        feats.append(f)
-        boxes.append(b)
+    state = {"n_obj": n_obj}
+
+    def images():                                                       # streamed: one image in memory at a time
+        for k in keys:
+            f = np.asarray(i_feat[k], dtype=np.float32)
+            b = np.array(np.asarray(bbox[k]), dtype=np.float32)         # a copy: the reference scales in place
+            if medical and state["n_obj"] is None:
+                state["n_obj"] = b.shape[0]
+            n = state["n_obj"]
+            if b.shape[0] < n or f.shape[0] < n or (medical and (b.shape[0] != n or f.shape[0] != n)):
+                raise ValueError(f"image {k}: {b.shape[0]} boxes / {f.shape[0]} feature rows, expected {n}")
+            f, b = f[:n], b[:n]
+            w, h = (float(x) for x in np.asarray(sizes[k]).reshape(-1)[:2])
+            b[:, 0] /= w
+            b[:, 1] /= h
+            b[:, 2] /= w
+            b[:, 3] /= h
+            yield f, b
+
     questions = np.zeros((len(records), q_width), dtype=np.int32)
     qlen = np.zeros(len(records), dtype=np.int32)
     answers, votes = [], []
@@ -165,7 +182,7 @@ def from_reference_records(records: Sequence[Mapping], q_wtoi: Mapping[str, int]
         vote_pairs = r["answers"].items() if variant == "imageclef" else r["answers"]
         answers.append([(a_wtoi[wd], float(c)) for wd, c in r["answers_w_scores"] if wd in a_wtoi])
         votes.append([(a_wtoi[wd], float(c)) for wd, c in vote_pairs if wd in a_wtoi])
-    return write_shards(out_dir, features=np.stack(feats), boxes=np.stack(boxes), questions=questions, qlen=qlen,
+    return write_shards(out_dir, image_iter=images(), questions=questions, qlen=qlen,
                         image_row=np.array([row_of[key_of(r)] for r in records], dtype=np.int64),
                         qid=np.array([r["question_id"] for r in records], dtype=np.int64), answers=answers, votes=votes,
                         n_answers=n_answers, feature_dtype=feature_dtype, image_keys=keys, variant=variant)
