@@ -46,9 +46,9 @@ def parse():
     return ap.parse_args()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/), bytes
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/r01c_*_ncu_full.txt)
-NCU_TRAFFIC = {"vqa_graphconv_mma_fwd": 267.9e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel from the committed `ncu --set full` captures
+# (profiles/), keyed by workload: a capture of one workload says nothing about another, so anything else reports null
+NCU_TRAFFIC = {("vqa2_b512", "vqa_graphconv_mma_fwd"): 267.9e6}
 
 
 def peaks():
@@ -59,9 +59,92 @@ def peaks():
     return 6650.0, 1400.0, "fallback"
 
 
+def load_reference_model_module():
+    """The UNMODIFIED reference (`sparse_graph_model.py` + `layers.py`) from the git-ignored install baseline/_ref (written by
+    __graft_entry__.build() in the build container, shipped with the snapshot), imported without disturbing the drop-in modules
+    of the same names.  None when the install is absent."""
+    d = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(d, "sparse_graph_model.py")):
+        return None
+    import importlib
+    import warnings
+    names = ("layers", "sparse_graph_model")
+    saved = {n: sys.modules.pop(n, None) for n in names}
+    sys.path.insert(0, d)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            importlib.import_module("layers")
+            ref = importlib.import_module("sparse_graph_model")
+        assert os.path.dirname(os.path.abspath(ref.__file__)) == d
+    finally:
+        sys.path.remove(d)
+        for n in names:
+            sys.modules.pop(n, None)
+            if saved[n] is not None:
+                sys.modules[n] = saved[n]
+    return ref
+
+
+def reference_train_steps(workload, sample, steps, warmup, device, threads=None, tf32=False):
+    """The reference's own train step - its Model, nn.MultiLabelSoftMarginLoss, torch.optim.Adam, the loop body of run.py:425-460 -
+    through its stock PyTorch code path on `device` ("cpu": the host cores; "cuda": eager PyTorch CUDA, the same-box competitor
+    of SURVEY.md 8d).  Returns (seconds per step list, last loss, peak device memory in GB)."""
+    import warnings
+    from vqa_b200.synthetic import make_batch, make_wemb
+    ref = load_reference_model_module()
+    if ref is None:
+        return None
+    warnings.filterwarnings("ignore")
+    if threads:
+        torch.set_num_threads(threads)
+    w = workload
+    old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = bool(tf32)
+    try:
+        torch.manual_seed(1000)
+        model = ref.Model(pretrained_wemb=make_wemb(w), **w.model_kwargs()).to(device).train()
+        crit = torch.nn.MultiLabelSoftMarginLoss().to(device)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+        batches = []
+        for i in range(2):
+            b = make_batch(w, seed=1000 + i, batch=sample)
+            batches.append((b["question"].to(device), b["image"].to(device), b["K"].to(device), b["qlen"], b["target"].to(device)))
+        cuda = torch.device(device).type == "cuda"
+        if cuda:
+            torch.cuda.reset_peak_memory_stats()
+        times = []
+        for it in range(warmup + steps):
+            q, img, K, qlen, tgt = batches[it % 2]
+            if cuda:
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out, _, _ = model(q, img, K, qlen)
+            loss = crit(out, tgt)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            if cuda:
+                torch.cuda.synchronize()
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        peak = torch.cuda.max_memory_allocated() / 2 ** 30 if cuda else None
+        last = float(loss.detach())
+        del model, opt, batches, loss, out
+        if cuda:
+            torch.cuda.empty_cache()
+        return times, last, peak
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
 def cpu_train_steps(workload, sample, steps, warmup, threads):
-    """The reference's algorithm (oracle/vqa_oracle.py restatement, PyTorch CPU, autograd) on the host cores."""
+    """-> (times, last loss, kind).  kind "reference": the unmodified reference on the host cores (baseline/_ref);
+    kind "port": the oracle restatement of its algorithm (oracle/vqa_oracle.py, PyTorch CPU autograd) when no install is present."""
+    r = reference_train_steps(workload, sample, steps, warmup, "cpu", threads=threads)
+    if r is not None:
+        return r[0], r[1], "reference"
     from oracle import vqa_oracle as O
     from vqa_b200.synthetic import make_batch
     torch.set_num_threads(threads)
@@ -84,7 +167,7 @@ def cpu_train_steps(workload, sample, steps, warmup, threads):
         opt.step()
         if it >= warmup:
             times.append(time.perf_counter() - t0)
-    return times, float(loss.detach())
+    return times, float(loss.detach()), "port"
 
 
 def run_reference(args, workload):
@@ -92,16 +175,18 @@ def run_reference(args, workload):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    times, _ = cpu_train_steps(workload, args.cpu_sample, args.steps, args.warmup, cores)
+    times, _, kind = cpu_train_steps(workload, args.cpu_sample, args.steps, args.warmup, cores)
     total = sum(times)
     value = args.cpu_sample * len(times) / total
-    sample = f"{args.cpu_sample} of {workload.batch} questions per step, {len(times)} steps, PyTorch CPU autograd through oracle/vqa_oracle.py"
+    how = ("the unmodified reference (baseline/_ref: sparse_graph_model.Model + nn.MultiLabelSoftMarginLoss + Adam, run.py:425-460 loop body), PyTorch CPU"
+           if kind == "reference" else "PyTorch CPU autograd through oracle/vqa_oracle.py (no reference install present)")
+    sample = f"{args.cpu_sample} of {workload.batch} questions per step, {len(times)} steps, {how}"
     line = {
         "impl": "reference", "metric": "train questions/sec (fwd+bwd)", "value": round(value, 3), "unit": "questions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * total / len(times), 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(workload, args, 1) | {"cpu_sample_batch": args.cpu_sample},
-        "cpu_baseline": {"value": round(value, 3), "unit": "questions/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": round(value, 3), "unit": "questions/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": round(value, 3), "unit": "questions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -115,7 +200,9 @@ def config_dict(w, args, world):
             "global_batch": w.batch * world, "step": "zero_grad+forward+MultiLabelSoftMarginLoss+backward+allreduce+Adam (" + ("criterion and Adam as single kernels of libvqa_sm100.so" if args.tail == "fused" else "torch criterion and fused Adam") + "), " + ("eager launches" if args.no_graph else "one CUDA-graph replay per step (vqa_b200.engine.TrainStep)"),
             "parallelism": f"dp{world}", "gru": "padded masked recurrence on split-bf16 x3 tcgen05 GEMMs (fp32-grade)", "gemm_precision": {"fp32": "split-bf16 x3 passes (fp32-grade, rel err ~1e-5)", "fp32_strict": "split-bf16 x3 passes + chunk-promoted 3xTF32 graph-learner forward",
                                    "bf16": "bf16 x1 pass (graph-learner forward x3 passes)"}[args.precision],
-            "l2_policy": "inputs larger than L2 (image batch 151 MB > 126 MB), 3 rotating batches"}
+            "l2_policy": f"inputs larger than L2 (image batch {w.batch * w.n_obj * w.feat_dim * 4 / 1e6:.0f} MB > 126 MB), 3 rotating batches"
+                         if w.batch * w.n_obj * w.feat_dim * 4 > 126e6 else
+                         f"3 rotating batches ({3 * w.batch * w.n_obj * w.feat_dim * 4 / 1e6:.0f} MB) + the step's own ~1 GB of activations and 0.8 GB of optimizer traffic between two uses of any input"}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -302,6 +389,24 @@ def run_b200(args, workload):
     _dbg(f"e2e loop done: {ms_e2e:.3f} ms/step")
     e2e_value = w.batch * world / (ms_e2e * 1e-3)
 
+    # ---- what the host link can deliver: every rank copies its pinned image batch to its GPU at the same time, nothing else running
+    probe = torch.empty_like(step.slots[0]["image"])
+    for _ in range(2):
+        probe.copy_(host[0]["image"], non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(10):
+        probe.copy_(host[i % NB]["image"], non_blocking=True)
+    e1.record()
+    barrier()
+    ms_copy = max_over_ranks(e0.elapsed_time(e1)) / 10
+    img_bytes = probe.numel() * 4
+    h2d_link = {"GB/s_per_gpu_all_ranks_copying": round(img_bytes / (ms_copy * 1e-3) / 1e9, 1), "copy_ms_of_one_image_batch": round(ms_copy, 3),
+                "bytes": img_bytes, "ranks_copying_at_once": world,
+                "note": "pinned host -> device, one cudaMemcpyAsync per batch, slowest rank; a step cannot be shorter end to end than this copy when the batch comes from the host"}
+    del probe
+
     # ---- end to end with the feature table RESIDENT in HBM (vqa_b200.shards.ShardLoader): the same three batches written as one
     # shard directory; every step the host sends row indices, tokens and CSR answer triplets (a few hundred KB) and two kernels
     # assemble the batch on the device; loss read back every step.  Reported next to "e2e", never instead of it. ----------------
@@ -400,6 +505,7 @@ def run_b200(args, workload):
     kn.enable_timing(GC, ADJ, "vqa_graphconv_mma_fwd", "vqa_graphconv_mma_pool_fwd", "vqa_graphconv_mma_bwd_data", "vqa_graphconv_mma_bwd_edges",
                      "vqa_adjacency_topk_bwd_f32", "vqa_gemm_bf16s")
     spin = int(10e-3 * getattr(torch.cuda.get_device_properties(local), "clock_rate", 1.9e6) * 1e3)   # ~10 ms of SM clock
+    kn.GEMM_LOG = []
     for i in range(6):
         # the host needs ~5 ms to enqueue one eager step: let it run ahead of the GPU behind a spin kernel, so that every
         # bracketed launch starts the moment its predecessor ends and the events see device time only, no launch gaps
@@ -408,6 +514,7 @@ def run_b200(args, workload):
         eager(*(resident[i % NB][k] for k in keys))
     torch.cuda.synchronize()
     timers = {k: [a.elapsed_time(b) for a, b in v] for k, v in kn.TIMERS.items()}
+    gemm_log, kn.GEMM_LOG = kn.GEMM_LOG, None
     kn.enable_timing()
     _dbg("eager timing pass done")
     barrier()
@@ -442,7 +549,7 @@ def run_b200(args, workload):
     if gc_ms:
         ach = gc_bytes / (gc_ms * 1e-3) / 1e9
         roof = {"kernel": gc_name + " (layer 1: Gaussian weights on selected edges + neighbourhood aggregate + ReLU + dropout)", "bound": "hbm",
-                "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "traffic": NCU_TRAFFIC.get(gc_name),
+                "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(ach / hbm_peak, 4), "traffic": NCU_TRAFFIC.get((w.name, gc_name)),
                 "algorithmic_bytes": gc_bytes, "us_per_launch": round(gc_ms * 1e3, 2), "peak_source": peak_src,
                 "timed": "CUDA events on the launching stream in an eager pass of the same step, enqueued behind a spin kernel so no host launch gap is inside the bracket (launches inside a graph replay cannot be bracketed)"}
     alg = {ADJ: Mrows * 512 * 4 + Mrows * K * 4 + 2 * Mrows * nb * 4,
@@ -460,30 +567,73 @@ def run_b200(args, workload):
     # dense projections: total tensor-core time and rate of the split-bf16 GEMMs in one step
     gm = timers.get("vqa_gemm_bf16s", [])
     roof_gemm = None
+    ceiling = None
     if gm:
         per_step = sum(gm) / 6.0                                             # 6 timed eager steps
         passes = 1 if args.precision == "bf16" else 3
-        roof_gemm = {"kernel": "gemm_bf16s_kernel (all dense projections of one step, event-bracketed launches incl. gaps)", "bound": "tensor",
-                     "ms_per_step": round(per_step, 3), "launches_per_step": len(gm) // 6, "passes": passes,
-                     "peak": tf_peak, "unit": "TFLOP/s (bf16 sustained, measured)" if peak_src == "measured" else "TFLOP/s (fallback)"}
+        # FLOPs of the products actually issued (kernels.GEMM_LOG: M, N, K, passes per launch).  Row-gated products (the padded GRU
+        # recurrence) skip the 128-row tiles whose questions have all ended: counted by the tiles alive at that step.
+        qh = [sorted((int(x) for x in hb["qlen"]), reverse=True) for hb in host]
+        def alive_rows(t):                                                   # rows of tiles with a question longer than t (batches are length-sorted)
+            n = [sum(128 for r0 in range(0, len(q), 128) if q[r0] > t) for q in qh]
+            return sum(n) / len(n)
+        raw = useful = 0.0
+        for (M_, N_, K_, ps, gate) in gemm_log:
+            rows = M_ if gate is None else min(M_, alive_rows(gate))
+            useful += 2.0 * rows * N_ * K_
+            raw += 2.0 * rows * N_ * K_ * ps
+        raw, useful = raw / 6.0, useful / 6.0
+        ach_tf = raw / (per_step * 1e-3) / 1e12
+        roof_gemm = {"kernel": "gemm_bf16s_kernel / gemm_bf16s_persistent_kernel (all dense projections of one step, event-bracketed launches incl. gaps)",
+                     "bound": "tensor", "ms_per_step": round(per_step, 3), "launches_per_step": len(gm) // 6, "passes": passes,
+                     "useful_tflop_per_step": round(useful / 1e12, 4), "mma_tflop_per_step": round(raw / 1e12, 4),
+                     "achieved": round(ach_tf, 1), "achieved_useful": round(useful / (per_step * 1e-3) / 1e12, 1),
+                     "peak": tf_peak, "frac": round(ach_tf / tf_peak, 4),
+                     "unit": "TFLOP/s (bf16 MMA rate incl. the 3 passes; peak = bf16 sustained, measured)" if peak_src == "measured" else "TFLOP/s (fallback peak)"}
+        # questions/s against the tensor-core ceiling: every required product once, in bf16, at the sustained peak
+        ceil_qps = tf_peak * 1e12 / (useful / B)
+        ceiling = {"ceiling_questions_per_s_per_gpu": round(ceil_qps, 0), "useful_gflop_per_question": round(useful / B / 1e9, 3),
+                   "frac": round(value / world / ceil_qps, 4),
+                   "note": "value per GPU / (measured sustained bf16 peak / dense FLOPs one question needs, forward + backward); the fp32-grade mode issues every product 3 times"}
     cpu = None
     if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only
         from vqa_b200.synthetic import WORKLOADS
         cores = os.cpu_count() or 1
-        t, _ = cpu_train_steps(WORKLOADS["vqa2_b64"], args.cpu_sample, 20, 2, cores)      # ~10 s of host work on the 16-core boxes
+        t, _, kind = cpu_train_steps(WORKLOADS["vqa2_b64"], args.cpu_sample, 8, 2, cores)      # ~20 s of host work on the 16-core boxes
         v = args.cpu_sample * len(t) / sum(t)
-        cpu = {"value": round(v, 3), "unit": "questions/s", "cores": cores, "kind": "port",
-               "sample": f"{len(t)} train steps of {args.cpu_sample} questions (BASELINE config[0] shapes), oracle port, PyTorch CPU"}
+        cpu = {"value": round(v, 3), "unit": "questions/s", "cores": cores, "kind": kind,
+               "sample": f"{len(t)} train steps of {args.cpu_sample} questions (BASELINE config[0] shapes), "
+                         + ("the unmodified reference from baseline/_ref, PyTorch CPU" if kind == "reference" else "oracle port, PyTorch CPU")}
+    # the reference in eager PyTorch CUDA on this same GPU (SURVEY.md 8d "same-box competitor"): its own Model / criterion / Adam at the
+    # bench batch, fp32 matmuls and with TF32 allowed; CUDA-synchronised wall clock per step
+    eager = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            del resident
+            torch.cuda.empty_cache()
+            e32 = reference_train_steps(w, w.batch, 10, 3, dev)
+            if e32 is not None:
+                etf = reference_train_steps(w, w.batch, 10, 3, dev, tf32=True)
+                m32, mtf = sorted(e32[0])[len(e32[0]) // 2], sorted(etf[0])[len(etf[0]) // 2]
+                eager = {"fp32": {"ms_per_step": round(m32 * 1e3, 2), "questions_per_s": round(w.batch / m32, 1)},
+                         "tf32": {"ms_per_step": round(mtf * 1e3, 2), "questions_per_s": round(w.batch / mtf, 1)},
+                         "peak_memory_GB": round(e32[2], 1), "batch": w.batch, "speedup_vs_fp32": round(value / (w.batch / m32), 2),
+                         "speedup_vs_tf32": round(value / (w.batch / mtf), 2),
+                         "what": "the unmodified reference (baseline/_ref) in eager PyTorch CUDA on the same B200: Model.forward + MultiLabelSoftMarginLoss + backward + Adam, "
+                                 "same workload and batch, median of 10 synchronised steps after 3 warm-up"}
+        except Exception as e:            # e.g. out of memory on a large workload: report, never fail the bench line
+            eager = {"error": repr(e)[:300]}
 
     line = {
         "metric": "train questions/sec (fwd+bwd)", "value": round(value, 1), "unit": "questions/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": config_dict(w, args, world),
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32 (split-bf16 x3 tensor-core products, fp32 accumulate)",
+        "data": "synthetic", "config": config_dict(w, args, world),
         "e2e": {"value": round(e2e_value, 1), "unit": "questions/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                "ms_per_step": round(ms_e2e, 4), "last_loss": last_loss},
+                "ms_per_step": round(ms_e2e, 4), "last_loss": last_loss, "h2d_link": h2d_link},
         "gpu_launches": int(launches),
-        "roofline": roof, "roofline_other_kernels": extra, "roofline_gemm": roof_gemm, "cpu_baseline": cpu,
+        "roofline": roof, "roofline_other_kernels": extra, "roofline_gemm": roof_gemm, "tensor_ceiling": ceiling, "cpu_baseline": cpu,
+        "gpu_eager_baseline": eager,
         "clocks": sampler.summary(), "final_loss": final_loss, "bf16_mode": bf16_mode,
         "e2e_resident_table": e2e_table,
     }
@@ -492,12 +642,191 @@ def run_b200(args, workload):
     leave()
 
 
+def run_eval(args, workload):
+    """BASELINE.json configs[4]: the inference sweep of run.py::test (`run.py:274-341`) - model.eval(), no_grad, B=4096 questions over
+    K=100 boxes, top-k=32 - forward only.  Replicas only at N > 1 (no collective: SURVEY.md 8e).  value = questions/s with the batch
+    resident in HBM; e2e = pinned host batch copied every step + the predicted answer ids read back (what the driver's loop consumes)."""
+    import torch.distributed as dist
+    from vqa_b200 import kernels as kn, ops
+    from vqa_b200.synthetic import make_batch, make_wemb
+    import sparse_graph_model as M
+
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the vqa_b200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ops.set_precision(args.precision)
+    w = workload
+    torch.manual_seed(1000)
+    model = M.Model(pretrained_wemb=make_wemb(w), **w.model_kwargs()).to(dev).eval()
+    model.max_question_len = w.max_qlen
+    NB = 2
+    host = []
+    for i in range(NB):
+        b = make_batch(w, seed=1000 + 17 * rank + i)
+        host.append({"question": b["question"].pin_memory(), "image": b["image"].pin_memory(), "K": b["K"].pin_memory(),
+                     "qlen": torch.tensor([int(x) for x in b["qlen"]], dtype=torch.int32).pin_memory()})
+    resident = [{k: v.to(dev, non_blocking=True) for k, v in b.items()} for b in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return ms
+
+    def fwd(b):
+        with torch.no_grad():
+            logits, adj, arg = model(b["question"], b["image"], b["K"], b["qlen"])
+        return logits
+
+    n0 = kn.LAUNCHES
+    fwd(resident[0])
+    launches = kn.LAUNCHES - n0
+    for i in range(max(args.warmup, 3)):
+        fwd(resident[i % NB])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        logits = fwd(resident[i % NB])
+    e1.record()
+    barrier()
+    ms_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    sampler.stop_flag = True
+    value = w.batch * world / (ms_step * 1e-3)
+
+    # end to end: double-buffered device slots, the copy of batch i+1 overlaps the forward of batch i, predictions read back every step
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [{k: torch.empty_like(v) for k, v in resident[0].items()} for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    pred_host = [torch.empty(w.batch, dtype=torch.int64).pin_memory() for _ in range(2)]
+    pred_ev = [torch.cuda.Event() for _ in range(2)]
+
+    def stage(i):
+        s = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[s])
+            for k, v in host[i % NB].items():
+                slots[s][k].copy_(v, non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_loop(n):
+        for s in range(2):
+            freed[s].record()
+        stage(0)
+        for i in range(n):
+            s = i & 1
+            torch.cuda.current_stream().wait_event(ready[s])
+            if i + 1 < n:
+                stage(i + 1)
+            lg = fwd(slots[s])
+            freed[s].record()
+            pred_host[s].copy_(lg.argmax(dim=1), non_blocking=True)
+            pred_ev[s].record()
+            if i > 0:
+                pred_ev[(i - 1) & 1].synchronize()
+        pred_ev[(n - 1) & 1].synchronize()
+        return int(pred_host[(n - 1) & 1][0])
+
+    e2e_loop(3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_loop(args.steps)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+
+    # per-kernel event times (eager launches, behind a spin kernel so the host is never inside a bracket)
+    names = ("vqa_adjacency_topk_fwd_f32", "vqa_graphconv_mma_fwd", "vqa_graphconv_mma_pool_fwd", "vqa_gemm_bf16s")
+    kn.enable_timing(*names)
+    kn.GEMM_LOG = []
+    spin = int(20e-3 * getattr(torch.cuda.get_device_properties(local), "clock_rate", 1.9e6) * 1e3)
+    for i in range(4):
+        torch.cuda.synchronize()
+        torch.cuda._sleep(spin)
+        fwd(resident[i % NB])
+    torch.cuda.synchronize()
+    timers = {k: [a.elapsed_time(b) for a, b in v] for k, v in kn.TIMERS.items()}
+    gemm_log, kn.GEMM_LOG = kn.GEMM_LOG, None
+    kn.enable_timing()
+    barrier()
+    if rank != 0:
+        if world > 1:
+            barrier()
+            os._exit(0)
+        return
+    hbm_peak, tf_peak, peak_src = peaks()
+    B, K, nb, H = w.batch, w.n_obj, w.neighbourhood, w.hid_dim
+    Mrows = B * K
+    med = lambda xs: sorted(xs)[len(xs) // 2] if xs else None
+    alg = {"vqa_graphconv_mma_fwd": 2 * Mrows * 2 * H * 4 + 2 * Mrows * nb * 4 + Mrows * 16,
+           "vqa_graphconv_mma_pool_fwd": Mrows * H * 4 + Mrows * nb * 4 + Mrows * 16 + 4 * B * H * 4,
+           "vqa_adjacency_topk_fwd_f32": Mrows * 512 * 4 + Mrows * K * 4 + 2 * Mrows * nb * 4}
+    per = {}
+    for k, nbytes in alg.items():
+        m = med(timers.get(k, []))
+        if m:
+            per[k] = {"us": round(m * 1e3, 1), "GB/s": round(nbytes / (m * 1e-3) / 1e9, 1), "frac": round(nbytes / (m * 1e-3) / 1e9 / hbm_peak, 4),
+                      "algorithmic_bytes": nbytes}
+    gc = per.get("vqa_graphconv_mma_fwd")
+    roof = None
+    if gc:
+        roof = {"kernel": "vqa_graphconv_mma_fwd (layer 1 aggregate at K=100, nb=32)", "bound": "hbm", "achieved": gc["GB/s"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": gc["frac"], "traffic": NCU_TRAFFIC.get((w.name, "vqa_graphconv_mma_fwd")), "algorithmic_bytes": gc["algorithmic_bytes"],
+                "us_per_launch": gc["us"], "peak_source": peak_src}
+    gm = timers.get("vqa_gemm_bf16s", [])
+    roof_gemm = None
+    if gm:
+        per_step = sum(gm) / 4.0
+        useful = sum(2.0 * m_ * n_ * k_ for (m_, n_, k_, ps, g) in gemm_log) / 4.0
+        raw = sum(2.0 * m_ * n_ * k_ * ps for (m_, n_, k_, ps, g) in gemm_log) / 4.0
+        roof_gemm = {"bound": "tensor", "ms_per_step": round(per_step, 3), "launches_per_step": len(gm) // 4, "mma_tflop_per_step": round(raw / 1e12, 3),
+                     "achieved": round(raw / (per_step * 1e-3) / 1e12, 1), "peak": tf_peak, "frac": round(raw / (per_step * 1e-3) / 1e12 / tf_peak, 4),
+                     "unit": "TFLOP/s (bf16 MMA rate incl. passes; GRU row gating not subtracted)",
+                     "tensor_ceiling_frac": round(value / world / (tf_peak * 1e12 / (useful / B)), 4)}
+    line = {"metric": "eval questions/sec (forward only)", "value": round(value, 1), "unit": "questions/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32 (split-bf16 x3 tensor-core products, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": f"{w.name}: inference sweep, model.eval(), per-GPU batch {w.batch}, K={w.n_obj} boxes x {w.feat_dim}-d, top-k={w.neighbourhood}, "
+                                   f"{w.n_kernels} Gaussian kernels, {w.out_dim} answers (BASELINE.json configs[4])",
+                       "global_batch": w.batch * world, "step": "Model.forward under no_grad, eager launches", "parallelism": f"replicas x{world}",
+                       "l2_policy": f"inputs larger than L2 (image batch {B * K * w.feat_dim * 4 / 1e9:.2f} GB), 2 rotating batches"},
+            "e2e": {"value": round(w.batch * world / (ms_e2e * 1e-3), 1), "unit": "questions/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": w.batch * 8,
+                    "ms_per_step": round(ms_e2e, 3)},
+            "gpu_launches": int(launches), "roofline": roof, "roofline_other_kernels": per, "roofline_gemm": roof_gemm, "cpu_baseline": None,
+            "clocks": sampler.summary()}
+    print(json.dumps(line), file=json_out, flush=True)
+    if world > 1:
+        barrier()
+        os._exit(0)
+
+
 def main():
     args = parse()
     from vqa_b200.synthetic import WORKLOADS
     workload = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, workload)
+    elif workload.name.startswith("eval"):
+        run_eval(args, workload)
     else:
         run_b200(args, workload)
 

@@ -201,9 +201,10 @@ int vqa_gaussian_weights_f32(const float* pseudo, const float* gauss, float* w, 
  * The recurrence runs over padded time-major steps; a sequence past its length keeps its state, which equals the
  * packed-sequence result.  The matrix products (x W_ih^T for all steps, h W_hh^T per step, and the backward
  * products) are vqa_gemm_bf16s calls; these entry points are the gather/scatter and the pointwise cell. */
-/* E[(t*B + b), :] = W[question[b,t], :] written as split planes (rows time-major), t < T. */
+/* E[(t*B + b), :] = W[question[b,t], :] written as split planes (rows time-major), t < T.  A token outside [0, vocab) - for
+ * which nn.Embedding raises - sets bit 0 of *err (device int, optional) and reads row 0; the host raises at its next sync point. */
 int vqa_embed_gather_split(const long long* question, long long ldq, const float* W, long long vocab, int emb, void* hi,
-                           void* lo, long long ldp, int B, int T, vqa_stream_t stream);
+                           void* lo, long long ldp, int B, int T, int* err, vqa_stream_t stream);
 /* dW[question[b,t], :] += dE[(t*B + b), :] for t < len[b]  (fp32 atomics; dW pre-zeroed / accumulated by the caller). */
 int vqa_embed_scatter_add_f32(const float* dE, long long ldd, const long long* question, long long ldq, const int* len,
                               float* dW, long long vocab, int emb, int B, int T, vqa_stream_t stream);

@@ -111,6 +111,54 @@ def main():
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **out)
         print(f"{name}: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB), loss={loss.item():.6f}")
+    topk_fixtures(ref_model)
+    score_fixture()
+
+
+def topk_fixtures(ref_model):
+    """Adjacency matrices produced by the unmodified reference at the node counts of BASELINE configs[3] / configs[4]
+    (K=51 / nb=19 and K=100 / nb=32; narrow feature widths keep the files small) with the neighbour sets and softmax
+    weights the reference derives from them (sparse_graph_model.py:225-227).  north_star: top-k indices bit-exact
+    GIVEN the reference's adjacency."""
+    from vqa_b200.synthetic import Workload
+    for name, K, nb in (("topk_k51", 51, 19), ("topk_k100", 100, 32)):
+        w = Workload(name, 3, K, 36, hid_dim=32, emb_dim=16, out_dim=24, vocab=60, n_kernels=4, neighbourhood=nb,
+                     max_qlen=6, q_width=8, dropout=0.0)
+        torch.manual_seed(1000)
+        model = ref_model.Model(pretrained_wemb=make_wemb(w), **w.model_kwargs()).train()
+        batch = make_batch(w, seed=1000)
+        _, adj, _ = model(batch["question"], batch["image"], batch["K"], batch["qlen"])
+        adj = adj.detach()
+        vals, idx = torch.topk(adj, k=nb, dim=-1, sorted=False)
+        alpha = torch.softmax(vals, dim=-1)
+        order = idx.argsort(dim=-1)
+        srt = adj.sort(dim=-1, descending=True).values
+        out = {"out.adjacency": adj.numpy(), "nbr.idx_sorted": torch.gather(idx, -1, order).numpy(),
+               "nbr.alpha_sorted": torch.gather(alpha, -1, order).numpy(), "nbr.margin": (srt[..., nb - 1] - srt[..., nb]).numpy()}
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: wrote {path} ({os.path.getsize(path) / 1e3:.1f} kB), min margin {out['nbr.margin'].min():.3e}")
+
+
+def score_fixture():
+    """Known answers of the reference's own ``utils.total_vqa_score`` (utils.py:47-55) on seeded logits / vote counts."""
+    import json
+    sys.path.insert(0, REF)
+    sys.modules.pop("utils", None)
+    import utils as ref_utils
+    assert ref_utils.__file__.startswith(REF)
+    sys.path.remove(REF)
+    sys.modules.pop("utils", None)
+    cases = []
+    for seed, (b, a) in enumerate([(7, 24), (64, 3000), (512, 512), (1, 5)]):
+        g = torch.Generator().manual_seed(seed)
+        logits = torch.randn(b, a, generator=g)
+        votes = torch.randint(0, 11, (b, a), generator=g).float() * (torch.rand(b, a, generator=g) < 0.3)
+        votes[torch.arange(b), logits.argmax(1)] = torch.randint(0, 11, (b,), generator=g).float()   # make the selected entries non-trivial
+        cases.append({"seed": seed, "batch": b, "answers": a, "score": float(ref_utils.total_vqa_score(logits, votes))})
+    with open(os.path.join(HERE, "score_kat.json"), "w") as f:
+        json.dump({"generator": "tests/golden/make_golden.py::score_fixture", "cases": cases}, f, indent=1)
+    print("score_kat.json:", cases)
 
 
 if __name__ == "__main__":

@@ -81,7 +81,9 @@ def test_reducer_single_process_keeps_views_and_zeroes():
     # default step start: gradients dropped, nothing zeroed; a gradient produced outside the sink is moved into its view
     red.zero_grad()
     assert all(p.grad is None for p in net.parameters())
-    assert red.sink(w) is not None and red.sink(w).data_ptr() == red.flat.data_ptr() + w._vqa_flat_off * 4
+    v = red.sink(w)
+    assert v is not None and v.data_ptr() == red.flat.data_ptr() + w._vqa_flat_off * 4
+    red.zero_grad()                                       # (a view is handed out once per step; start the step again)
     x = torch.randn(3, 5)
     net(x).sum().backward()
     red.finish()
@@ -189,4 +191,83 @@ def test_reducer_average_flag_leaves_the_sum_for_an_optimiser_that_scales_itself
     red.average = True
     red.finish()
     assert torch.allclose(red.flat, before * 0.5)
+    red.remove()
+
+
+def _accum_worker(rank, world, port, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "vqa-project_b200")]
+    from vqa_b200.ddp import GradReducer, broadcast_parameters
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)
+    net = torch.nn.Sequential(torch.nn.Linear(20, 33), torch.nn.ReLU(), torch.nn.Linear(33, 3))
+    broadcast_parameters(net)
+    red = GradReducer(net.parameters(), bucket_bytes=1024)
+    torch.manual_seed(7)
+    x_all, y_all = torch.randn(4 * world, 20), torch.randn(4 * world, 3)
+    xs, ys = x_all[rank * 4:(rank + 1) * 4], y_all[rank * 4:(rank + 1) * 4]
+    red.zero_grad(set_to_none=False)                   # accumulation over two micro-batches of 2
+    launched0 = red.launched
+    for m in range(2):
+        (((net(xs[2 * m:2 * m + 2]) - ys[2 * m:2 * m + 2]) ** 2).sum() / (4 * 3)).backward()
+        assert red.launched == launched0               # nothing is reduced before finish()
+    red.finish()
+    assert red.launched - launched0 == len(red.bucket_size)
+    torch.manual_seed(100)
+    ref = torch.nn.Sequential(torch.nn.Linear(20, 33), torch.nn.ReLU(), torch.nn.Linear(33, 3))
+    (((ref(x_all) - y_all) ** 2).sum() / (4 * world * 3)).backward()
+    err = max((a.grad - b.grad).abs().max().item() for a, b in zip(net.parameters(), ref.parameters()))
+    q.put((rank, err))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_accumulation_reduces_once_in_finish():
+    """zero_grad(set_to_none=False) + two backwards per step at world 2: the averaged gradient equals the single-process gradient of
+    the concatenated batch (a bucket reduced after the FIRST backward would miss the second micro-batch and race it)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_accum_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err in res:
+        assert err < 1e-6, (rank, err)
+
+
+def test_sink_hands_a_view_out_once_per_step_so_shared_parameters_sum_correctly():
+    """A parameter feeding two autograd nodes (the model called twice before one backward): the second node must not get an aliasing
+    view of the same memory - autograd would add two views of one buffer and produce 2 * g_last instead of g_a + g_b."""
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "vqa-project_b200")]
+    from vqa_b200.ddp import GradReducer
+    lin = torch.nn.Linear(4, 5, bias=False)
+    red = GradReducer(lin.parameters())
+
+    class F(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w):
+            ctx.save_for_backward(x, w)
+            return x @ w.t()
+
+        @staticmethod
+        def backward(ctx, g):
+            x, w = ctx.saved_tensors
+            out = red.sink(w)
+            if out is None:
+                out = torch.empty_like(w)
+            torch.mm(g.t(), x, out=out)
+            return None, out
+
+    xa, xb = torch.randn(3, 4), torch.randn(6, 4)
+    red.zero_grad()
+    (F.apply(xa, lin.weight).sum() + 2.0 * F.apply(xb, lin.weight).sum()).backward()
+    red.finish()
+    want = torch.ones(3, 5).t() @ xa + 2.0 * torch.ones(6, 5).t() @ xb
+    assert torch.allclose(lin.weight.grad, want, atol=1e-6)
+    assert lin.weight.grad.data_ptr() == red.flat.data_ptr() + lin.weight._vqa_flat_off * 4
+    red.zero_grad()
+    assert red.sink(lin.weight) is not None and red.sink(lin.weight) is None       # once per step
     red.remove()

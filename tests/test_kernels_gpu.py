@@ -638,3 +638,22 @@ def test_graphconv_argument_errors(kn):
         kn.graphconv_fwd(torch.randn(24, 24, device=DEV), idx.int().to(DEV), None, image.float().to(DEV), gauss, 2, 12)
     with pytest.raises(RuntimeError):   # nb > K
         kn.topk_softmax(torch.randn(1, 4, 4, device=DEV), 5)
+
+
+def test_out_of_range_token_is_flagged_like_nn_embedding(kn):
+    """nn.Embedding raises on a token id outside the table (reference sparse_graph_model.py:117); the gather kernel never reads out of
+    range, sets a device error bit instead, and the host raises IndexError at its next sync point (kernels.check_device_errors)."""
+    wemb = torch.randn(50, 24, device=DEV)
+    q = torch.randint(1, 50, (6, 9), device=DEV)
+    kn.embed_gather_split(q, wemb, 7)
+    kn.check_device_errors()                              # clean
+    q[2, 3] = 50
+    out = kn.embed_gather_split(q, wemb, 7)
+    assert torch.isfinite(out.float()).all()
+    with pytest.raises(IndexError):
+        kn.check_device_errors()
+    kn.check_device_errors()                              # the flag was cleared by the raise
+    q[2, 3] = -1
+    kn.embed_gather_split(q, wemb, 7)
+    with pytest.raises(IndexError):
+        kn.check_device_errors()

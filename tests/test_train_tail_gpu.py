@@ -165,3 +165,68 @@ def test_captured_step_with_fused_tail_matches_torch_tail():
         total += d.numel()
         off += int((d > 1e-4).sum())
     assert off <= 1e-3 * total, (off, total)
+
+
+def test_captured_step_follows_the_plain_loop_trajectory():
+    """TrainStep == the reference loop body run eagerly (run.py:425-460), update for update: the warm-up iterations before a capture
+    run on a snapshot (no hidden parameter / Adam-moment / step-count updates), a second batch shape captures once and is then
+    replayed from the cache, and a question longer than model.max_question_len is rejected instead of truncated."""
+    from vqa_b200.ddp import GradReducer
+    from vqa_b200.engine import TrainStep
+    from vqa_b200.loss import MultiLabelSoftMarginLoss
+    from vqa_b200.optim import FlatAdam
+    from vqa_b200.synthetic import WORKLOADS, make_batch, make_wemb
+    import sparse_graph_model as M
+    w = WORKLOADS["small"]
+    full = [make_batch(w, seed=60 + i) for i in range(2)]
+    short = make_batch(w, seed=70, batch=5)                       # the ragged last batch of an epoch
+    order = [full[0], full[1], short, full[0], short, full[1]]
+    runs = []
+    for mode in ("graph", "plain"):
+        torch.manual_seed(1000)
+        kw = w.model_kwargs()
+        kw["dropout"] = 0.0
+        model = M.Model(pretrained_wemb=make_wemb(w), **kw).to(DEV).train()
+        model.max_question_len = w.max_qlen
+        red = GradReducer(model.parameters())
+        crit, opt = MultiLabelSoftMarginLoss(), FlatAdam(red, lr=1e-3)
+        losses = []
+        if mode == "graph":
+            step = TrainStep(model, opt, crit, reducer=red, use_graph=True, seed=77)
+            for b in order:
+                losses.append(step(b["question"], b["image"], b["K"], b["qlen"], b["target"]).item())
+            assert len(step._cache) == 2                          # one capture per batch shape, however often the shape comes back
+            with pytest.raises(ValueError, match="max_question_len"):
+                b = dict(full[0]); b["qlen"] = [torch.tensor(w.max_qlen + 1)] + list(b["qlen"][1:])
+                step(b["question"], b["image"], b["K"], b["qlen"], b["target"])
+            step.close()
+        else:
+            qlen_t = lambda b: torch.tensor([int(x) for x in b["qlen"]], dtype=torch.int32, device=DEV)
+            for b in order:
+                red.zero_grad()
+                logits, _, _ = model(b["question"].to(DEV), b["image"].to(DEV), b["K"].to(DEV), qlen_t(b))
+                loss = crit(logits, b["target"].to(DEV))
+                loss.backward()
+                red.finish()
+                opt.step()
+                losses.append(loss.item())
+        torch.cuda.synchronize()
+        assert opt.steps_taken == len(order)                      # Adam's bias correction saw exactly the real steps
+        runs.append((losses, {k: v.detach().clone() for k, v in model.state_dict().items()}))
+        red.remove()
+    (lg, pg), (lp, pp) = runs
+    assert lg == pytest.approx(lp, rel=1e-6), (lg, lp)            # same kernels, same order: the first loss would already differ after a hidden update
+    for k in pp:
+        assert torch.allclose(pg[k], pp[k], rtol=0, atol=1e-6), k
+
+
+def test_train_step_requires_max_question_len():
+    from vqa_b200.engine import TrainStep
+    from vqa_b200.synthetic import WORKLOADS, make_batch, make_wemb
+    import sparse_graph_model as M
+    w = WORKLOADS["tiny"]
+    model = M.Model(pretrained_wemb=make_wemb(w), **w.model_kwargs()).to(DEV).train()
+    step = TrainStep(model, torch.optim.Adam(model.parameters()), torch.nn.MultiLabelSoftMarginLoss())
+    b = make_batch(w, seed=1)
+    with pytest.raises(ValueError, match="max_question_len"):
+        step(b["question"], b["image"], b["K"], b["qlen"], b["target"])

@@ -35,8 +35,24 @@ def test_total_vqa_score_equals_the_reference_loop():
 
 
 def test_shadow_module_reexports_the_reference_utils_when_it_is_on_the_path(tmp_path, monkeypatch):
-    (tmp_path / "utils.py").write_text("def total_vqa_score(a, b):\n    return -1\n\ndef save(args, model, path, name):\n    return 'ref-save'\n")
+    (tmp_path / "utils.py").write_text("def total_vqa_score(a, b):\n    return -1\n\ndef batch_to_cuda(batch):\n    return None\n\n"
+                                       "def save(args, model, path, name):\n    return 'ref-save'\n")
+    other = tmp_path / "other"
+    other.mkdir()
+    (other / "utils.py").write_text("raise SystemExit('an unrelated utils.py must never be executed')\n")
     monkeypatch.syspath_prepend(str(tmp_path))
+    monkeypatch.syspath_prepend(str(other))                                 # found first, skipped by its text, not run
     u = _load()
     assert u.save(None, None, None, None) == "ref-save"                     # re-exported
     assert u.total_vqa_score(torch.zeros(2, 3), torch.ones(2, 3) * 3) == 2.0   # replaced
+
+
+def test_shadow_module_fails_loudly_without_a_reference_utils(tmp_path, monkeypatch):
+    import pytest
+    spec = importlib.util.spec_from_file_location("vqa_dropin_utils_probe", os.path.join(ROOT, "vqa-project_b200", "utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    monkeypatch.setattr(sys, "path", [str(tmp_path)])
+    monkeypatch.setenv("VQA_REFERENCE_DIR", str(tmp_path))
+    monkeypatch.setattr(os.path, "isfile", lambda p: False)
+    with pytest.raises(ImportError):
+        spec.loader.exec_module(mod)

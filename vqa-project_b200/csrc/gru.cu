@@ -33,12 +33,15 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 __global__ void __launch_bounds__(256) embed_gather_split_kernel(const long long* __restrict__ question, long long ldq,
                                                                 const float* __restrict__ W, int emb, long long vocab,
                                                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                                                long long ldp, int B, int T) {
+                                                                long long ldp, int B, int T, int* __restrict__ err) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= T * B) return;
   const int t = row / B, b = row - t * B;
   long long tok = question[(long long)b * ldq + t];
-  if (tok < 0 || tok >= vocab) tok = 0;
+  if (tok < 0 || tok >= vocab) {            // nn.Embedding raises: flag it (the host raises at its next sync point), never read out of range
+    if (lane == 0 && err) atomicOr(err, 1);
+    tok = 0;
+  }
   const float* src = W + tok * emb;
   for (int c = lane * 4; c < (int)ldp; c += 128) {
     float v[4];
@@ -172,11 +175,11 @@ __global__ void __launch_bounds__(256) gru_cell_bwd_kernel(const float* __restri
 using namespace vqa;
 
 extern "C" int vqa_embed_gather_split(const long long* question, long long ldq, const float* W, long long vocab, int emb,
-                                      void* hi, void* lo, long long ldp, int B, int T, cudaStream_t stream) {
+                                      void* hi, void* lo, long long ldp, int B, int T, int* err, cudaStream_t stream) {
   VQA_CHECK_ARG(question && W && hi && B > 0 && T > 0 && emb > 0 && vocab > 0, "vqa_embed_gather_split: bad arguments");
   VQA_CHECK_ARG((ldp & 7) == 0 && ldp >= emb && aligned16(hi) && (!lo || aligned16(lo)), "vqa_embed_gather_split: planes need ld %% 8 == 0, ld >= emb");
   embed_gather_split_kernel<<<(T * B + 7) / 8, 256, 0, stream>>>(question, ldq, W, emb, vocab, reinterpret_cast<__nv_bfloat16*>(hi),
-                                                                reinterpret_cast<__nv_bfloat16*>(lo), ldp, B, T);
+                                                                reinterpret_cast<__nv_bfloat16*>(lo), ldp, B, T, err);
   VQA_LAUNCH_CHECK("embed_gather_split_kernel");
   return VQA_OK;
 }

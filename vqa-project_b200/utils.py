@@ -18,32 +18,49 @@ import sys
 import torch
 
 
-def _load_reference_utils():
+def _find_reference_utils():
+    """Path of the reference's own ``utils.py``: ``$VQA_REFERENCE_DIR``, else the first LATER ``sys.path`` entry whose ``utils.py``
+    defines both per-step functions (decided by reading the file - nothing is executed to find out), else the repo's
+    reference install ``baseline/_ref``."""
     here = os.path.dirname(os.path.abspath(__file__))
-    for d in sys.path:
-        cand = os.path.join(d or ".", "utils.py")
-        if os.path.isfile(cand) and os.path.abspath(os.path.dirname(cand)) != here:
-            spec = importlib.util.spec_from_file_location("_reference_utils", cand)
-            mod = importlib.util.module_from_spec(spec)
+    cands = [os.environ["VQA_REFERENCE_DIR"]] if os.environ.get("VQA_REFERENCE_DIR") else []
+    cands += [d or "." for d in sys.path] + [os.path.join(os.path.dirname(here), "baseline", "_ref")]
+    for d in cands:
+        cand = os.path.join(d, "utils.py")
+        if os.path.isfile(cand) and os.path.abspath(d) != here:
             try:
-                spec.loader.exec_module(mod)
-            except Exception:                 # not the reference's utils (or its imports are missing): keep looking
+                text = open(cand, encoding="utf-8", errors="replace").read()
+            except OSError:
                 continue
-            if hasattr(mod, "total_vqa_score"):
-                return mod
+            if "def total_vqa_score(" in text and "def batch_to_cuda(" in text:
+                return cand
     return None
 
 
+def _load_reference_utils():
+    cand = _find_reference_utils()
+    if cand is None:
+        raise ImportError("vqa-project_b200/utils.py shadows the reference's `utils` module and re-exports everything else it defines "
+                          "(save, xyxy2xywh, ...): put the reference checkout on sys.path behind vqa-project_b200, or set VQA_REFERENCE_DIR")
+    spec = importlib.util.spec_from_file_location("_reference_utils", cand)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)              # errors propagate: a half-imported reference module must not go unnoticed
+    return mod
+
+
 _ref = _load_reference_utils()
-if _ref is not None:
-    globals().update({k: v for k, v in vars(_ref).items() if not k.startswith("_")})
+globals().update({k: v for k, v in vars(_ref).items() if not k.startswith("_")})
 
 
 def total_vqa_score(logits, n_votes_batch):
     """Total VQA score of a batch as assessed by the challenge: sum_i min(n_votes[i, argmax_j logits[i, j]] / 3, 1)."""
     oix = logits.detach().argmax(dim=1, keepdim=True)
     votes = n_votes_batch.detach().gather(1, oix).squeeze(1).double()
-    return float((votes / 3.0).clamp_(max=1.0).sum())
+    score = float((votes / 3.0).clamp_(max=1.0).sum())        # the one read-back of the step: device-side error flags ride along
+    if logits.is_cuda:
+        from vqa_b200 import kernels
+        kernels.check_device_errors(logits.device)
+    return score
 
 
 def batch_to_cuda(batch, volatile=False):

@@ -54,7 +54,7 @@ SIGNATURES = {
     "vqa_graphconv_edge_blocks": [_i, _i, _i],
     "vqa_graphconv_edge_bwd_f32": [_p, _p, _p, _p, _ll, _p, _p, _p, _i, _i, _i, _i, _p],
     "vqa_gaussian_weights_f32": [_p, _p, _p, _ll, _i, _p],
-    "vqa_embed_gather_split": [_p, _ll, _p, _ll, _i, _p, _p, _ll, _i, _i, _p],
+    "vqa_embed_gather_split": [_p, _ll, _p, _ll, _i, _p, _p, _ll, _i, _i, _p, _p],
     "vqa_embed_scatter_add_f32": [_p, _ll, _p, _ll, _p, _p, _ll, _i, _i, _i, _p],
     "vqa_gru_cell_fwd_f32": [_p, _ll, _p, _p, _p, _p, _i, _p, _p, _p, _ll, _p, _i, _i, _p],
     "vqa_gru_step_fused": [_p, _p, _ll, _p, _p, _ll, _p, _ll, _p, _p, _p, _i, _p, _p, _p, _ll, _p, _p, _i, _i, _p],

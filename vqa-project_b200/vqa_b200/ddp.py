@@ -66,8 +66,11 @@ class GradReducer:
             p.grad = self._view(p)
         self._ready = [0] * len(self.bucket_size)
         self._done = [False] * len(self.params)           # counted towards its bucket in this step (by mark_ready or by the hook)
+        self._issued = [False] * len(self.params)         # sink() handed this parameter's view out in this step (at most once)
+        self._accumulating = False                        # zero_grad(set_to_none=False): several backwards per step, reduce in finish()
         self._index = {p.data_ptr(): i for i, p in enumerate(self.params)}
         self._handles = []
+        self._launched_now = [False] * len(self.bucket_size)
         self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
         self.launched = 0
         self.average = True                               # finish() scales by 1/world; optim.FlatAdam folds the factor into its pass instead
@@ -82,10 +85,17 @@ class GradReducer:
         return self.flat[p._vqa_flat_off:p._vqa_flat_off + p.numel()].view_as(p)
 
     def sink(self, t: torch.Tensor) -> Optional[torch.Tensor]:
-        """Destination for the gradient of the parameter whose storage ``t`` starts at (None if it is not one of ours)."""
-        p = self._by_ptr.get(t.data_ptr())
-        if p is None or p.shape != t.shape or p.grad is not None:      # accumulating into an existing .grad: autograd's job
+        """Destination for the gradient of the parameter whose storage ``t`` starts at (None if it is not one of ours).
+        Handed out AT MOST ONCE per parameter and step: when a parameter feeds two autograd nodes (the model called twice
+        before one backward), the second node gets None, computes into a tensor of its own, and autograd adds the two -
+        two aliasing views of the same memory would otherwise be overwritten by the later kernel and summed to 2 * g_last."""
+        i = self._index.get(t.data_ptr())
+        if i is None:
             return None
+        p = self.params[i]
+        if p.shape != t.shape or p.grad is not None or self._issued[i]:      # existing .grad: accumulation is autograd's job
+            return None
+        self._issued[i] = True
         return self._view(p)
 
     def _count(self, i: int) -> None:
@@ -94,7 +104,7 @@ class GradReducer:
         self._done[i] = True
         b = self.bucket_of[i]
         self._ready[b] += 1
-        if self._ready[b] == self.bucket_size[b]:
+        if self._ready[b] == self.bucket_size[b] and not self._accumulating:
             self._launch(b)
 
     def mark_ready(self, t: torch.Tensor) -> None:
@@ -102,7 +112,7 @@ class GradReducer:
         The fused operators are single autograd nodes: without this, the hooks of ALL their parameters would fire together when
         the node returns, and the classifier's 36 MB bucket could not start its all-reduce under the rest of backward."""
         i = self._index.get(t.data_ptr())
-        if i is not None and self.params[i].grad is None:  # (.grad exists: accumulation mode, the hook does the counting)
+        if i is not None and self.params[i].grad is None and not self._accumulating:  # (.grad exists: the hook does the counting)
             self._count(i)
 
     def _make_hook(self, i: int):
@@ -118,6 +128,7 @@ class GradReducer:
         return hook
 
     def _launch(self, b: int) -> None:
+        self._launched_now[b] = True
         if self.world > 1:
             h = dist.all_reduce(self.flat[self.bucket_slices[b]], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             self._handles.append(h)
@@ -125,7 +136,11 @@ class GradReducer:
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         """Start a step.  Default: drop every ``.grad`` (the step WRITES gradients into the flat buffer, nothing to zero).
-        ``set_to_none=False``: zero the flat buffer in one memset and (re)attach the views, for accumulation over micro-batches."""
+        ``set_to_none=False``: zero the flat buffer in one memset and (re)attach the views, for accumulation over micro-batches:
+        any number of backwards may follow, autograd adds into the views, and NO bucket is reduced before ``finish()`` (the
+        equivalent of DDP's ``no_sync`` for all but the last micro-batch - reducing after the first backward would race the
+        later additions and leave them un-reduced)."""
+        self._accumulating = not set_to_none
         if set_to_none:
             for p in self.params:
                 p.grad = None
@@ -136,12 +151,15 @@ class GradReducer:
                     p.grad = self._view(p)
         self._ready = [0] * len(self.bucket_size)
         self._done = [False] * len(self.params)
+        self._issued = [False] * len(self.params)
+        self._launched_now = [False] * len(self.bucket_size)
 
     def finish(self) -> None:
-        """Wait for the in-flight buckets (launching any whose parameters received no gradient) and average (unless
-        ``average`` was cleared by an optimiser that applies 1/world itself: the buffer then holds the SUM over ranks)."""
+        """Wait for the in-flight buckets (launching any that has not started: parameters without a gradient, or accumulation
+        mode) and average (unless ``average`` was cleared by an optimiser that applies 1/world itself: the buffer then holds the
+        SUM over ranks)."""
         for b in range(len(self.bucket_size)):
-            if self._ready[b] != self.bucket_size[b]:
+            if not self._launched_now[b]:
                 self._ready[b] = self.bucket_size[b]
                 self._launch(b)
         for h in self._handles:

@@ -15,6 +15,7 @@ from ._cabi import PREC_TF32, PREC_TF32X3, PREC_TF32X3_HP, GEMM_RELU, GEMM_ACCUM
 
 LAUNCHES = 0
 _LAUNCH_COST = {}          # every entry point is one launch (the column sum became a single kernel)
+GEMM_LOG = None            # list of (M, N, K, passes, row-gate step or None) per split-bf16 product while a caller (bench.py) collects it
 
 
 def _stream() -> int:
@@ -194,6 +195,8 @@ def gemm_s(a: SplitT, b: SplitT, *, a_mn: bool = False, b_mn: bool = False, out:
         raise RuntimeError(f"gemm_s: out_split has shape {out_split.shape}, expected {(M, N)}")
     ldrb = ldaux = ldauxh = 0
     aux_f = aux_h = None
+    if GEMM_LOG is not None:
+        GEMM_LOG.append((M, N, Ka, passes, None if row_gate is None else int(row_gate[1])))
     if rowbcast is not None:
         rowbcast, ldrb = _rows_view(_chk(rowbcast, "gemm_s rowbcast"), "gemm_s rowbcast")
     if isinstance(aux, SplitT):
@@ -256,8 +259,9 @@ _COLSUM_COUNTERS = {}
 
 
 def _colsum_counters(device: torch.device) -> torch.Tensor:
-    """Persistent zero-initialised ticket counters of the single-launch column sum (the kernel leaves them zero)."""
-    key = device.index if device.index is not None else torch.cuda.current_device()
+    """Persistent zero-initialised ticket counters of the single-launch column sum (the kernel leaves them zero).  One set per
+    (device, stream): launches on one stream are ordered, launches on different streams may overlap and must not share tickets."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
     buf = _COLSUM_COUNTERS.get(key)
     if buf is None:
         buf = _COLSUM_COUNTERS[key] = torch.zeros(4096, device=device, dtype=torch.int32)
@@ -488,6 +492,32 @@ def gaussian_weights(pseudo: torch.Tensor, gauss: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------- question encoder
+_ERR_WORDS = {}
+
+
+def device_error_word(device: torch.device) -> torch.Tensor:
+    """One int32 per device that kernels OR error bits into (bit 0: a token id outside the embedding table)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    w = _ERR_WORDS.get(key)
+    if w is None:
+        w = _ERR_WORDS[key] = torch.zeros(1, device=device, dtype=torch.int32)
+    return w
+
+
+def check_device_errors(device=None) -> None:
+    """Read the error words back (a sync point: call it where the host waits anyway, e.g. with the loss / score read-back) and raise
+    what the reference's modules would have raised at the offending call."""
+    for key, w in list(_ERR_WORDS.items()):
+        if device is not None and torch.device(device).index not in (None, key):
+            continue
+        e = int(w.item())
+        if e:
+            w.zero_()
+            if e & 1:
+                raise IndexError("vqa_b200: a question token id lies outside the embedding table (nn.Embedding raises 'index out of range' here)")
+            raise RuntimeError(f"vqa_b200: device error word {e:#x}")
+
+
 def embed_gather_split(question: torch.Tensor, wemb: torch.Tensor, T: int, with_lo: bool = True) -> SplitT:
     """question (B, >=T) int64, wemb (V, E) fp32 -> split planes of the time-major embeddings (T*B, E)."""
     if question.dtype != torch.int64 or not question.is_cuda or question.stride(1) != 1:
@@ -498,7 +528,7 @@ def embed_gather_split(question: torch.Tensor, wemb: torch.Tensor, T: int, with_
         raise RuntimeError(f"embed_gather_split: T={T} exceeds the question width {question.shape[1]}")
     out = empty_split(T * B, wemb.shape[1], wemb.device, with_lo)
     _call("vqa_embed_gather_split", question.data_ptr(), question.stride(0), wemb.data_ptr(), wemb.shape[0], wemb.shape[1],
-          out.hi.data_ptr(), _ptr(out.lo), out.ld, B, T, _stream())
+          out.hi.data_ptr(), _ptr(out.lo), out.ld, B, T, device_error_word(wemb.device).data_ptr(), _stream())
     return out
 
 
@@ -560,11 +590,17 @@ def gru_cell_bwd(dh, gates, h_prev, qlen, t, dgi, dgh, dgi_s: SplitT, dgh_s: Spl
 _LOSS_SCRATCH = {}
 
 
+_LOSS_SCRATCH_RETIRED = []      # outgrown buffers stay alive: a captured graph may still hold their addresses
+
+
 def _loss_scratch(device: torch.device, blocks: int):
-    key = device.index if device.index is not None else torch.cuda.current_device()
+    """Partial sums + ticket of the loss kernel, one set per (device, stream) (see _colsum_counters)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
     ent = _LOSS_SCRATCH.get(key)
     if ent is None or ent[0].numel() < blocks:
-        ent = _LOSS_SCRATCH[key] = (torch.empty(max(blocks, 1024), device=device, dtype=torch.float32),
+        if ent is not None:
+            _LOSS_SCRATCH_RETIRED.append(ent)
+        ent = _LOSS_SCRATCH[key] = (torch.empty(max(blocks, 4096), device=device, dtype=torch.float32),
                                     torch.zeros(1, device=device, dtype=torch.int32))
     return ent
 

@@ -206,6 +206,9 @@ class ConditionedGraphFn(torch.autograd.Function):
         B, K, F = image.shape
         H = qenc.shape[1]
         dev = image.device
+        if image.requires_grad:
+            raise RuntimeError("ConditionedGraphFn: image.requires_grad is set, but no gradient with respect to the image features is "
+                               "computed (the reference's data layer never asks for one: torch_dataset.py:157-164, utils.py:22-31)")
         image = image.contiguous()
         qenc = qenc.contiguous()
         drop = training and p_drop > 0.0
