@@ -25,7 +25,9 @@ def main():
     a = ap.parse_args()
     warnings.filterwarnings("ignore")
     import torch
-    torch.cuda.init()                       # run.py:33 rewrites CUDA_VISIBLE_DEVICES at import; the context exists by then
+    torch.cuda.init()                       # run.py:33 pins CUDA_VISIBLE_DEVICES='1' at import; the context exists by then ...
+    torch.cuda.device_count()
+    visible = os.environ.get("CUDA_VISIBLE_DEVICES")
     pkg = os.path.join(ROOT, "vqa-project_b200")
     sys.path[:0] = [os.path.join(HERE, "stubs")] + ([pkg] if a.impl == "b200" else []) + [a.ref]
     if a.impl == "reference":
@@ -41,6 +43,10 @@ def main():
     sys.argv = ["run.py", "--bsize", "8", "--ep", "1", "--hid", "512", "--emb", "32", "--n_obj", "36", "--neighbourhood_size", "16",
                 "--n_kernels", "4", "--dropout", a.dropout, "--save_dir", a.save_dir, "--log_interval", "1", "--model_path", "/nonexistent"]
     import run                              # the reference driver, unmodified
+    if visible is None:                     # ... and the caller's device selection is put back (a one-GPU box has no device 1:
+        os.environ.pop("CUDA_VISIBLE_DEVICES", None)   # torch.cuda.device_count() re-reads the variable and would report 0 devices)
+    else:
+        os.environ["CUDA_VISIBLE_DEVICES"] = visible
     import sparse_graph_model
     import layers
     import utils
