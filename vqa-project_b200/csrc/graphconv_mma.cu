@@ -470,6 +470,11 @@ struct Agg2Params {
   int B, K, KP, nb, nk, out_dim, D, nkc, tpk, slabs, nitems, nstage, nacc, ni, rpg, flags, with_lo;
   float drop_scale; unsigned drop_thresh16; unsigned long long seed, offset; const unsigned long long* step_ptr;
   int off_coef, coef_plane, coef_buf, off_stage, stage_bytes, off_out, out_plane, off_pool, off_bars, tmem_cols;
+  // Large node counts (K = 100: one coefficient buffer of one kernel is 57 KB, one input stage 57 KB, one output tile 51 KB): the
+  // plan with two coefficient buffers and separate output staging does not fit 227 KB.  cshift = 0: ONE coefficient buffer (the
+  // builders wait for the previous item's MMAs); alias = 1: the epilogue writes the output tile into the input stage its MMAs have
+  // just finished reading, the store warp hands the stage back to the producer once the TMA store has read it.
+  int cshift, alias;
 };
 
 __device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
@@ -582,14 +587,14 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
         if (++owner == p.ni) owner = 0;
       };
       for (int it = it0; it < it1; ++it, ++n) {
-        const int cb = n & 1;
+        const int cb = n & p.cshift;
         bool waited = false, mine = false;
         int kk = 0, tk = 0;                               // kernel of the item this tile belongs to
         for (int t = 0; t < tiles_per_item; ++t, ++g, next_tile()) {
           const int kcur = kk;
           if (++tk == p.tpk) { tk = 0; ++kk; }
           if (owner != me) continue;
-          if (!waited) { mbar_wait(&cfull[cb], (n >> 1) & 1); waited = true; }
+          if (!waited) { mbar_wait(&cfull[cb], (n >> p.cshift) & 1); waited = true; }
           mbar_wait(&tempty[acc], aph ^ 1);
           mbar_wait(&full[s], sph);
           tc_fence_after();
@@ -608,7 +613,7 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
               tc_mma<1>(d_tmem, dah, dbh, idesc, ks > 0 ? 1u : 0u);
             }
           }
-          tc_commit(&empty[s]);
+          if (!p.alias) tc_commit(&empty[s]);                       // (alias: the stage now receives the output tile; the store warp frees it)
           tc_commit(&tfull[acc]);
           mine = t + p.ni >= tiles_per_item;                        // my last tile of this item
           if (mine) tc_commit(&cempty[cb]);                          // coefficient buffer free once every issuer's MMAs of the item retire
@@ -627,13 +632,15 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
     constexpr bool RELU = MODE == AGG_FWD;                 // layer-1 forward always applies the ReLU (flags checked on the host)
     const uint32_t thresh_hi = p.drop_thresh16 << 16;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
-    int g = 0, acc = 0; uint32_t aph = 0;
+    int g = 0, acc = 0, sg = 0; uint32_t aph = 0;
     int b = it0 / p.slabs, sl = it0 - b * p.slabs;
     for (int it = it0; it < it1; ++it) {
       for (int t = 0; t < tiles_per_item; ++t, ++g) {
         const int buf = g & 1;
         const int col0 = (sl * tiles_per_item + t) * MT, col = col0 + cl;
-        __nv_bfloat16* st_hi = reinterpret_cast<__nv_bfloat16*>(sm + p.off_out + (size_t)buf * planes * p.out_plane);
+        __nv_bfloat16* st_hi = reinterpret_cast<__nv_bfloat16*>(p.alias ? sm + p.off_stage + (size_t)sg * p.stage_bytes
+                                                                         : sm + p.off_out + (size_t)buf * planes * p.out_plane);
+        if (++sg == S) sg = 0;
         __nv_bfloat16* st_lo = st_hi + p.out_plane / 2;
         float best = -1.f; int barg = 0;
         // dropout: one counter hash per (pair of node rows, column)
@@ -670,7 +677,8 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
         if (MODE == AGG_FWD_POOL && grp == 0) qv = p.q[(long long)b * p.out_dim + col];   // in flight during the wait
         if (lane == 0) {                                  // one poller per warp
           mbar_wait(&tfull[acc], aph);
-          if (MODE != AGG_FWD_POOL) mbar_wait(&sempty[buf], ((g >> 1) & 1) ^ 1);   // the store of two tiles ago has read this staging buffer
+          if (MODE != AGG_FWD_POOL) mbar_wait(&sempty[buf], ((g >> 1) & 1) ^ 1);   // the store of two tiles ago is done (alias mode: it
+                                                                                   // keeps the sfull / sempty phases from lapping)
         }
         __syncwarp();
         tc_fence_after();
@@ -736,8 +744,8 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
     if (it0 < it1) load_chunk(it0, 0);
     int n = 0;
     for (int it = it0; it < it1; ++it, ++n) {
-      const int cb = n & 1;
-      if (lane == 0) mbar_wait(&cempty[cb], ((n >> 1) & 1) ^ 1);   // every issuer's MMAs of two items ago are done with this buffer
+      const int cb = n & p.cshift;
+      if (lane == 0) mbar_wait(&cempty[cb], ((n >> p.cshift) & 1) ^ 1);   // every issuer's MMAs of the item that used this buffer are done
       __syncwarp();
       uint8_t* cbase = sm + p.off_coef + (size_t)cb * p.coef_buf;
       {
@@ -778,24 +786,57 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
     }
   } else if (MODE != AGG_FWD_POOL) {
     // ------------------------------------------------------------ last warp: TMA stores of the staged tiles
-    if (lane == 0) {
-      int g = 0;
+    if (!p.alias) {
+      if (lane == 0) {
+        int g = 0;
+        int b = it0 / p.slabs, sl = it0 - b * p.slabs;
+        for (int it = it0; it < it1; ++it) {
+          for (int t = 0; t < tiles_per_item; ++t, ++g) {
+            const int buf = g & 1;
+            const int col0 = (sl * tiles_per_item + t) * MT;
+            const uint8_t* st_hi = sm + p.off_out + (size_t)buf * planes * p.out_plane;
+            mbar_wait(&sfull[buf], (g >> 1) & 1);
+            tma_store_2d(&tm.out_hi, st_hi, col0, b * K);
+            if (WITH_LO) tma_store_2d(&tm.out_lo, st_hi + p.out_plane, col0, b * K);
+            bulk_commit();
+            bulk_wait_read<0>();                            // ~18 KB of shared memory read: a few hundred cycles
+            mbar_arrive(&sempty[buf]);                      // staging buffer free again
+          }
+          if (++sl == p.slabs) { sl = 0; ++b; }
+        }
+        bulk_wait_read<0>();
+      }
+    } else {
+      // alias mode: the tile sits in the input stage of its own Y tile.  After the store has read it, the K-padding rows of the
+      // stage's boxes (which the output overwrote, and which the next TMA load - K rows per box - will not) are zeroed again,
+      // then the stage goes back to the producer.
+      int g = 0, sg = 0;
       int b = it0 / p.slabs, sl = it0 - b * p.slabs;
+      const int pad16 = (KP - K) * 8, nbox = planes * 2;
       for (int it = it0; it < it1; ++it) {
         for (int t = 0; t < tiles_per_item; ++t, ++g) {
           const int buf = g & 1;
           const int col0 = (sl * tiles_per_item + t) * MT;
-          const uint8_t* st_hi = sm + p.off_out + (size_t)buf * planes * p.out_plane;
-          mbar_wait(&sfull[buf], (g >> 1) & 1);
-          tma_store_2d(&tm.out_hi, st_hi, col0, b * K);
-          if (WITH_LO) tma_store_2d(&tm.out_lo, st_hi + p.out_plane, col0, b * K);
-          bulk_commit();
-          bulk_wait_read<0>();                            // ~18 KB of shared memory read: a few hundred cycles
-          mbar_arrive(&sempty[buf]);                      // staging buffer free again
+          uint8_t* st = sm + p.off_stage + (size_t)sg * p.stage_bytes;
+          if (lane == 0) {
+            mbar_wait(&sfull[buf], (g >> 1) & 1);
+            tma_store_2d(&tm.out_hi, st, col0, b * K);
+            if (WITH_LO) tma_store_2d(&tm.out_lo, st + p.out_plane, col0, b * K);
+            bulk_commit();
+            bulk_wait_read<0>();
+          }
+          __syncwarp();
+          for (int v = lane; v < nbox * pad16; v += 32) {
+            const int bx = v / pad16, w = v - bx * pad16;
+            *reinterpret_cast<uint4*>(st + (size_t)bx * KP * 128 + K * 128 + w * 16) = make_uint4(0u, 0u, 0u, 0u);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(&sempty[buf]); mbar_arrive(&empty[sg]); }   // stage free: the producer may load the next Y tile into it
+          if (++sg == S) sg = 0;
         }
         if (++sl == p.slabs) { sl = 0; ++b; }
       }
-      bulk_wait_read<0>();
     }
     __syncwarp();
   }
@@ -1159,16 +1200,27 @@ static int agg_launch(const void* in_hi, const void* in_lo, long long ldin, void
     a.coef_plane = p.coef_plane; a.coef_buf = nkc2 * planes * p.coef_plane; a.stage_bytes = p.stage_bytes; a.out_plane = p.out_plane;
     const int pool = MODE == AGG_FWD_POOL ? 2 * P_EG * MT * 8 : 0;
     a.rpg = (((K + P_EG - 1) / P_EG) + 1) & ~1;               // node rows per epilogue group (even: dropout hashes cover row pairs)
-    const int fixed2 = 2 * a.coef_buf + 2 * planes * p.out_plane + pool + 1024;
+    a.cshift = 1; a.alias = 0;
+    int fixed2 = 2 * a.coef_buf + 2 * planes * p.out_plane + pool + 1024;
     int S2 = (226 * 1024 - 2048 - fixed2) / p.stage_bytes;
+    if (S2 < 2) {
+      // large node counts (K = 100): one kernel per item, ONE coefficient buffer, output tiles staged inside the input stages
+      a.nkc = 1; a.slabs = p.nk; a.nitems = B * a.slabs; a.coef_buf = planes * p.coef_plane;
+      a.cshift = 0; a.alias = MODE != AGG_FWD_POOL && planes * p.out_plane <= p.stage_bytes ? 1 : 0;
+      fixed2 = a.coef_buf + (a.alias || MODE == AGG_FWD_POOL ? 0 : 2 * planes * p.out_plane) + pool;
+      S2 = (227 * 1024 - 1024 /* alignment slack */ - 1024 /* barriers, rounding */ - fixed2) / p.stage_bytes;
+    }
     if (S2 >= 2) {
       if (S2 > 8) S2 = 8;
       a.nstage = S2;
       a.ni = S2 < P_NI ? S2 : P_NI;
+      // every issuer must own a tile of every item: an issuer without one passes the item without waiting for anything and its
+      // "not mine" arrival on cempty could land in an earlier item's phase (tile g belongs to issuer g % ni)
+      if (a.ni > a.nkc * tpk) a.ni = a.nkc * tpk;
       int o2 = 0;
-      a.off_coef = o2; o2 += 2 * a.coef_buf; o2 = (o2 + 1023) & ~1023;
+      a.off_coef = o2; o2 += (a.cshift ? 2 : 1) * a.coef_buf; o2 = (o2 + 1023) & ~1023;
       a.off_stage = o2; o2 += S2 * p.stage_bytes;
-      a.off_out = o2; o2 += 2 * planes * p.out_plane; o2 = (o2 + 127) & ~127;
+      a.off_out = o2; o2 += a.alias ? 0 : 2 * planes * p.out_plane; o2 = (o2 + 127) & ~127;
       a.off_pool = o2; o2 += pool;
       a.off_bars = o2; o2 += (2 * S2 + 26) * 8;
       a.nacc = (512 - 16) / KP < 4 ? (512 - 16) / KP : 4;     // accumulators in flight between the MMA issuers and the epilogue
