@@ -42,6 +42,7 @@ def parse():
                     help="criterion + optimiser: our single-launch kernels (vqa_b200.loss / vqa_b200.optim) or torch's modules")
     ap.add_argument("--no-resident-table", action="store_true", help="skip the ShardLoader (feature table in HBM) end-to-end leg")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying the captured CUDA graph")
+    ap.add_argument("--quick", action="store_true", help="device-resident and end-to-end legs only (scaling experiments)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="questions per CPU step (bounded sample of the workload)")
     return ap.parse_args()
 
@@ -411,7 +412,7 @@ def run_b200(args, workload):
     # shard directory; every step the host sends row indices, tokens and CSR answer triplets (a few hundred KB) and two kernels
     # assemble the batch on the device; loss read back every step.  Reported next to "e2e", never instead of it. ----------------
     e2e_table = None
-    if not args.no_resident_table and not args.no_graph:
+    if not args.no_resident_table and not args.no_graph and not args.quick:
         import shutil
         import tempfile
         from vqa_b200 import shards
@@ -475,7 +476,7 @@ def run_b200(args, workload):
     # ---- the same step in bf16 mode (BASELINE config[1] names both precisions): single-pass tensor-core products outside the
     # graph-learner chain; same model, optimizer and batches, its own captured graph --------------------------------
     bf16_mode = None
-    if args.precision == "fp32" and not args.no_graph:
+    if args.precision == "fp32" and not args.no_graph and not args.quick:
         ops.set_precision("bf16")
         step16 = TrainStep(model, opt, criterion, reducer=reducer, use_graph=True, seed=4321 + rank)
         for i in range(max(args.warmup, 3)):
@@ -500,13 +501,13 @@ def run_b200(args, workload):
     # every rank runs it (the gradient all-reduce inside the step is a collective); rank 0 reads the timers
     timers = {}
     eager = TrainStep(model, opt, criterion, reducer=reducer, use_graph=False, seed=99)
-    for i in range(3):
+    for i in range(0 if args.quick else 3):
         eager(*(resident[i % NB][k] for k in keys))
     kn.enable_timing(GC, ADJ, "vqa_graphconv_mma_fwd", "vqa_graphconv_mma_pool_fwd", "vqa_graphconv_mma_bwd_data", "vqa_graphconv_mma_bwd_edges",
                      "vqa_adjacency_topk_bwd_f32", "vqa_gemm_bf16s")
     spin = int(10e-3 * getattr(torch.cuda.get_device_properties(local), "clock_rate", 1.9e6) * 1e3)   # ~10 ms of SM clock
     kn.GEMM_LOG = []
-    for i in range(6):
+    for i in range(0 if args.quick else 6):
         # the host needs ~5 ms to enqueue one eager step: let it run ahead of the GPU behind a spin kernel, so that every
         # bracketed launch starts the moment its predecessor ends and the events see device time only, no launch gaps
         torch.cuda.synchronize()
@@ -596,7 +597,7 @@ def run_b200(args, workload):
                    "frac": round(value / world / ceil_qps, 4),
                    "note": "value per GPU / (measured sustained bf16 peak / dense FLOPs one question needs, forward + backward); the fp32-grade mode issues every product 3 times"}
     cpu = None
-    if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only
+    if not args.no_cpu_baseline and world == 1 and not args.quick:      # reported on rank 0 at N = 1 only
         from vqa_b200.synthetic import WORKLOADS
         cores = os.cpu_count() or 1
         t, _, kind = cpu_train_steps(WORKLOADS["vqa2_b64"], args.cpu_sample, 8, 2, cores)      # ~20 s of host work on the 16-core boxes
@@ -607,7 +608,7 @@ def run_b200(args, workload):
     # the reference in eager PyTorch CUDA on this same GPU (SURVEY.md 8d "same-box competitor"): its own Model / criterion / Adam at the
     # bench batch, fp32 matmuls and with TF32 allowed; CUDA-synchronised wall clock per step
     eager = None
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and not args.quick:
         try:
             del resident
             torch.cuda.empty_cache()
@@ -638,6 +639,8 @@ def run_b200(args, workload):
         "e2e_resident_table": e2e_table,
     }
     line["config"]["host_affinity"] = numa
+    line["config"]["allreduce"] = {"buckets_mb": args.bucket_mb, "start": "inside backward, as each bucket's last gradient kernel is enqueued" if reducer.early else "when the fused operator's autograd node returns",
+                                   "sm_reserve": step.sm_reserve if world > 1 else 0, "NCCL_MAX_CTAS": os.environ.get("NCCL_MAX_CTAS")}
     print(json.dumps(line), file=json_out, flush=True)
     leave()
 

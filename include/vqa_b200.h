@@ -37,6 +37,10 @@ typedef struct CUstream_st* vqa_stream_t; /* cudaStream_t */
 #define VQA_GC_RELU 1
 
 const char* vqa_last_error(void);
+/* SMs the persistent (one CTA per SM, statically partitioned) kernels may occupy: 8 .. 148, default 148; returns the previous
+ * value.  Read at launch time (a captured graph keeps the grids it was captured with).  Used while a collective runs under
+ * backward: a persistent grid that finds some SMs taken would otherwise finish a whole wave late. */
+int vqa_set_sm_budget(int n_sms);
 int vqa_abi_version(void);
 
 /* C[M,N] = epi( sum_k A[m,k] * B[n,k] ) on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulator, TMA operands).

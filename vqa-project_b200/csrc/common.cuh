@@ -40,6 +40,11 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 namespace vqa {
 
 constexpr int kNumSMs = 148;  // B200
+}  // namespace vqa
+// SMs the one-CTA-per-SM persistent kernels may occupy (vqa_set_sm_budget): statically partitioned persistent grids finish late
+// by a whole extra wave when another kernel - a collective running under backward - holds some SMs, so their grids leave room.
+extern int g_vqa_sm_budget;
+namespace vqa {
 
 // ------------------------------------------------------------------ warp helpers
 __device__ __forceinline__ float warp_sum(float v) {

@@ -7,6 +7,12 @@
 thread_local char g_vqa_err[512] = "";
 
 extern "C" const char* vqa_last_error(void) { return g_vqa_err; }
+int g_vqa_sm_budget = vqa::kNumSMs;
+extern "C" int vqa_set_sm_budget(int n_sms) {
+  const int old = g_vqa_sm_budget;
+  g_vqa_sm_budget = n_sms < 8 ? 8 : (n_sms > vqa::kNumSMs ? vqa::kNumSMs : n_sms);
+  return old;
+}
 extern "C" int vqa_abi_version(void) { return VQA_ABI_VERSION; }
 
 namespace vqa {

@@ -834,7 +834,7 @@ static int launch(const Maps& tm, const Params& p, int splits, cudaStream_t st) 
   PSched sc;
   sc.tiles_n = (p.N + BN - 1) / BN; sc.tiles_m = mt; sc.units_m = mt / CL; sc.splits = splits;
   sc.units = sc.tiles_n * sc.units_m * splits;
-  const int cap = kNumSMs / CL;                    // one CTA per SM (the double-buffered accumulator takes 2 * BN TMEM columns)
+  const int cap = g_vqa_sm_budget / CL;            // one CTA per SM (the double-buffered accumulator takes 2 * BN TMEM columns)
   sc.nclusters = sc.units < cap ? sc.units : cap;
   if (!one_tile_per_cta && BN >= 128 && sc.units > sc.nclusters) {   // more tiles than SMs: walk them persistently, epilogue overlapped
     // (BN = 64 is the small-problem tile: two co-resident CTAs per SM with shallow rings already overlap each other)

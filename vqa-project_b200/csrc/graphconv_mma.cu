@@ -1226,7 +1226,7 @@ static int agg_launch(const void* in_hi, const void* in_lo, long long ldin, void
       a.nacc = (512 - 16) / KP < 4 ? (512 - 16) / KP : 4;     // accumulators in flight between the MMA issuers and the epilogue
       a.tmem_cols = 32; while (a.tmem_cols < a.nacc * KP + 16) a.tmem_cols <<= 1;   // +16: the last 16-column epilogue read may overhang
       const size_t smem2 = (size_t)o2 + 1024;
-      int grid2 = kNumSMs < a.nitems ? kNumSMs : a.nitems;
+      int grid2 = g_vqa_sm_budget < a.nitems ? g_vqa_sm_budget : a.nitems;
       const bool dropk = MODE == AGG_FWD && a.drop_thresh16 != 0;
       auto go = [&](auto kern) -> int {
         VQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));

@@ -62,6 +62,7 @@ SIGNATURES = {
     "vqa_gru_cell_bwd_f32": [_p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _ll, _p, _i, _i, _p],
     "vqa_gate_bwd_f32": [_p, _p, _p, _p, _p, _ll, _p],
     "vqa_mlsm_loss_blocks": [_ll],
+    "vqa_set_sm_budget": [_i],
     "vqa_mlsm_loss_fwd_f32": [_p, _p, _ll, _f, _p, _p, _p, _p],
     "vqa_mlsm_loss_bwd_f32": [_p, _p, _p, _p, _ll, _f, _p],
     "vqa_adam_flat_f32": [_p, _i, _p, _p, _p, _p, _f, _f, _f, _f, _f, _p, _p],

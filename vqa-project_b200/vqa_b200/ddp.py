@@ -26,7 +26,12 @@ import torch.distributed as dist
 
 class GradReducer:
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20,
-                 process_group: Optional[dist.ProcessGroup] = None):
+                 process_group: Optional[dist.ProcessGroup] = None, early: Optional[bool] = None):
+        """``early``: let the fused operators start a bucket's all-reduce from INSIDE their backward, the moment the bucket's last
+        gradient kernel is enqueued (``mark_ready``), instead of when the operator's autograd node returns.  Default: the
+        ``VQA_EARLY_READY`` environment variable ("1" unless set to "0")."""
+        import os
+        self.early = (os.environ.get("VQA_EARLY_READY", "1") != "0") if early is None else bool(early)
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("GradReducer: no trainable parameters")
@@ -76,7 +81,7 @@ class GradReducer:
         self.average = True                               # finish() scales by 1/world; optim.FlatAdam folds the factor into its pass instead
         try:                                              # the fused operators write their parameter gradients through the sink
             from . import ops
-            ops.set_grad_sink(self.sink, self.mark_ready)
+            ops.set_grad_sink(self.sink, self.mark_ready if self.early else None)
         except Exception:                                 # pragma: no cover - CPU-only use of the reducer (tests)
             pass
 

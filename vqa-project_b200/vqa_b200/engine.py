@@ -44,6 +44,8 @@ class TrainStep:
                  use_graph: bool = True, warmup: int = 3, seed: Optional[int] = None, slots: int = 2):
         self.model, self.opt, self.criterion, self.reducer = model, optimizer, criterion, reducer
         self.use_graph, self.warmup, self.nslots = use_graph, warmup, slots
+        import os
+        self.sm_reserve = int(os.environ.get("VQA_SM_RESERVE", "0"))          # SMs left to NCCL during backward (N > 1)
         self.device = next(model.parameters()).device
         self.seed = torch.initial_seed() if seed is None else seed
         self.rng_step = torch.zeros((), dtype=torch.int64, device=self.device)
@@ -68,9 +70,18 @@ class TrainStep:
             self.opt.zero_grad(set_to_none=False)
         logits, _, _ = self.model(b["question"], b["image"], b["K"], b["qlen"])
         loss = self.criterion(logits, b["target"])
-        loss.backward()
-        if self.reducer is not None:
-            self.reducer.finish()
+        # while buckets travel under backward, the persistent one-CTA-per-SM kernels leave `sm_reserve` SMs to the collective: a
+        # statically partitioned persistent grid that finds SMs taken finishes a whole wave late (vqa_set_sm_budget)
+        reserve = self.sm_reserve if self.reducer is not None and self.reducer.world > 1 else 0
+        if reserve:
+            old = kn.set_sm_budget(148 - reserve)
+        try:
+            loss.backward()
+            if self.reducer is not None:
+                self.reducer.finish()
+        finally:
+            if reserve:
+                kn.set_sm_budget(old)
         self.opt.step()
         self.rng_step += 1
         return loss

@@ -34,6 +34,12 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def set_sm_budget(n_sms: int) -> int:
+    """SMs the persistent one-CTA-per-SM kernels may occupy from now on (8..148); returns the previous value.  Host-side state read at
+    launch time; see include/vqa_b200.h."""
+    return int(_cabi.load().vqa_set_sm_budget(int(n_sms)))
+
+
 # name -> list of (start_event, end_event): filled when a caller (bench.py) asks for in-stream kernel timing
 TIMERS = {}
 

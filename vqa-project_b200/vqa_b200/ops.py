@@ -114,10 +114,8 @@ def set_grad_sink(fn=None, ready=None) -> None:
 def _ready(*params):
     """Tell the reducer that these parameters' gradients are complete in their sink views (their bucket may start its
     all-reduce now, under the rest of backward)."""
-    # Measured at N=2 (same box, B=512 per GPU): starting the buckets from inside backward gives 4.07 vs 4.12 ms/step with
-    # device-resident batches but 4.27 vs 4.17 ms end to end (host batches: the ranks are less aligned, an early all-reduce
-    # spins on its peer while holding SMs).  End to end is what training looks like, so it is opt-in: VQA_EARLY_READY=1.
-    if _GRAD_READY is not None and os.environ.get("VQA_EARLY_READY", "0") == "1":
+    # (whether the reducer wants these calls is its decision: ddp.GradReducer(early=...) installs the callback or not)
+    if _GRAD_READY is not None:
         for t in params:
             if t is not None:
                 _GRAD_READY(t)
