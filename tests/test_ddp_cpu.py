@@ -73,7 +73,7 @@ def test_reducer_single_process_keeps_views_and_zeroes():
     offs = [p._vqa_flat_off for p in net.parameters()]
     assert offs == sorted(offs)
     covered = sorted((s.start, s.stop) for s in red.bucket_slices)
-    assert covered[0][0] == 0 and covered[-1][1] == red.flat.numel()
+    assert covered[0][0] == 0 and 0 <= red.flat.numel() - covered[-1][1] < 4      # (the buffer is padded to whole float4s)
     assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
     net(torch.randn(3, 5)).sum().backward()               # .grad defined: autograd accumulates in place
     red.finish()

@@ -1,0 +1,97 @@
+"""Data-parallel training over NVLink peer memory (vqa_b200.ddp.GradReducer(p2p=True) + vqa_b200.optim.FlatAdam): the fused
+reduce-scatter + Adam + all-gather kernel and its flag barriers, two ranks on two GPUs of one node, against single-process training on
+the concatenated batch.  Needs >= 2 GPUs (skipped on the one-GPU boxes; run with `gpurun --gpus 2`)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q, p2p):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "vqa-project_b200")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), VQA_P2P="1" if p2p else "0")
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from vqa_b200.ddp import GradReducer, broadcast_parameters
+    from vqa_b200.engine import TrainStep
+    from vqa_b200.loss import MultiLabelSoftMarginLoss
+    from vqa_b200.optim import FlatAdam
+    from vqa_b200.synthetic import WORKLOADS, make_batch, make_wemb
+    import sparse_graph_model as M
+    w = WORKLOADS["small"]
+    kw = w.model_kwargs()
+    kw["dropout"] = 0.0
+    torch.manual_seed(1000 + rank)                      # deliberately different initial weights per rank
+    model = M.Model(pretrained_wemb=make_wemb(w), **kw).to(dev).train()
+    model.max_question_len = w.max_qlen
+    broadcast_parameters(model)
+    red = GradReducer(model.parameters())
+    assert red.p2p == p2p
+    opt = FlatAdam(red, lr=1e-3)
+    crit = MultiLabelSoftMarginLoss()
+    step = TrainStep(model, opt, crit, reducer=red, use_graph=True, seed=5)
+    B = w.batch
+    full = [make_batch(w, seed=80 + i, batch=2 * B) for i in range(3)]
+    losses = []
+    for it in range(4):
+        b = full[it % 3]
+        sl = slice(rank * B, (rank + 1) * B)
+        losses.append(float(step(b["question"][sl], b["image"][sl], b["K"][sl], b["qlen"][sl], b["target"][sl])))
+    torch.cuda.synchronize()
+    assert opt.steps_taken == 4
+    state = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    if rank == 0:                                       # single-process reference on the concatenated batches (same kernels, one GPU)
+        torch.manual_seed(1000)
+        ref = M.Model(pretrained_wemb=make_wemb(w), **kw).to(dev).train()
+        ref.max_question_len = w.max_qlen
+        ropt = torch.optim.Adam(ref.parameters(), lr=1e-3)
+        for it in range(4):
+            b = full[it % 3]
+            qlen = torch.tensor([int(x) for x in b["qlen"]], dtype=torch.int32, device=dev)
+            ropt.zero_grad()
+            # mean over the 2B questions = average of the two ranks' means
+            crit(ref(b["question"].to(dev), b["image"].to(dev), b["K"].to(dev), qlen)[0], b["target"].to(dev)).backward()
+            ropt.step()
+        rstate = {k: v.detach().float().cpu() for k, v in ref.state_dict().items()}
+        q.put(("ref", rstate))
+    q.put((rank, state, losses))
+    dist.barrier()
+    step.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("p2p", [True, False])
+def test_two_gpu_training_equals_single_process_on_the_concatenated_batch(p2p):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 23500 + os.getpid() % 2000 + (7 if p2p else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, p2p)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=600) for _ in range(3)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ref = next(g[1] for g in got if g[0] == "ref")
+    states = {g[0]: g[1] for g in got if g[0] != "ref"}
+    # both ranks hold the same parameters bit for bit (p2p: each element is computed once, by its owner, and stored everywhere)
+    for k in ref:
+        assert torch.equal(states[0][k], states[1][k]), k
+    # ... and they are the single-process result up to the Adam sign lottery of rounding-level gradients (see test_train_tail_gpu.py)
+    lr, steps, total, off = 1e-3, 4, 0, 0
+    for k in ref:
+        d = (states[0][k] - ref[k]).abs()
+        assert d.max().item() <= 2 * lr * steps, k
+        total += d.numel()
+        off += int((d > 1e-4).sum())
+    print(f"p2p={p2p}: {off}/{total} elements differ by more than 1e-4 from single-process training after 4 Adam steps")
+    assert off <= 2e-3 * total

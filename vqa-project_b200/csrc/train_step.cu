@@ -174,6 +174,99 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(const AdamChunk* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------ data-parallel Adam over NVLink peer memory
+// One process per GPU, every rank's flat gradient buffer G_q and flat parameter buffer P_q mapped into every other rank's address
+// space (symmetric memory over NVLink / NVSwitch).  The reference has no distributed code; the stock recipe is an all-reduce of the
+// gradients (2 (N-1)/N x 121 MB over the links per GPU, then N identical Adam passes of 848 MB each).  Here ONE kernel per rank does
+//   reduce-scatter : g[i] = sum_q G_q[i] for the rank's own 1/N slice of the flat index space, peers read straight over NVLink in
+//                    rank order (deterministic),
+//   Adam           : on that slice only (moments are sharded: each rank touches 1/N of exp_avg / exp_avg_sq),
+//   all-gather     : the updated parameters are stored into every rank's P_q[i],
+// so the gradient sum is never written anywhere, the Adam traffic per rank drops N-fold and no collective kernel competes with
+// backward for SMs.  Two flag barriers (p2p_barrier_kernel) bracket it: all gradients written before anyone reads, all parameters
+// written before anyone's next forward.
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.relaxed.sys.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+constexpr int P2P_MAX_WORLD = 16;
+struct P2PPtrs { float* g[P2P_MAX_WORLD]; float* p[P2P_MAX_WORLD]; };
+
+__global__ void __launch_bounds__(256) adam_p2p_kernel(const __grid_constant__ P2PPtrs pp, float* __restrict__ exp_avg,
+                                                       float* __restrict__ exp_avg_sq, long long lo4, long long hi4, int rank, int world,
+                                                       const float* __restrict__ hyper, float b1, float b2, float eps, float wd,
+                                                       float grad_scale, int* __restrict__ state) {
+  __shared__ float s_step_size, s_inv_sqrt_bc2;
+  __shared__ int s_step;
+  if (threadIdx.x == 0) {
+    const int step = state[0] + 1;
+    const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
+    s_step = step;
+    s_step_size = (float)((double)__ldg(hyper) / bc1);
+    s_inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  }
+  __syncthreads();
+  const float step_size = s_step_size, isb2 = s_inv_sqrt_bc2;
+  float* pl = pp.p[rank];
+  for (long long i = lo4 + (long long)blockIdx.x * 256 + threadIdx.x; i < hi4; i += (long long)gridDim.x * 256) {
+    float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int q = 0; q < world; ++q) {                      // rank order: every element is summed the same way whoever owns it
+      const float4 t = ld_peer_f4(pp.g[q] + 4 * i);
+      gg.x += t.x; gg.y += t.y; gg.z += t.z; gg.w += t.w;
+    }
+    float4 w = reinterpret_cast<const float4*>(pl)[i];
+    float4 mm = reinterpret_cast<float4*>(exp_avg)[i];
+    float4 vv = reinterpret_cast<float4*>(exp_avg_sq)[i];
+    adam_one(w.x, gg.x, mm.x, vv.x, grad_scale, wd, b1, b2, step_size, isb2, eps);
+    adam_one(w.y, gg.y, mm.y, vv.y, grad_scale, wd, b1, b2, step_size, isb2, eps);
+    adam_one(w.z, gg.z, mm.z, vv.z, grad_scale, wd, b1, b2, step_size, isb2, eps);
+    adam_one(w.w, gg.w, mm.w, vv.w, grad_scale, wd, b1, b2, step_size, isb2, eps);
+    reinterpret_cast<float4*>(exp_avg)[i] = mm;
+    reinterpret_cast<float4*>(exp_avg_sq)[i] = vv;
+#pragma unroll 4
+    for (int q = 0; q < world; ++q) reinterpret_cast<float4*>(pp.p[q])[i] = w;
+  }
+  __threadfence_system();                                   // my parameter stores are performed before the barrier kernel announces them
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(state + 1, 1) == (int)gridDim.x - 1) {
+      state[0] = s_step;
+      state[1] = 0;
+    }
+  }
+}
+
+// Flag barrier across the ranks of one node: flags[q] = address of rank q's flag array (world ints, zero at start) as mapped HERE;
+// *epoch counts the barriers this rank has passed.  Thread q announces the new epoch in rank q's slot [rank] (release, system scope)
+// and waits for rank q's announcement in the local slot [q] (acquire).  Bounded: a rank that never arrives traps the launch after ~4 s
+// of SM clock instead of hanging the GPU.
+struct P2PFlags { int* f[P2P_MAX_WORLD]; };
+__global__ void p2p_barrier_kernel(const __grid_constant__ P2PFlags fl, int rank, int world, int* __restrict__ epoch) {
+  __shared__ int s_e;
+  if (threadIdx.x == 0) { s_e = *epoch + 1; }
+  __syncthreads();
+  const int e = s_e, q = threadIdx.x;
+  if (q < world) {
+    __threadfence_system();
+    asm volatile("st.global.release.sys.b32 [%0], %1;" ::"l"(fl.f[q] + rank), "r"(e) : "memory");
+    const int* mine = fl.f[rank] + q;
+    const long long t0 = clock64();
+    for (;;) {
+      int seen;
+      asm volatile("ld.global.acquire.sys.b32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+      if (seen - e >= 0) break;
+      if (clock64() - t0 > 8000000000LL) {
+        printf("vqa_b200: p2p barrier timed out (rank %d waiting for rank %d, epoch %d, saw %d)\n", rank, q, e, seen);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *epoch = e;
+}
+
 }  // namespace vqa
 using namespace vqa;
 
@@ -211,5 +304,43 @@ extern "C" int vqa_adam_flat_f32(const long long* chunks, int nchunks, const flo
   adam_flat_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const AdamChunk*>(chunks), nchunks, grad, exp_avg, exp_avg_sq,
                                                lr, beta1, beta2, eps, weight_decay, grad_scale, state);
   VQA_LAUNCH_CHECK("adam_flat_kernel");
+  return VQA_OK;
+}
+
+extern "C" int vqa_p2p_barrier(const long long* flag_addrs, int rank, int world, int* epoch, cudaStream_t stream) {
+  VQA_CHECK_ARG(flag_addrs && epoch && world >= 1 && world <= P2P_MAX_WORLD && rank >= 0 && rank < world,
+                "vqa_p2p_barrier: bad arguments (rank %d of %d, at most %d ranks)", rank, world, P2P_MAX_WORLD);
+  P2PFlags fl{};
+  for (int q = 0; q < world; ++q) {
+    VQA_CHECK_ARG(flag_addrs[q] != 0, "vqa_p2p_barrier: null flag array for rank %d", q);
+    fl.f[q] = reinterpret_cast<int*>(flag_addrs[q]);
+  }
+  p2p_barrier_kernel<<<1, 32, 0, stream>>>(fl, rank, world, epoch);
+  VQA_LAUNCH_CHECK("p2p_barrier_kernel");
+  return VQA_OK;
+}
+
+extern "C" int vqa_adam_flat_p2p(const long long* grad_addrs, const long long* param_addrs, float* exp_avg, float* exp_avg_sq,
+                                 long long lo, long long hi, int rank, int world, const float* lr, float beta1, float beta2, float eps,
+                                 float weight_decay, float grad_scale, int* state, cudaStream_t stream) {
+  VQA_CHECK_ARG(grad_addrs && param_addrs && exp_avg && exp_avg_sq && lr && state, "vqa_adam_flat_p2p: null pointer");
+  VQA_CHECK_ARG(world >= 1 && world <= P2P_MAX_WORLD && rank >= 0 && rank < world, "vqa_adam_flat_p2p: rank %d of %d (at most %d ranks)", rank, world, P2P_MAX_WORLD);
+  VQA_CHECK_ARG(lo >= 0 && hi >= lo && (lo & 3) == 0 && (hi & 3) == 0, "vqa_adam_flat_p2p: the slice [%lld, %lld) must be float4 aligned", lo, hi);
+  VQA_CHECK_ARG(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "vqa_adam_flat_p2p: betas must be in [0,1) and eps >= 0");
+  VQA_CHECK_ARG(aligned16(exp_avg) && aligned16(exp_avg_sq), "vqa_adam_flat_p2p: moment buffers must be 16-byte aligned");
+  P2PPtrs pp{};
+  for (int q = 0; q < world; ++q) {
+    VQA_CHECK_ARG(grad_addrs[q] && param_addrs[q] && (grad_addrs[q] & 15) == 0 && (param_addrs[q] & 15) == 0,
+                  "vqa_adam_flat_p2p: rank %d's buffers must be mapped and 16-byte aligned", q);
+    pp.g[q] = reinterpret_cast<float*>(grad_addrs[q]);
+    pp.p[q] = reinterpret_cast<float*>(param_addrs[q]);
+  }
+  const long long n4 = (hi - lo) >> 2;
+  if (n4 == 0) return VQA_OK;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+  adam_p2p_kernel<<<(unsigned)blocks, 256, 0, stream>>>(pp, exp_avg, exp_avg_sq, lo >> 2, hi >> 2, rank, world, lr, beta1, beta2, eps,
+                                                        weight_decay, grad_scale, state);
+  VQA_LAUNCH_CHECK("adam_p2p_kernel");
   return VQA_OK;
 }

@@ -24,9 +24,19 @@ import torch
 import torch.distributed as dist
 
 
+def symmetric_empty(numel: int, dtype: torch.dtype, device: torch.device, group=None):
+    """A zero-filled buffer every rank of the node can address: (local tensor, [address of rank q's buffer in THIS process], handle).
+    torch's symmetric-memory allocator (CUDA VMM handles exchanged at rendezvous) maps the peers' allocations over NVLink."""
+    import torch.distributed._symmetric_memory as symm
+    t = symm.empty(numel, dtype=dtype, device=device)
+    t.zero_()
+    hdl = symm.rendezvous(t, dist.group.WORLD if group is None else group)
+    return t, [int(a) for a in hdl.buffer_ptrs], hdl
+
+
 class GradReducer:
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20,
-                 process_group: Optional[dist.ProcessGroup] = None, early: Optional[bool] = None):
+                 process_group: Optional[dist.ProcessGroup] = None, early: Optional[bool] = None, p2p: Optional[bool] = None):
         """``early``: let the fused operators start a bucket's all-reduce from INSIDE their backward, the moment the bucket's last
         gradient kernel is enqueued (``mark_ready``), instead of when the operator's autograd node returns.  Default: the
         ``VQA_EARLY_READY`` environment variable ("1" unless set to "0")."""
@@ -64,8 +74,23 @@ class GradReducer:
                 self.bucket_slices.append(slice(p._vqa_flat_off, end))
                 self.bucket_size.append(count)
                 end, nbytes, count = p._vqa_flat_off, 0, 0
-        # pass 3: one buffer, every .grad a view into it
-        self.flat = torch.zeros(total, device=dev, dtype=dt)
+        # pass 3: one buffer, every .grad a view into it.  p2p (world > 1 on one NVLink node, CUDA): the buffer is symmetric memory, the
+        # peers read it directly (optim.FlatAdam's fused reduce-scatter + Adam + all-gather kernel) and NO all-reduce is issued here.
+        import os
+        want = (os.environ.get("VQA_P2P", "1") != "0") if p2p is None else bool(p2p)
+        self.p2p, self.peer_grad_addrs, self._symm = False, None, []
+        self.total = total = (total + 3) // 4 * 4
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        if want and self.world > 1 and dev.type == "cuda":
+            try:
+                self.flat, self.peer_grad_addrs, h = symmetric_empty(total, dt, dev, process_group)
+                self._symm.append(h)
+                self.p2p = True
+            except Exception as e:                       # no NVLink peer access / allocator unavailable: the NCCL path below
+                import warnings
+                warnings.warn(f"vqa_b200.ddp: symmetric memory unavailable ({e!r}); gradients will be all-reduced with NCCL")
+        if not self.p2p:
+            self.flat = torch.zeros(total, device=dev, dtype=dt)
         self._by_ptr = {p.data_ptr(): p for p in self.params}
         for p in self.params:
             p.grad = self._view(p)
@@ -134,7 +159,7 @@ class GradReducer:
 
     def _launch(self, b: int) -> None:
         self._launched_now[b] = True
-        if self.world > 1:
+        if self.world > 1 and not self.p2p:
             h = dist.all_reduce(self.flat[self.bucket_slices[b]], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             self._handles.append(h)
         self.launched += 1
@@ -170,7 +195,7 @@ class GradReducer:
         for h in self._handles:
             h.wait()
         self._handles.clear()
-        if self.world > 1 and self.average:
+        if self.world > 1 and self.average and not self.p2p:
             self.flat.mul_(1.0 / self.world)
 
     def remove(self) -> None:

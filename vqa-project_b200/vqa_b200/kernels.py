@@ -649,6 +649,26 @@ def adam_flat(chunks: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, e
           lr.data_ptr(), float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale), state.data_ptr(), _stream())
 
 
+def _addr_array(addrs):
+    import ctypes
+    return (ctypes.c_longlong * len(addrs))(*[int(a) for a in addrs])
+
+
+def p2p_barrier(flag_addrs, rank: int, world: int, epoch: torch.Tensor) -> None:
+    """Stream-ordered flag barrier between the ranks of one node (see include/vqa_b200.h)."""
+    _chk(epoch, "p2p epoch", torch.int32)
+    _call("vqa_p2p_barrier", _addr_array(flag_addrs), int(rank), int(world), epoch.data_ptr(), _stream())
+
+
+def adam_flat_p2p(grad_addrs, param_addrs, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, lo: int, hi: int, rank: int, world: int,
+                  lr: torch.Tensor, beta1: float, beta2: float, eps: float, weight_decay: float, grad_scale: float, state: torch.Tensor) -> None:
+    """Reduce-scatter + Adam on flat elements [lo, hi) + all-gather over NVLink peer memory, one launch (include/vqa_b200.h)."""
+    _chk(exp_avg, "adam exp_avg"); _chk(exp_avg_sq, "adam exp_avg_sq"); _chk(lr, "adam lr"); _chk(state, "adam state", torch.int32)
+    _call("vqa_adam_flat_p2p", _addr_array(grad_addrs), _addr_array(param_addrs), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), int(lo), int(hi),
+          int(rank), int(world), lr.data_ptr(), float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale),
+          state.data_ptr(), _stream())
+
+
 # ------------------------------------------------------------------------------------------- batch assembly (loader.cu)
 def gather_image(features: torch.Tensor, boxes: torch.Tensor, rows: torch.Tensor, err: torch.Tensor) -> torch.Tensor:
     """image (B, K, D+4) fp32 = [features[rows] | boxes[rows]] from a (n, K, D) fp32/bf16 table and (n, K, 4) fp32 boxes."""

@@ -38,6 +38,9 @@ class FlatAdam(torch.optim.Optimizer):
         self._lr_host = float(lr)
         self._build_chunks()
         reducer.average = False                                                       # 1/world is applied by the Adam pass
+        self.p2p = bool(getattr(reducer, "p2p", False))
+        if self.p2p:
+            self._setup_p2p()
         for p in reducer.params:                                                      # torch.optim.Adam-style per-parameter views
             st = self.state[p]
             st["exp_avg"] = self.exp_avg[p._vqa_flat_off:p._vqa_flat_off + p.numel()].view_as(p)
@@ -55,6 +58,50 @@ class FlatAdam(torch.optim.Optimizer):
                 rows.append((addr + 4 * s, off + s, min(CHUNK, n - s)))
         self._ptrs = [p.data_ptr() for p in self.reducer.params]
         self.chunks = torch.tensor(rows, dtype=torch.int64).to(self.reducer.flat.device)
+
+    def _setup_p2p(self) -> None:
+        """Data-parallel mode over NVLink peer memory (ddp.GradReducer(p2p=True)): the parameters move into ONE symmetric flat buffer
+        with the gradient buffer's layout (every ``p.data`` becomes a view of it, values kept), so that the fused kernel
+        (``kernels.adam_flat_p2p``) can read every rank's gradients and write every rank's parameters.  Each rank owns a contiguous
+        1/world slice of the flat index space: it sums that slice over the ranks, updates it (its moments are the only ones that
+        ever change: optimizer state is sharded) and stores the new values into all ranks' parameter buffers."""
+        import torch.distributed as dist
+        from .ddp import symmetric_empty
+        r = self.reducer
+        dev = r.flat.device
+        self.pflat, self.peer_param_addrs, h = symmetric_empty(r.total, torch.float32, dev, r.group)
+        self.flags, self.peer_flag_addrs, h2 = symmetric_empty(64, torch.int32, dev, r.group)
+        r._symm += [h, h2]
+        self.epoch = torch.zeros(1, device=dev, dtype=torch.int32)
+        with torch.no_grad():
+            for p in r.params:
+                v = self.pflat[p._vqa_flat_off:p._vqa_flat_off + p.numel()].view_as(p)
+                v.copy_(p)
+                p.data = v
+        per = (r.total // 4 + r.world - 1) // r.world * 4
+        self.slice = (min(r.total, r.rank * per), min(r.total, (r.rank + 1) * per))
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=r.group)                   # every rank's flags are zero and its parameters in place before the first kernel barrier
+
+    def _check_p2p_views(self) -> None:
+        base = self.pflat.data_ptr()
+        for p in self.reducer.params:
+            if p.data_ptr() != base + 4 * p._vqa_flat_off:
+                raise RuntimeError("FlatAdam (p2p): a parameter no longer lives in the shared flat buffer (was the module moved with .to() / "
+                                   "re-flattened after the optimiser was built?)")
+
+    def gather_state(self) -> None:
+        """Make every rank's exp_avg / exp_avg_sq complete (each rank only ever updates its own slice): call before ``state_dict()``."""
+        if not self.p2p:
+            return
+        import torch.distributed as dist
+        r = self.reducer
+        per = (r.total // 4 + r.world - 1) // r.world * 4
+        for buf in (self.exp_avg, self.exp_avg_sq):
+            for q in range(r.world):
+                lo, hi = min(r.total, q * per), min(r.total, (q + 1) * per)
+                if hi > lo:
+                    dist.broadcast(buf[lo:hi], src=dist.get_global_rank(r.group, q) if r.group is not None else q, group=r.group)
 
     @property
     def steps_taken(self) -> int:
@@ -76,6 +123,20 @@ class FlatAdam(torch.optim.Optimizer):
         if len(self.param_groups) != 1:
             raise RuntimeError("FlatAdam: one parameter group (the reducer's parameters) is supported")
         g = self.param_groups[0]
+        if self.p2p:
+            capturing = torch.cuda.is_current_stream_capturing()
+            if not capturing:
+                self.sync_lr()
+                self._check_p2p_views()
+            missing = [i for i, p in enumerate(self.reducer.params) if p.grad is None]
+            if missing:
+                raise RuntimeError(f"FlatAdam.step: parameters {missing} (reducer order) received no gradient in this step")
+            r = self.reducer
+            kn.p2p_barrier(self.peer_flag_addrs, r.rank, r.world, self.epoch)      # every rank's gradients are written
+            kn.adam_flat_p2p(r.peer_grad_addrs, self.peer_param_addrs, self.exp_avg, self.exp_avg_sq, self.slice[0], self.slice[1], r.rank,
+                             r.world, self._lr, g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], 1.0 / r.world, self._state)
+            kn.p2p_barrier(self.peer_flag_addrs, r.rank, r.world, self.epoch)      # every rank's parameters are complete
+            return loss
         moved = [p.data_ptr() for p in self.reducer.params] != self._ptrs
         if not torch.cuda.is_current_stream_capturing():
             self.sync_lr()
