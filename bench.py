@@ -639,8 +639,13 @@ def run_b200(args, workload):
         "e2e_resident_table": e2e_table,
     }
     line["config"]["host_affinity"] = numa
-    line["config"]["allreduce"] = {"buckets_mb": args.bucket_mb, "start": "inside backward, as each bucket's last gradient kernel is enqueued" if reducer.early else "when the fused operator's autograd node returns",
-                                   "sm_reserve": step.sm_reserve if world > 1 else 0, "NCCL_MAX_CTAS": os.environ.get("NCCL_MAX_CTAS")}
+    if getattr(reducer, "p2p", False):
+        line["config"]["gradient_exchange"] = ("NVLink peer memory (symmetric memory): one fused kernel per rank = reduce-scatter of the flat gradient buffer + Adam on "
+                                               "the rank's 1/N slice (sharded moments) + all-gather of the updated parameters, bracketed by two flag barriers; no NCCL call in the step")
+    else:
+        line["config"]["gradient_exchange"] = {"collective": "bucketed NCCL all-reduce of the flat gradient buffer" if world > 1 else "none (one GPU)", "buckets_mb": args.bucket_mb,
+                                               "start": "inside backward, as each bucket's last gradient kernel is enqueued" if reducer.early else "when the fused operator's autograd node returns",
+                                               "sm_reserve": step.sm_reserve if world > 1 else 0, "NCCL_MAX_CTAS": os.environ.get("NCCL_MAX_CTAS")}
     print(json.dumps(line), file=json_out, flush=True)
     leave()
 
