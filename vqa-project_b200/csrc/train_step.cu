@@ -209,24 +209,38 @@ __global__ void __launch_bounds__(256) adam_p2p_kernel(const __grid_constant__ P
   __syncthreads();
   const float step_size = s_step_size, isb2 = s_inv_sqrt_bc2;
   float* pl = pp.p[rank];
-  for (long long i = lo4 + (long long)blockIdx.x * 256 + threadIdx.x; i < hi4; i += (long long)gridDim.x * 256) {
-    float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+  constexpr int U = 4;                                     // float4 elements per thread and pass: U x (loads of one peer) in flight -
+  const long long stride = (long long)gridDim.x * 256;     // with one, a two-rank run was bound by the NVLink round trip (227 us)
+  for (long long i0 = lo4 + (long long)blockIdx.x * 256 + threadIdx.x; i0 < hi4; i0 += stride * U) {
+    float4 gg[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) gg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
     for (int q = 0; q < world; ++q) {                      // rank order: every element is summed the same way whoever owns it
-      const float4 t = ld_peer_f4(pp.g[q] + 4 * i);
-      gg.x += t.x; gg.y += t.y; gg.z += t.z; gg.w += t.w;
+      float4 t[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        t[u] = i0 + u * stride < hi4 ? ld_peer_f4(pp.g[q] + 4 * (i0 + u * stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < U; ++u) { gg[u].x += t[u].x; gg[u].y += t[u].y; gg[u].z += t[u].z; gg[u].w += t[u].w; }
     }
-    float4 w = reinterpret_cast<const float4*>(pl)[i];
-    float4 mm = reinterpret_cast<float4*>(exp_avg)[i];
-    float4 vv = reinterpret_cast<float4*>(exp_avg_sq)[i];
-    adam_one(w.x, gg.x, mm.x, vv.x, grad_scale, wd, b1, b2, step_size, isb2, eps);
-    adam_one(w.y, gg.y, mm.y, vv.y, grad_scale, wd, b1, b2, step_size, isb2, eps);
-    adam_one(w.z, gg.z, mm.z, vv.z, grad_scale, wd, b1, b2, step_size, isb2, eps);
-    adam_one(w.w, gg.w, mm.w, vv.w, grad_scale, wd, b1, b2, step_size, isb2, eps);
-    reinterpret_cast<float4*>(exp_avg)[i] = mm;
-    reinterpret_cast<float4*>(exp_avg_sq)[i] = vv;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < hi4) {
+        float4 w = reinterpret_cast<const float4*>(pl)[i];
+        float4 mm = reinterpret_cast<float4*>(exp_avg)[i];
+        float4 vv = reinterpret_cast<float4*>(exp_avg_sq)[i];
+        adam_one(w.x, gg[u].x, mm.x, vv.x, grad_scale, wd, b1, b2, step_size, isb2, eps);
+        adam_one(w.y, gg[u].y, mm.y, vv.y, grad_scale, wd, b1, b2, step_size, isb2, eps);
+        adam_one(w.z, gg[u].z, mm.z, vv.z, grad_scale, wd, b1, b2, step_size, isb2, eps);
+        adam_one(w.w, gg[u].w, mm.w, vv.w, grad_scale, wd, b1, b2, step_size, isb2, eps);
+        reinterpret_cast<float4*>(exp_avg)[i] = mm;
+        reinterpret_cast<float4*>(exp_avg_sq)[i] = vv;
 #pragma unroll 4
-    for (int q = 0; q < world; ++q) reinterpret_cast<float4*>(pp.p[q])[i] = w;
+        for (int q = 0; q < world; ++q) reinterpret_cast<float4*>(pp.p[q])[i] = w;
+      }
+    }
   }
   __threadfence_system();                                   // my parameter stores are performed before the barrier kernel announces them
   __syncthreads();
