@@ -12,7 +12,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 n = 30_300_000 // 4 * 4
-G, gaddr, h1 = symmetric_empty(n, torch.float32, dev)
+G = torch.zeros(n, device=dev)
 P, paddr, h2 = symmetric_empty(n, torch.float32, dev)
 F, faddr, h3 = symmetric_empty(64, torch.int32, dev)
 G.normal_(); P.normal_()
@@ -38,16 +38,29 @@ def timeit(name, fn, iters=20):
     t = torch.tensor([sorted(ts)[len(ts) // 2]], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0: print(json.dumps({"world": world, "what": name, "us": round(t.item(), 1)}), flush=True)
 
+per4 = per
+R_, raddr, h4 = symmetric_empty(world * per, torch.float32, dev)
+peers_r = [None if q == rank else h4.get_buffer(q, (world * per,), torch.float32, 0) for q in range(world)]
+def push():
+    for d in range(1, world):
+        q = (rank + d) % world
+        a, e = min(n, q * per), min(n, (q + 1) * per)
+        if a < e: peers_r[q][rank * per:rank * per + (e - a)].copy_(G[a:e], non_blocking=True)
+def kernel(paddrs=None):
+    kn.adam_flat_p2p(G, R_, per, paddr if paddrs is None else paddrs, m, v, lo, hi, rank, world, lr, 0.9, 0.999, 1e-8, 0.0, 1.0 / world, state)
 def fused():
+    push()
     kn.p2p_barrier(faddr, rank, world, epoch)
-    kn.adam_flat_p2p(gaddr, paddr, m, v, lo, hi, rank, world, lr, 0.9, 0.999, 1e-8, 0.0, 1.0 / world, state)
+    kernel()
     kn.p2p_barrier(faddr, rank, world, epoch)
 def nccl():
     dist.all_reduce(G)
     kn.adam_flat(chunks, G, m, v, lr, 0.9, 0.999, 1e-8, 0.0, 1.0 / world, state)
 timeit("flag barrier", lambda: kn.p2p_barrier(faddr, rank, world, epoch))
-timeit("fused reduce-scatter + Adam + all-gather (2 barriers included)", fused)
-timeit("fused kernel only", lambda: kn.adam_flat_p2p(gaddr, paddr, m, v, lo, hi, rank, world, lr, 0.9, 0.999, 1e-8, 0.0, 1.0 / world, state))
+timeit("copy-engine push of the gradient slices to their owners", push)
+timeit("sum + Adam on my slice + parameter stores to all ranks (one kernel)", kernel)
+timeit("the same kernel with all parameter stores local", lambda: kernel([paddr[rank]] * world))
+timeit("whole tail, nothing hidden: push + barrier + kernel + barrier", fused)
 timeit("NCCL all-reduce (121 MB) + Adam on the whole buffer", nccl)
 timeit("Adam on the whole buffer (N = 1 work)", lambda: kn.adam_flat(chunks, G, m, v, lr, 0.9, 0.999, 1e-8, 0.0, 1.0, state))
 timeit("NCCL all-reduce (121 MB) alone", lambda: dist.all_reduce(G))

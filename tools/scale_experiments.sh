@@ -13,6 +13,10 @@ print(json.dumps({'label': '$label', 'n': d['n_gpus'], 'ms': d['ms_per_step'], '
   tail -1 $OUT
 }
 : > $OUT
-run "peer-memory fused reduce-scatter + Adam + all-gather" VQA_P2P=1
-run "NCCL all-reduce, late start" VQA_P2P=0 VQA_EARLY_READY=0
-run "NCCL all-reduce, early start" VQA_P2P=0 VQA_EARLY_READY=1
+if [ -n "$ONLY_P2P" ]; then
+  run "peer-memory fused reduce-scatter + Adam + all-gather" VQA_P2P=1
+else
+  run "peer-memory fused reduce-scatter + Adam + all-gather" VQA_P2P=1
+  run "NCCL all-reduce, late start" VQA_P2P=0 VQA_EARLY_READY=0
+  run "NCCL all-reduce, early start" VQA_P2P=0 VQA_EARLY_READY=1
+fi

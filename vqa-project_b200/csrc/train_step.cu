@@ -175,25 +175,23 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(const AdamChunk* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ data-parallel Adam over NVLink peer memory
-// One process per GPU, every rank's flat gradient buffer G_q and flat parameter buffer P_q mapped into every other rank's address
-// space (symmetric memory over NVLink / NVSwitch).  The reference has no distributed code; the stock recipe is an all-reduce of the
-// gradients (2 (N-1)/N x 121 MB over the links per GPU, then N identical Adam passes of 848 MB each).  Here ONE kernel per rank does
-//   reduce-scatter : g[i] = sum_q G_q[i] for the rank's own 1/N slice of the flat index space, peers read straight over NVLink in
-//                    rank order (deterministic),
-//   Adam           : on that slice only (moments are sharded: each rank touches 1/N of exp_avg / exp_avg_sq),
-//   all-gather     : the updated parameters are stored into every rank's P_q[i],
-// so the gradient sum is never written anywhere, the Adam traffic per rank drops N-fold and no collective kernel competes with
-// backward for SMs.  Two flag barriers (p2p_barrier_kernel) bracket it: all gradients written before anyone reads, all parameters
-// written before anyone's next forward.
-__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
-  float4 v;
-  asm volatile("ld.global.relaxed.sys.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
-}
+// One process per GPU; symmetric memory maps every rank's buffers into every other rank's address space over NVLink / NVSwitch.
+// The reference has no distributed code; the stock recipe is an all-reduce of the gradients (measured at N = 8: 370 us for the
+// 121 MB buffer, with NCCL's CTAs competing with backward for SMs) followed by N identical 848 MB Adam passes (155 us).  Here:
+//   reduce-scatter, pushed: every rank owns a 1/N slice of the flat index space.  While backward runs, each finished gradient bucket
+//       is COPIED (cudaMemcpyAsync over NVLink: copy engines, no SMs) into the owners' receive buffers R_r[q] (vqa_b200.ddp).
+//       Pushing, not pulling: measured with this kernel's first version, remote LOADS sustain ~330 GB/s per GPU, remote STORES and
+//       copy-engine pushes ~600 GB/s (profiles/r02_p2p_adam.md).
+//   this kernel, per rank: g[i] = sum_q (q == rank ? G[i] : R[q][i - lo]) in rank order (all local reads), Adam on the slice (moments
+//       are sharded: each rank touches 1/N of exp_avg / exp_avg_sq), and the all-gather: the updated parameters are stored into every
+//       rank's flat parameter buffer P_q[i] (remote stores).
+// Two flag barriers (p2p_barrier_kernel) bracket it: all pushes landed before anyone sums, all parameters written before anyone's
+// next forward.
 constexpr int P2P_MAX_WORLD = 16;
-struct P2PPtrs { float* g[P2P_MAX_WORLD]; float* p[P2P_MAX_WORLD]; };
+struct P2PPtrs { float* p[P2P_MAX_WORLD]; };
 
-__global__ void __launch_bounds__(256) adam_p2p_kernel(const __grid_constant__ P2PPtrs pp, float* __restrict__ exp_avg,
+__global__ void __launch_bounds__(256) adam_p2p_kernel(const __grid_constant__ P2PPtrs pp, const float* __restrict__ grad,
+                                                       const float* __restrict__ recv, long long per4, float* __restrict__ exp_avg,
                                                        float* __restrict__ exp_avg_sq, long long lo4, long long hi4, int rank, int world,
                                                        const float* __restrict__ hyper, float b1, float b2, float eps, float wd,
                                                        float grad_scale, int* __restrict__ state) {
@@ -209,38 +207,26 @@ __global__ void __launch_bounds__(256) adam_p2p_kernel(const __grid_constant__ P
   __syncthreads();
   const float step_size = s_step_size, isb2 = s_inv_sqrt_bc2;
   float* pl = pp.p[rank];
-  constexpr int U = 4;                                     // float4 elements per thread and pass: U x (loads of one peer) in flight -
-  const long long stride = (long long)gridDim.x * 256;     // with one, a two-rank run was bound by the NVLink round trip (227 us)
-  for (long long i0 = lo4 + (long long)blockIdx.x * 256 + threadIdx.x; i0 < hi4; i0 += stride * U) {
-    float4 gg[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) gg[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-    for (int q = 0; q < world; ++q) {                      // rank order: every element is summed the same way whoever owns it
-      float4 t[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        t[u] = i0 + u * stride < hi4 ? ld_peer_f4(pp.g[q] + 4 * (i0 + u * stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int u = 0; u < U; ++u) { gg[u].x += t[u].x; gg[u].y += t[u].y; gg[u].z += t[u].z; gg[u].w += t[u].w; }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long i = i0 + u * stride;
-      if (i < hi4) {
-        float4 w = reinterpret_cast<const float4*>(pl)[i];
-        float4 mm = reinterpret_cast<float4*>(exp_avg)[i];
-        float4 vv = reinterpret_cast<float4*>(exp_avg_sq)[i];
-        adam_one(w.x, gg[u].x, mm.x, vv.x, grad_scale, wd, b1, b2, step_size, isb2, eps);
-        adam_one(w.y, gg[u].y, mm.y, vv.y, grad_scale, wd, b1, b2, step_size, isb2, eps);
-        adam_one(w.z, gg[u].z, mm.z, vv.z, grad_scale, wd, b1, b2, step_size, isb2, eps);
-        adam_one(w.w, gg[u].w, mm.w, vv.w, grad_scale, wd, b1, b2, step_size, isb2, eps);
-        reinterpret_cast<float4*>(exp_avg)[i] = mm;
-        reinterpret_cast<float4*>(exp_avg_sq)[i] = vv;
+  const float4* g4 = reinterpret_cast<const float4*>(grad);
+  const float4* r4 = reinterpret_cast<const float4*>(recv);
+  for (long long i = lo4 + (long long)blockIdx.x * 256 + threadIdx.x; i < hi4; i += (long long)gridDim.x * 256) {
+    float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-        for (int q = 0; q < world; ++q) reinterpret_cast<float4*>(pp.p[q])[i] = w;
-      }
+    for (int q = 0; q < world; ++q) {                      // rank order: the sum does not depend on who owns the element
+      const float4 t = q == rank ? __ldcs(g4 + i) : __ldcs(r4 + q * per4 + (i - lo4));
+      gg.x += t.x; gg.y += t.y; gg.z += t.z; gg.w += t.w;
     }
+    float4 w = reinterpret_cast<const float4*>(pl)[i];
+    float4 mm = reinterpret_cast<float4*>(exp_avg)[i];
+    float4 vv = reinterpret_cast<float4*>(exp_avg_sq)[i];
+    adam_one(w.x, gg.x, mm.x, vv.x, grad_scale, wd, b1, b2, step_size, isb2, eps);
+    adam_one(w.y, gg.y, mm.y, vv.y, grad_scale, wd, b1, b2, step_size, isb2, eps);
+    adam_one(w.z, gg.z, mm.z, vv.z, grad_scale, wd, b1, b2, step_size, isb2, eps);
+    adam_one(w.w, gg.w, mm.w, vv.w, grad_scale, wd, b1, b2, step_size, isb2, eps);
+    reinterpret_cast<float4*>(exp_avg)[i] = mm;
+    reinterpret_cast<float4*>(exp_avg_sq)[i] = vv;
+#pragma unroll 4
+    for (int q = 0; q < world; ++q) reinterpret_cast<float4*>(pp.p[q])[i] = w;
   }
   __threadfence_system();                                   // my parameter stores are performed before the barrier kernel announces them
   __syncthreads();
@@ -334,27 +320,26 @@ extern "C" int vqa_p2p_barrier(const long long* flag_addrs, int rank, int world,
   return VQA_OK;
 }
 
-extern "C" int vqa_adam_flat_p2p(const long long* grad_addrs, const long long* param_addrs, float* exp_avg, float* exp_avg_sq,
-                                 long long lo, long long hi, int rank, int world, const float* lr, float beta1, float beta2, float eps,
-                                 float weight_decay, float grad_scale, int* state, cudaStream_t stream) {
-  VQA_CHECK_ARG(grad_addrs && param_addrs && exp_avg && exp_avg_sq && lr && state, "vqa_adam_flat_p2p: null pointer");
+extern "C" int vqa_adam_flat_p2p(const float* grad, const float* recv, long long per, const long long* param_addrs, float* exp_avg,
+                                 float* exp_avg_sq, long long lo, long long hi, int rank, int world, const float* lr, float beta1,
+                                 float beta2, float eps, float weight_decay, float grad_scale, int* state, cudaStream_t stream) {
+  VQA_CHECK_ARG(grad && recv && param_addrs && exp_avg && exp_avg_sq && lr && state, "vqa_adam_flat_p2p: null pointer");
   VQA_CHECK_ARG(world >= 1 && world <= P2P_MAX_WORLD && rank >= 0 && rank < world, "vqa_adam_flat_p2p: rank %d of %d (at most %d ranks)", rank, world, P2P_MAX_WORLD);
-  VQA_CHECK_ARG(lo >= 0 && hi >= lo && (lo & 3) == 0 && (hi & 3) == 0, "vqa_adam_flat_p2p: the slice [%lld, %lld) must be float4 aligned", lo, hi);
+  VQA_CHECK_ARG(lo >= 0 && hi >= lo && (lo & 3) == 0 && (hi & 3) == 0 && (per & 3) == 0 && hi - lo <= per,
+                "vqa_adam_flat_p2p: the slice [%lld, %lld) must be float4 aligned and fit the receive stride %lld", lo, hi, per);
   VQA_CHECK_ARG(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "vqa_adam_flat_p2p: betas must be in [0,1) and eps >= 0");
-  VQA_CHECK_ARG(aligned16(exp_avg) && aligned16(exp_avg_sq), "vqa_adam_flat_p2p: moment buffers must be 16-byte aligned");
+  VQA_CHECK_ARG(aligned16(grad) && aligned16(recv) && aligned16(exp_avg) && aligned16(exp_avg_sq), "vqa_adam_flat_p2p: buffers must be 16-byte aligned");
   P2PPtrs pp{};
   for (int q = 0; q < world; ++q) {
-    VQA_CHECK_ARG(grad_addrs[q] && param_addrs[q] && (grad_addrs[q] & 15) == 0 && (param_addrs[q] & 15) == 0,
-                  "vqa_adam_flat_p2p: rank %d's buffers must be mapped and 16-byte aligned", q);
-    pp.g[q] = reinterpret_cast<float*>(grad_addrs[q]);
+    VQA_CHECK_ARG(param_addrs[q] && (param_addrs[q] & 15) == 0, "vqa_adam_flat_p2p: rank %d's parameter buffer must be mapped and 16-byte aligned", q);
     pp.p[q] = reinterpret_cast<float*>(param_addrs[q]);
   }
   const long long n4 = (hi - lo) >> 2;
   if (n4 == 0) return VQA_OK;
   long long blocks = (n4 + 255) / 256;
   if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
-  adam_p2p_kernel<<<(unsigned)blocks, 256, 0, stream>>>(pp, exp_avg, exp_avg_sq, lo >> 2, hi >> 2, rank, world, lr, beta1, beta2, eps,
-                                                        weight_decay, grad_scale, state);
+  adam_p2p_kernel<<<(unsigned)blocks, 256, 0, stream>>>(pp, grad, recv, per >> 2, exp_avg, exp_avg_sq, lo >> 2, hi >> 2, rank, world, lr, beta1,
+                                                        beta2, eps, weight_decay, grad_scale, state);
   VQA_LAUNCH_CHECK("adam_p2p_kernel");
   return VQA_OK;
 }

@@ -83,8 +83,14 @@ class GradReducer:
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
         if want and self.world > 1 and dev.type == "cuda":
             try:
-                self.flat, self.peer_grad_addrs, h = symmetric_empty(total, dt, dev, process_group)
+                # every rank owns a contiguous 1/world slice of the flat index space; `recv` holds, per peer, that peer's gradients
+                # for MY slice (pushed there by the peer, see _launch)
+                self.per = (total // 4 + self.world - 1) // self.world * 4
+                self.flat = torch.zeros(total, device=dev, dtype=dt)
+                self.recv, self.peer_recv_addrs, h = symmetric_empty(self.world * self.per, dt, dev, process_group)
+                self._peer_recv = [None if q == self.rank else h.get_buffer(q, (self.world * self.per,), dt, 0) for q in range(self.world)]
                 self._symm.append(h)
+                self.comm_stream = torch.cuda.Stream(device=dev)
                 self.p2p = True
             except Exception as e:                       # no NVLink peer access / allocator unavailable: the NCCL path below
                 import warnings
@@ -157,8 +163,26 @@ class GradReducer:
             self._count(i)
         return hook
 
+    def _push(self, b: int) -> None:
+        """p2p: copy the parts of bucket b that other ranks own into their receive buffers - cudaMemcpyAsync over NVLink on a side
+        stream (copy engines: no SMs taken from backward), ordered after everything enqueued so far on the current stream."""
+        s0, s1 = self.bucket_slices[b].start, min(self.bucket_slices[b].stop, self.total)
+        cur = torch.cuda.current_stream(self.flat.device)
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            for d in range(1, self.world):                       # staggered: at any moment the ranks write to different peers
+                r = (self.rank + d) % self.world
+                a, e = max(s0, r * self.per), min(s1, (r + 1) * self.per)
+                if a < e:
+                    o = self.rank * self.per + (a - r * self.per)
+                    self._peer_recv[r][o:o + (e - a)].copy_(self.flat[a:e], non_blocking=True)
+
     def _launch(self, b: int) -> None:
         self._launched_now[b] = True
+        if self.p2p:
+            self._push(b)
+            self.launched += 1
+            return
         if self.world > 1 and not self.p2p:
             h = dist.all_reduce(self.flat[self.bucket_slices[b]], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
             self._handles.append(h)
@@ -195,6 +219,8 @@ class GradReducer:
         for h in self._handles:
             h.wait()
         self._handles.clear()
+        if self.p2p:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self.comm_stream)   # the pushes precede the optimiser's barrier
         if self.world > 1 and self.average and not self.p2p:
             self.flat.mul_(1.0 / self.world)
 

@@ -62,9 +62,10 @@ class FlatAdam(torch.optim.Optimizer):
     def _setup_p2p(self) -> None:
         """Data-parallel mode over NVLink peer memory (ddp.GradReducer(p2p=True)): the parameters move into ONE symmetric flat buffer
         with the gradient buffer's layout (every ``p.data`` becomes a view of it, values kept), so that the fused kernel
-        (``kernels.adam_flat_p2p``) can read every rank's gradients and write every rank's parameters.  Each rank owns a contiguous
-        1/world slice of the flat index space: it sums that slice over the ranks, updates it (its moments are the only ones that
-        ever change: optimizer state is sharded) and stores the new values into all ranks' parameter buffers."""
+        (``kernels.adam_flat_p2p``) can write every rank's parameters.  Each rank owns a contiguous 1/world slice of the flat index
+        space: the peers push their gradients for that slice into its receive buffer while backward runs (``ddp.GradReducer._push``),
+        it sums them, updates the slice (its moments are the only ones that ever change: optimizer state is sharded) and stores the
+        new values into all ranks' parameter buffers."""
         import torch.distributed as dist
         from .ddp import symmetric_empty
         r = self.reducer
@@ -78,7 +79,7 @@ class FlatAdam(torch.optim.Optimizer):
                 v = self.pflat[p._vqa_flat_off:p._vqa_flat_off + p.numel()].view_as(p)
                 v.copy_(p)
                 p.data = v
-        per = (r.total // 4 + r.world - 1) // r.world * 4
+        per = r.per
         self.slice = (min(r.total, r.rank * per), min(r.total, (r.rank + 1) * per))
         torch.cuda.synchronize(dev)
         dist.barrier(group=r.group)                   # every rank's flags are zero and its parameters in place before the first kernel barrier
@@ -96,7 +97,7 @@ class FlatAdam(torch.optim.Optimizer):
             return
         import torch.distributed as dist
         r = self.reducer
-        per = (r.total // 4 + r.world - 1) // r.world * 4
+        per = r.per
         for buf in (self.exp_avg, self.exp_avg_sq):
             for q in range(r.world):
                 lo, hi = min(r.total, q * per), min(r.total, (q + 1) * per)
@@ -133,7 +134,7 @@ class FlatAdam(torch.optim.Optimizer):
                 raise RuntimeError(f"FlatAdam.step: parameters {missing} (reducer order) received no gradient in this step")
             r = self.reducer
             kn.p2p_barrier(self.peer_flag_addrs, r.rank, r.world, self.epoch)      # every rank's gradients are written
-            kn.adam_flat_p2p(r.peer_grad_addrs, self.peer_param_addrs, self.exp_avg, self.exp_avg_sq, self.slice[0], self.slice[1], r.rank,
+            kn.adam_flat_p2p(r.flat, r.recv, r.per, self.peer_param_addrs, self.exp_avg, self.exp_avg_sq, self.slice[0], self.slice[1], r.rank,
                              r.world, self._lr, g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], 1.0 / r.world, self._state)
             kn.p2p_barrier(self.peer_flag_addrs, r.rank, r.world, self.epoch)      # every rank's parameters are complete
             return loss
