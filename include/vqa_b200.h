@@ -264,15 +264,21 @@ int vqa_mlsm_loss_bwd_f32(const float* logits, const float* target, const float*
  * lr: device float (so a CUDA-graph replay sees a scheduler's new rate).  state: two device ints, {steps taken, 0}; the
  * launch applies step state[0]+1 (bias corrections in double) and its last block stores the new count. */
 /* Data-parallel Adam over NVLink peer memory (one process per GPU on one node; no counterpart in the reference, which is single
- * process - SURVEY.md 8e): the tail of a pushed reduce-scatter, Adam on the rank's own slice and the all-gather of the updated
- * parameters in ONE kernel.  The rank owns flat elements [lo, hi) (multiples of 4).  grad: its own flat gradient buffer; recv: its
- * receive buffer, `world` strides of `per` floats, stride q holding rank q's gradients for [lo, hi) (pushed there by rank q before
- * the barrier; stride `rank` is unused); param_addrs: HOST array of `world` addresses - every rank's flat parameter buffer (same
- * layout as the gradients) as mapped into THIS process; exp_avg / exp_avg_sq local, same layout.  g = grad_scale * sum over ranks in
- * rank order, Adam, P_q[i] = p for every q.  lr / state as in vqa_adam_flat_f32.  Bracket with vqa_p2p_barrier on every rank. */
-int vqa_adam_flat_p2p(const float* grad, const float* recv, long long per, const long long* param_addrs, float* exp_avg,
-                      float* exp_avg_sq, long long lo, long long hi, int rank, int world, const float* lr, float beta1, float beta2,
-                      float eps, float weight_decay, float grad_scale, int* state, vqa_stream_t stream);
+ * process - SURVEY.md 8e): the tail of a pushed reduce-scatter, Adam on the rank's own elements and the all-gather of the updated
+ * parameters in ONE kernel.  Ownership is interleaved: chunk c of 2^chunk_log2 floats of the flat index space belongs to rank
+ * c % world; the rank owns n_own elements (whole chunks), in its own order e -> flat index ((e / chunk) * world + rank) * chunk +
+ * e % chunk.  grad: its own flat gradient buffer; recv: its receive buffer, `world` strides of n_own floats, stride q holding rank
+ * q's gradients for the rank's elements in that order (pushed there by rank q before the barrier, e.g. with vqa_memcpy2d_async;
+ * stride `rank` is unused); param_addrs: HOST array of `world` addresses - every rank's flat parameter buffer (layout of the
+ * gradients) as mapped into THIS process; exp_avg / exp_avg_sq local, same layout.  g = grad_scale * sum over ranks in rank order,
+ * Adam, P_q[i] = p for every q.  lr / state as in vqa_adam_flat_f32.  Bracket with vqa_p2p_barrier on every rank. */
+int vqa_adam_flat_p2p(const float* grad, const float* recv, long long n_own, int chunk_log2, const long long* param_addrs, float* exp_avg,
+                      float* exp_avg_sq, int rank, int world, const float* lr, float beta1, float beta2, float eps, float weight_decay,
+                      float grad_scale, int* state, vqa_stream_t stream);
+/* cudaMemcpy2DAsync, device to device (pitches / width in bytes): the strided pushes of the interleaved layout above as ONE copy per
+ * (bucket, peer) on the copy engines; capturable into a CUDA graph as a memcpy node. */
+int vqa_memcpy2d_async(void* dst, long long dpitch, const void* src, long long spitch, long long width, long long height,
+                       vqa_stream_t stream);
 /* Flag barrier between the ranks of one node, stream ordered: flag_addrs = HOST array of `world` addresses of the ranks' flag arrays
  * (`world` ints each, zero-initialised, peer mapped); epoch = local device int, zero-initialised, incremented by every barrier.
  * A rank that does not arrive within ~4 s of SM clock makes the launch trap (error to the caller) instead of hanging the GPU. */

@@ -46,7 +46,7 @@ def _worker(rank, world, port, q, p2p):
         losses.append(float(step(b["question"][sl], b["image"][sl], b["K"][sl], b["qlen"][sl], b["target"][sl])))
     torch.cuda.synchronize()
     assert opt.steps_taken == 4
-    state = {k: v.detach().float().cpu() for k, v in model.state_dict().items()}
+    state = {k: v.detach().float().cpu().numpy() for k, v in model.state_dict().items()}    # (numpy: pickled by value through the queue)
     if rank == 0:                                       # single-process reference on the concatenated batches (same kernels, one GPU)
         torch.manual_seed(1000)
         ref = M.Model(pretrained_wemb=make_wemb(w), **kw).to(dev).train()
@@ -59,7 +59,7 @@ def _worker(rank, world, port, q, p2p):
             # mean over the 2B questions = average of the two ranks' means
             crit(ref(b["question"].to(dev), b["image"].to(dev), b["K"].to(dev), qlen)[0], b["target"].to(dev)).backward()
             ropt.step()
-        rstate = {k: v.detach().float().cpu() for k, v in ref.state_dict().items()}
+        rstate = {k: v.detach().float().cpu().numpy() for k, v in ref.state_dict().items()}
         q.put(("ref", rstate))
     q.put((rank, state, losses))
     q.close()
@@ -85,8 +85,8 @@ def test_two_gpu_training_equals_single_process_on_the_concatenated_batch(p2p):
         if p.exitcode is None:
             p.kill()
         assert p.exitcode == 0
-    ref = next(g[1] for g in got if g[0] == "ref")
-    states = {g[0]: g[1] for g in got if g[0] != "ref"}
+    ref = {k: torch.from_numpy(v) for k, v in next(g[1] for g in got if g[0] == "ref").items()}
+    states = {g[0]: {k: torch.from_numpy(v) for k, v in g[1].items()} for g in got if g[0] != "ref"}
     # both ranks hold the same parameters bit for bit (p2p: each element is computed once, by its owner, and stored everywhere)
     for k in ref:
         assert torch.equal(states[0][k], states[1][k]), k

@@ -38,16 +38,18 @@ def timeit(name, fn, iters=20):
     t = torch.tensor([sorted(ts)[len(ts) // 2]], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0: print(json.dumps({"world": world, "what": name, "us": round(t.item(), 1)}), flush=True)
 
-per4 = per
-R_, raddr, h4 = symmetric_empty(world * per, torch.float32, dev)
-peers_r = [None if q == rank else h4.get_buffer(q, (world * per,), torch.float32, 0) for q in range(world)]
+CHL = 16; CH = 1 << CHL; row = CH * world
+nrows = (n + row - 1) // row; n = nrows * row; n_own = nrows * CH
+G = torch.randn(n, device=dev); m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+P, paddr, h2 = symmetric_empty(n, torch.float32, dev)
+R_, raddr, h4 = symmetric_empty(world * n_own, torch.float32, dev)
+chunks = torch.tensor([[P.data_ptr() + 4 * s, s, min(4096, n - s)] for s in range(0, n, 4096)], dtype=torch.int64, device=dev)
 def push():
     for d in range(1, world):
         q = (rank + d) % world
-        a, e = min(n, q * per), min(n, (q + 1) * per)
-        if a < e: peers_r[q][rank * per:rank * per + (e - a)].copy_(G[a:e], non_blocking=True)
+        kn.memcpy2d_async(raddr[q] + (rank * n_own) * 4, CH * 4, G.data_ptr() + q * CH * 4, row * 4, CH * 4, nrows)
 def kernel(paddrs=None):
-    kn.adam_flat_p2p(G, R_, per, paddr if paddrs is None else paddrs, m, v, lo, hi, rank, world, lr, 0.9, 0.999, 1e-8, 0.0, 1.0 / world, state)
+    kn.adam_flat_p2p(G, R_, n_own, CHL, paddr if paddrs is None else paddrs, m, v, rank, world, lr, 0.9, 0.999, 1e-8, 0.0, 1.0 / world, state)
 def fused():
     push()
     kn.p2p_barrier(faddr, rank, world, epoch)

@@ -13,7 +13,11 @@ print(json.dumps({'label': '$label', 'n': d['n_gpus'], 'ms': d['ms_per_step'], '
   tail -1 $OUT
 }
 : > $OUT
-if [ -n "$ONLY_P2P" ]; then
+if [ -n "$DIAG" ]; then
+  run "p2p without pushes" VQA_P2P=1 VQA_P2P_DIAG=nopush
+  run "p2p without pushes, barriers" VQA_P2P=1 VQA_P2P_DIAG=nopush,nobarrier
+  run "p2p without pushes, barriers, kernel" VQA_P2P=1 VQA_P2P_DIAG=nopush,nokernel
+elif [ -n "$ONLY_P2P" ]; then
   run "peer-memory fused reduce-scatter + Adam + all-gather" VQA_P2P=1
 else
   run "peer-memory fused reduce-scatter + Adam + all-gather" VQA_P2P=1

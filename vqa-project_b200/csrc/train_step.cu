@@ -190,9 +190,12 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(const AdamChunk* __restr
 constexpr int P2P_MAX_WORLD = 16;
 struct P2PPtrs { float* p[P2P_MAX_WORLD]; };
 
+// Ownership is interleaved: the flat index space is cut into chunks of 2^ch_log2 floats, chunk c belongs to rank c % world ("row" k =
+// chunks k * world .. k * world + world - 1), so every gradient bucket spreads evenly over the owners and its push can start the
+// moment the bucket is complete.  The rank's elements in its own order: n4 float4s, element e = (row e >> chl4, offset e & mask).
 __global__ void __launch_bounds__(256) adam_p2p_kernel(const __grid_constant__ P2PPtrs pp, const float* __restrict__ grad,
-                                                       const float* __restrict__ recv, long long per4, float* __restrict__ exp_avg,
-                                                       float* __restrict__ exp_avg_sq, long long lo4, long long hi4, int rank, int world,
+                                                       const float* __restrict__ recv, long long n4, int chl4, float* __restrict__ exp_avg,
+                                                       float* __restrict__ exp_avg_sq, int rank, int world,
                                                        const float* __restrict__ hyper, float b1, float b2, float eps, float wd,
                                                        float grad_scale, int* __restrict__ state) {
   __shared__ float s_step_size, s_inv_sqrt_bc2;
@@ -209,11 +212,13 @@ __global__ void __launch_bounds__(256) adam_p2p_kernel(const __grid_constant__ P
   float* pl = pp.p[rank];
   const float4* g4 = reinterpret_cast<const float4*>(grad);
   const float4* r4 = reinterpret_cast<const float4*>(recv);
-  for (long long i = lo4 + (long long)blockIdx.x * 256 + threadIdx.x; i < hi4; i += (long long)gridDim.x * 256) {
+  const long long mask = (1LL << chl4) - 1;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < n4; e += (long long)gridDim.x * 256) {
+    const long long i = (((e >> chl4) * world + rank) << chl4) + (e & mask);     // flat float4 index of my e-th element
     float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
     for (int q = 0; q < world; ++q) {                      // rank order: the sum does not depend on who owns the element
-      const float4 t = q == rank ? __ldcs(g4 + i) : __ldcs(r4 + q * per4 + (i - lo4));
+      const float4 t = q == rank ? __ldcs(g4 + i) : __ldcs(r4 + q * n4 + e);
       gg.x += t.x; gg.y += t.y; gg.z += t.z; gg.w += t.w;
     }
     float4 w = reinterpret_cast<const float4*>(pl)[i];
@@ -320,13 +325,13 @@ extern "C" int vqa_p2p_barrier(const long long* flag_addrs, int rank, int world,
   return VQA_OK;
 }
 
-extern "C" int vqa_adam_flat_p2p(const float* grad, const float* recv, long long per, const long long* param_addrs, float* exp_avg,
-                                 float* exp_avg_sq, long long lo, long long hi, int rank, int world, const float* lr, float beta1,
-                                 float beta2, float eps, float weight_decay, float grad_scale, int* state, cudaStream_t stream) {
+extern "C" int vqa_adam_flat_p2p(const float* grad, const float* recv, long long n_own, int chunk_log2, const long long* param_addrs,
+                                 float* exp_avg, float* exp_avg_sq, int rank, int world, const float* lr, float beta1, float beta2,
+                                 float eps, float weight_decay, float grad_scale, int* state, cudaStream_t stream) {
   VQA_CHECK_ARG(grad && recv && param_addrs && exp_avg && exp_avg_sq && lr && state, "vqa_adam_flat_p2p: null pointer");
   VQA_CHECK_ARG(world >= 1 && world <= P2P_MAX_WORLD && rank >= 0 && rank < world, "vqa_adam_flat_p2p: rank %d of %d (at most %d ranks)", rank, world, P2P_MAX_WORLD);
-  VQA_CHECK_ARG(lo >= 0 && hi >= lo && (lo & 3) == 0 && (hi & 3) == 0 && (per & 3) == 0 && hi - lo <= per,
-                "vqa_adam_flat_p2p: the slice [%lld, %lld) must be float4 aligned and fit the receive stride %lld", lo, hi, per);
+  VQA_CHECK_ARG(chunk_log2 >= 2 && chunk_log2 <= 30 && n_own >= 0 && (n_own & ((1LL << chunk_log2) - 1)) == 0,
+                "vqa_adam_flat_p2p: the rank's %lld elements must be whole chunks of 2^%d floats", n_own, chunk_log2);
   VQA_CHECK_ARG(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "vqa_adam_flat_p2p: betas must be in [0,1) and eps >= 0");
   VQA_CHECK_ARG(aligned16(grad) && aligned16(recv) && aligned16(exp_avg) && aligned16(exp_avg_sq), "vqa_adam_flat_p2p: buffers must be 16-byte aligned");
   P2PPtrs pp{};
@@ -334,12 +339,19 @@ extern "C" int vqa_adam_flat_p2p(const float* grad, const float* recv, long long
     VQA_CHECK_ARG(param_addrs[q] && (param_addrs[q] & 15) == 0, "vqa_adam_flat_p2p: rank %d's parameter buffer must be mapped and 16-byte aligned", q);
     pp.p[q] = reinterpret_cast<float*>(param_addrs[q]);
   }
-  const long long n4 = (hi - lo) >> 2;
+  const long long n4 = n_own >> 2;
   if (n4 == 0) return VQA_OK;
   long long blocks = (n4 + 255) / 256;
   if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
-  adam_p2p_kernel<<<(unsigned)blocks, 256, 0, stream>>>(pp, grad, recv, per >> 2, exp_avg, exp_avg_sq, lo >> 2, hi >> 2, rank, world, lr, beta1,
-                                                        beta2, eps, weight_decay, grad_scale, state);
+  adam_p2p_kernel<<<(unsigned)blocks, 256, 0, stream>>>(pp, grad, recv, n4, chunk_log2 - 2, exp_avg, exp_avg_sq, rank, world, lr, beta1, beta2, eps,
+                                                        weight_decay, grad_scale, state);
   VQA_LAUNCH_CHECK("adam_p2p_kernel");
+  return VQA_OK;
+}
+
+extern "C" int vqa_memcpy2d_async(void* dst, long long dpitch, const void* src, long long spitch, long long width, long long height,
+                                  cudaStream_t stream) {
+  VQA_CHECK_ARG(dst && src && width > 0 && height > 0 && dpitch >= width && spitch >= width, "vqa_memcpy2d_async: bad arguments");
+  VQA_CUDA(cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width, (size_t)height, cudaMemcpyDeviceToDevice, stream));
   return VQA_OK;
 }

@@ -47,6 +47,9 @@ class GradReducer:
             raise ValueError("GradReducer: no trainable parameters")
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        import os
+        if os.environ.get("VQA_NO_EXCHANGE") == "1":      # measurement aid: N independent replicas (what the box does without any exchange)
+            self.world = 1
         dev, dt = self.params[0].device, self.params[0].dtype
         # pass 1: offsets in registration order (64-element alignment keeps views 256-byte aligned)
         off = 0
@@ -85,11 +88,25 @@ class GradReducer:
             try:
                 # every rank owns a contiguous 1/world slice of the flat index space; `recv` holds, per peer, that peer's gradients
                 # for MY slice (pushed there by the peer, see _launch)
-                self.per = (total // 4 + self.world - 1) // self.world * 4
+                # interleaved ownership: chunk c of CH floats belongs to rank c % world, a "row" = world consecutive chunks, the buffers
+                # are padded to whole rows.  `recv` holds, per peer, that peer's gradients for MY chunks (pushed there, see _push_rows)
+                self.chunk_log2 = 16                                  # 65536 floats = 256 KB per chunk
+                CH = 1 << self.chunk_log2
+                row = CH * self.world
+                self.nrows = (total + row - 1) // row
+                self.total = total = self.nrows * row
+                self.n_own = self.nrows * CH
                 self.flat = torch.zeros(total, device=dev, dtype=dt)
-                self.recv, self.peer_recv_addrs, h = symmetric_empty(self.world * self.per, dt, dev, process_group)
-                self._peer_recv = [None if q == self.rank else h.get_buffer(q, (self.world * self.per,), dt, 0) for q in range(self.world)]
+                self.recv, self.peer_recv_addrs, h = symmetric_empty(self.world * self.n_own, dt, dev, process_group)
                 self._symm.append(h)
+                # a row may be pushed once every bucket it touches is complete
+                starts = [p._vqa_flat_off for p in self.params] + [1 << 62]
+                self._row_buckets = []
+                for k in range(self.nrows):
+                    a, e = k * row, (k + 1) * row
+                    self._row_buckets.append({self.bucket_of[i] for i in range(len(self.params)) if starts[i] < e and starts[i] + self.params[i].numel() > a})
+                self._row_pushed = [False] * self.nrows
+                self._bucket_ready = [False] * len(self.bucket_size)
                 self.comm_stream = torch.cuda.Stream(device=dev)
                 self.p2p = True
             except Exception as e:                       # no NVLink peer access / allocator unavailable: the NCCL path below
@@ -164,18 +181,31 @@ class GradReducer:
         return hook
 
     def _push(self, b: int) -> None:
-        """p2p: copy the parts of bucket b that other ranks own into their receive buffers - cudaMemcpyAsync over NVLink on a side
-        stream (copy engines: no SMs taken from backward), ordered after everything enqueued so far on the current stream."""
-        s0, s1 = self.bucket_slices[b].start, min(self.bucket_slices[b].stop, self.total)
+        """p2p: bucket b is complete - copy every row that has now all its buckets complete into the owners' receive buffers: ONE
+        strided copy (cudaMemcpy2DAsync over NVLink: copy engines, no SMs taken from backward) per peer and run of rows, on a side
+        stream, ordered after everything enqueued so far on the current stream."""
+        import os
+        from . import kernels as kn
+        self._bucket_ready[b] = True
+        rows = [k for k in range(self.nrows) if not self._row_pushed[k] and all(self._bucket_ready[x] for x in self._row_buckets[k])]
+        if not rows or "nopush" in os.environ.get("VQA_P2P_DIAG", ""):       # (timing diagnosis only: wrong results)
+            return
+        for k in rows:
+            self._row_pushed[k] = True
+        runs, k0 = [], rows[0]
+        for prev, k in zip(rows, rows[1:] + [None]):
+            if k != prev + 1:
+                runs.append((k0, prev + 1))
+                k0 = k
+        CH, W, es = 1 << self.chunk_log2, self.world, self.flat.element_size()
         cur = torch.cuda.current_stream(self.flat.device)
         self.comm_stream.wait_stream(cur)
         with torch.cuda.stream(self.comm_stream):
-            for d in range(1, self.world):                       # staggered: at any moment the ranks write to different peers
-                r = (self.rank + d) % self.world
-                a, e = max(s0, r * self.per), min(s1, (r + 1) * self.per)
-                if a < e:
-                    o = self.rank * self.per + (a - r * self.per)
-                    self._peer_recv[r][o:o + (e - a)].copy_(self.flat[a:e], non_blocking=True)
+            for d in range(1, W):                                # staggered: at any moment the ranks write to different peers
+                r = (self.rank + d) % W
+                for k0, k1 in runs:
+                    kn.memcpy2d_async(self.peer_recv_addrs[r] + (self.rank * self.n_own + k0 * CH) * es, CH * es,
+                                      self.flat.data_ptr() + (k0 * W * CH + r * CH) * es, W * CH * es, CH * es, k1 - k0)
 
     def _launch(self, b: int) -> None:
         self._launched_now[b] = True
@@ -207,6 +237,9 @@ class GradReducer:
         self._done = [False] * len(self.params)
         self._issued = [False] * len(self.params)
         self._launched_now = [False] * len(self.bucket_size)
+        if self.p2p:
+            self._row_pushed = [False] * self.nrows
+            self._bucket_ready = [False] * len(self.bucket_size)
 
     def finish(self) -> None:
         """Wait for the in-flight buckets (launching any that has not started: parameters without a gradient, or accumulation
@@ -219,7 +252,8 @@ class GradReducer:
         for h in self._handles:
             h.wait()
         self._handles.clear()
-        if self.p2p:
+        import os
+        if self.p2p and "nopush" not in os.environ.get("VQA_P2P_DIAG", ""):
             torch.cuda.current_stream(self.flat.device).wait_stream(self.comm_stream)   # the pushes precede the optimiser's barrier
         if self.world > 1 and self.average and not self.p2p:
             self.flat.mul_(1.0 / self.world)

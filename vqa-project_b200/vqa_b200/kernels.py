@@ -660,18 +660,23 @@ def p2p_barrier(flag_addrs, rank: int, world: int, epoch: torch.Tensor) -> None:
     _call("vqa_p2p_barrier", _addr_array(flag_addrs), int(rank), int(world), epoch.data_ptr(), _stream())
 
 
-def adam_flat_p2p(grad: torch.Tensor, recv: torch.Tensor, per: int, param_addrs, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, lo: int,
-                  hi: int, rank: int, world: int, lr: torch.Tensor, beta1: float, beta2: float, eps: float, weight_decay: float,
-                  grad_scale: float, state: torch.Tensor) -> None:
-    """Sum of the pushed gradient slices + Adam on flat elements [lo, hi) + all-gather of the new parameters over NVLink peer memory,
-    one launch (include/vqa_b200.h)."""
+def adam_flat_p2p(grad: torch.Tensor, recv: torch.Tensor, n_own: int, chunk_log2: int, param_addrs, exp_avg: torch.Tensor,
+                  exp_avg_sq: torch.Tensor, rank: int, world: int, lr: torch.Tensor, beta1: float, beta2: float, eps: float,
+                  weight_decay: float, grad_scale: float, state: torch.Tensor) -> None:
+    """Sum of the pushed gradient chunks + Adam on the rank's elements + all-gather of the new parameters over NVLink peer memory, one
+    launch (include/vqa_b200.h)."""
     _chk(grad, "adam grad"); _chk(recv, "adam recv"); _chk(exp_avg, "adam exp_avg"); _chk(exp_avg_sq, "adam exp_avg_sq")
     _chk(lr, "adam lr"); _chk(state, "adam state", torch.int32)
-    if recv.numel() < world * per:
-        raise RuntimeError("adam_flat_p2p: the receive buffer must hold world strides of `per` floats")
-    _call("vqa_adam_flat_p2p", grad.data_ptr(), recv.data_ptr(), int(per), _addr_array(param_addrs), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
-          int(lo), int(hi), int(rank), int(world), lr.data_ptr(), float(beta1), float(beta2), float(eps), float(weight_decay),
+    if recv.numel() < world * n_own:
+        raise RuntimeError("adam_flat_p2p: the receive buffer must hold world strides of n_own floats")
+    _call("vqa_adam_flat_p2p", grad.data_ptr(), recv.data_ptr(), int(n_own), int(chunk_log2), _addr_array(param_addrs), exp_avg.data_ptr(),
+          exp_avg_sq.data_ptr(), int(rank), int(world), lr.data_ptr(), float(beta1), float(beta2), float(eps), float(weight_decay),
           float(grad_scale), state.data_ptr(), _stream())
+
+
+def memcpy2d_async(dst_addr: int, dpitch: int, src_addr: int, spitch: int, width: int, height: int) -> None:
+    """cudaMemcpy2DAsync device to device on the current stream (addresses / pitches / width in bytes)."""
+    _call("vqa_memcpy2d_async", int(dst_addr), int(dpitch), int(src_addr), int(spitch), int(width), int(height), _stream())
 
 
 # ------------------------------------------------------------------------------------------- batch assembly (loader.cu)

@@ -62,9 +62,9 @@ class FlatAdam(torch.optim.Optimizer):
     def _setup_p2p(self) -> None:
         """Data-parallel mode over NVLink peer memory (ddp.GradReducer(p2p=True)): the parameters move into ONE symmetric flat buffer
         with the gradient buffer's layout (every ``p.data`` becomes a view of it, values kept), so that the fused kernel
-        (``kernels.adam_flat_p2p``) can write every rank's parameters.  Each rank owns a contiguous 1/world slice of the flat index
-        space: the peers push their gradients for that slice into its receive buffer while backward runs (``ddp.GradReducer._push``),
-        it sums them, updates the slice (its moments are the only ones that ever change: optimizer state is sharded) and stores the
+        (``kernels.adam_flat_p2p``) can write every rank's parameters.  Each rank owns every world-th 256 KB chunk of the flat index
+        space: the peers push their gradients for those chunks into its receive buffer while backward runs (``ddp.GradReducer._push``),
+        it sums them, updates its chunks (its moments are the only ones that ever change: optimizer state is sharded) and stores the
         new values into all ranks' parameter buffers."""
         import torch.distributed as dist
         from .ddp import symmetric_empty
@@ -79,8 +79,6 @@ class FlatAdam(torch.optim.Optimizer):
                 v = self.pflat[p._vqa_flat_off:p._vqa_flat_off + p.numel()].view_as(p)
                 v.copy_(p)
                 p.data = v
-        per = r.per
-        self.slice = (min(r.total, r.rank * per), min(r.total, (r.rank + 1) * per))
         torch.cuda.synchronize(dev)
         dist.barrier(group=r.group)                   # every rank's flags are zero and its parameters in place before the first kernel barrier
 
@@ -92,17 +90,18 @@ class FlatAdam(torch.optim.Optimizer):
                                    "re-flattened after the optimiser was built?)")
 
     def gather_state(self) -> None:
-        """Make every rank's exp_avg / exp_avg_sq complete (each rank only ever updates its own slice): call before ``state_dict()``."""
+        """Make every rank's exp_avg / exp_avg_sq complete (each rank only ever updates its own chunks): call before ``state_dict()``."""
         if not self.p2p:
             return
         import torch.distributed as dist
         r = self.reducer
-        per = r.per
+        CH = 1 << r.chunk_log2
         for buf in (self.exp_avg, self.exp_avg_sq):
+            rows = buf.view(r.nrows, r.world, CH)
             for q in range(r.world):
-                lo, hi = min(r.total, q * per), min(r.total, (q + 1) * per)
-                if hi > lo:
-                    dist.broadcast(buf[lo:hi], src=dist.get_global_rank(r.group, q) if r.group is not None else q, group=r.group)
+                mine = rows[:, q, :].contiguous()
+                dist.broadcast(mine, src=dist.get_global_rank(r.group, q) if r.group is not None else q, group=r.group)
+                rows[:, q, :].copy_(mine)
 
     @property
     def steps_taken(self) -> int:
@@ -133,9 +132,16 @@ class FlatAdam(torch.optim.Optimizer):
             if missing:
                 raise RuntimeError(f"FlatAdam.step: parameters {missing} (reducer order) received no gradient in this step")
             r = self.reducer
+            import os
+            diag = os.environ.get("VQA_P2P_DIAG", "")             # timing diagnosis only (wrong results)
+            if "nobarrier" in diag or "nokernel" in diag:
+                if "nokernel" not in diag:
+                    kn.adam_flat_p2p(r.flat, r.recv, r.n_own, r.chunk_log2, self.peer_param_addrs, self.exp_avg, self.exp_avg_sq, r.rank, r.world,
+                                     self._lr, g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], 1.0 / r.world, self._state)
+                return loss
             kn.p2p_barrier(self.peer_flag_addrs, r.rank, r.world, self.epoch)      # every rank's gradients are written
-            kn.adam_flat_p2p(r.flat, r.recv, r.per, self.peer_param_addrs, self.exp_avg, self.exp_avg_sq, self.slice[0], self.slice[1], r.rank,
-                             r.world, self._lr, g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], 1.0 / r.world, self._state)
+            kn.adam_flat_p2p(r.flat, r.recv, r.n_own, r.chunk_log2, self.peer_param_addrs, self.exp_avg, self.exp_avg_sq, r.rank, r.world,
+                             self._lr, g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], 1.0 / r.world, self._state)
             kn.p2p_barrier(self.peer_flag_addrs, r.rank, r.world, self.epoch)      # every rank's parameters are complete
             return loss
         moved = [p.data_ptr() for p in self.reducer.params] != self._ptrs
