@@ -42,6 +42,7 @@ def parse():
                     help="criterion + optimiser: our single-launch kernels (vqa_b200.loss / vqa_b200.optim) or torch's modules")
     ap.add_argument("--no-resident-table", action="store_true", help="skip the ShardLoader (feature table in HBM) end-to-end leg")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying the captured CUDA graph")
+    ap.add_argument("--kernel-totals", default="", help="also run 10 steps under torch.profiler on rank 0 and write per-kernel device time totals to this file (diagnosis)")
     ap.add_argument("--quick", action="store_true", help="device-resident and end-to-end legs only (scaling experiments)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="questions per CPU step (bounded sample of the workload)")
     return ap.parse_args()
@@ -353,6 +354,24 @@ def run_b200(args, workload):
     ms_step = ms_total / args.steps
     value = w.batch * world / (ms_step * 1e-3)
     final_loss = float(loss.detach())
+
+    if args.kernel_totals:                # diagnosis: where does the device time of a step go (kernels inside the graph replays included)
+        from torch.profiler import profile, ProfilerActivity
+        barrier()
+        if rank == 0:
+            with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+                for i in range(10):
+                    run(resident[i % NB])
+                torch.cuda.synchronize()
+            rows = [(e.key, e.count, getattr(e, "device_time_total", getattr(e, "cuda_time_total", 0))) for e in prof.key_averages()]
+            rows = sorted([r for r in rows if r[2] > 0], key=lambda r: -r[2])
+            with open(args.kernel_totals, "w") as f:
+                json.dump({"n_gpus": world, "steps": 10, "ms_per_step": ms_step, "kernels": [{"name": k[:120], "count": c, "us_per_step": round(t / 10, 2)} for k, c, t in rows]}, f, indent=1)
+        else:
+            for i in range(10):
+                run(resident[i % NB])
+            torch.cuda.synchronize()
+        barrier()
 
     # ---- end to end through the public API: pinned host -> device every step, loss read back ---------------
     loss_host = torch.empty(2, dtype=torch.float32).pin_memory()

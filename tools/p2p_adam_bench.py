@@ -38,16 +38,18 @@ def timeit(name, fn, iters=20):
     t = torch.tensor([sorted(ts)[len(ts) // 2]], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0: print(json.dumps({"world": world, "what": name, "us": round(t.item(), 1)}), flush=True)
 
-CHL = 16; CH = 1 << CHL; row = CH * world
+CHL = 20; CH = 1 << CHL; row = CH * world
 nrows = (n + row - 1) // row; n = nrows * row; n_own = nrows * CH
 G = torch.randn(n, device=dev); m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
 P, paddr, h2 = symmetric_empty(n, torch.float32, dev)
 R_, raddr, h4 = symmetric_empty(world * n_own, torch.float32, dev)
 chunks = torch.tensor([[P.data_ptr() + 4 * s, s, min(4096, n - s)] for s in range(0, n, 4096)], dtype=torch.int64, device=dev)
+peers_r = [None if q == rank else h4.get_buffer(q, (world * n_own,), torch.float32, 0) for q in range(world)]
 def push():
     for d in range(1, world):
         q = (rank + d) % world
-        kn.memcpy2d_async(raddr[q] + (rank * n_own) * 4, CH * 4, G.data_ptr() + q * CH * 4, row * 4, CH * 4, nrows)
+        for k in range(nrows):
+            peers_r[q][rank * n_own + k * CH:rank * n_own + (k + 1) * CH].copy_(G[(k * world + q) * CH:(k * world + q + 1) * CH], non_blocking=True)
 def kernel(paddrs=None):
     kn.adam_flat_p2p(G, R_, n_own, CHL, paddr if paddrs is None else paddrs, m, v, rank, world, lr, 0.9, 0.999, 1e-8, 0.0, 1.0 / world, state)
 def fused():
@@ -58,6 +60,13 @@ def fused():
 def nccl():
     dist.all_reduce(G)
     kn.adam_flat(chunks, G, m, v, lr, 0.9, 0.999, 1e-8, 0.0, 1.0 / world, state)
+tmp = torch.empty(n, device=dev)
+timeit("read+write 121 MB: regular -> regular (torch copy_)", lambda: tmp.copy_(G))
+timeit("read+write 121 MB: symmetric -> regular", lambda: tmp.copy_(P))
+timeit("read+write 121 MB: regular -> symmetric", lambda: P.copy_(G))
+Gs = kn.split(G[:30_000_000].view(-1, 3000))
+timeit("split planes of a regular fp32 matrix (120 MB)", lambda: kn.split(G[:30_000_000].view(-1, 3000)))
+timeit("split planes of a symmetric fp32 matrix (120 MB)", lambda: kn.split(P[:30_000_000].view(-1, 3000)))
 timeit("flag barrier", lambda: kn.p2p_barrier(faddr, rank, world, epoch))
 timeit("copy-engine push of the gradient slices to their owners", push)
 timeit("sum + Adam on my slice + parameter stores to all ranks (one kernel)", kernel)

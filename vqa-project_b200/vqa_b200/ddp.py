@@ -89,8 +89,10 @@ class GradReducer:
                 # every rank owns a contiguous 1/world slice of the flat index space; `recv` holds, per peer, that peer's gradients
                 # for MY slice (pushed there by the peer, see _launch)
                 # interleaved ownership: chunk c of CH floats belongs to rank c % world, a "row" = world consecutive chunks, the buffers
-                # are padded to whole rows.  `recv` holds, per peer, that peer's gradients for MY chunks (pushed there, see _push_rows)
-                self.chunk_log2 = 16                                  # 65536 floats = 256 KB per chunk
+                # are padded to whole rows.  `recv` holds, per peer, that peer's gradients for MY chunks (pushed there, see _push).
+                # 4 MB chunks: one plain cudaMemcpyAsync per chunk (copy engines; strided cudaMemcpy2DAsync pushes of finer chunks were
+                # executed by SM copy kernels - 136 us of device time per step at N = 2, profiles/r02_p2p_adam.md)
+                self.chunk_log2 = 20                                  # 2^20 floats = 4 MB per chunk
                 CH = 1 << self.chunk_log2
                 row = CH * self.world
                 self.nrows = (total + row - 1) // row
@@ -98,14 +100,15 @@ class GradReducer:
                 self.n_own = self.nrows * CH
                 self.flat = torch.zeros(total, device=dev, dtype=dt)
                 self.recv, self.peer_recv_addrs, h = symmetric_empty(self.world * self.n_own, dt, dev, process_group)
+                self._peer_recv = [None if q == self.rank else h.get_buffer(q, (self.world * self.n_own,), dt, 0) for q in range(self.world)]
                 self._symm.append(h)
-                # a row may be pushed once every bucket it touches is complete
-                starts = [p._vqa_flat_off for p in self.params] + [1 << 62]
-                self._row_buckets = []
-                for k in range(self.nrows):
-                    a, e = k * row, (k + 1) * row
-                    self._row_buckets.append({self.bucket_of[i] for i in range(len(self.params)) if starts[i] < e and starts[i] + self.params[i].numel() > a})
-                self._row_pushed = [False] * self.nrows
+                # a chunk may be pushed once every bucket it touches is complete
+                starts = [p._vqa_flat_off for p in self.params]
+                self._chunk_buckets = []
+                for c in range(self.nrows * self.world):
+                    a, e = c * CH, (c + 1) * CH
+                    self._chunk_buckets.append({self.bucket_of[i] for i in range(len(self.params)) if starts[i] < e and starts[i] + self.params[i].numel() > a})
+                self._chunk_pushed = [False] * (self.nrows * self.world)
                 self._bucket_ready = [False] * len(self.bucket_size)
                 self.comm_stream = torch.cuda.Stream(device=dev)
                 self.p2p = True
@@ -181,31 +184,25 @@ class GradReducer:
         return hook
 
     def _push(self, b: int) -> None:
-        """p2p: bucket b is complete - copy every row that has now all its buckets complete into the owners' receive buffers: ONE
-        strided copy (cudaMemcpy2DAsync over NVLink: copy engines, no SMs taken from backward) per peer and run of rows, on a side
-        stream, ordered after everything enqueued so far on the current stream."""
+        """p2p: bucket b is complete - copy every chunk that has now all its buckets complete (and that another rank owns) into the
+        owner's receive buffer: one cudaMemcpyAsync over NVLink per chunk (copy engines, no SMs taken from backward) on a side stream,
+        ordered after everything enqueued so far on the current stream."""
         import os
-        from . import kernels as kn
         self._bucket_ready[b] = True
-        rows = [k for k in range(self.nrows) if not self._row_pushed[k] and all(self._bucket_ready[x] for x in self._row_buckets[k])]
-        if not rows or "nopush" in os.environ.get("VQA_P2P_DIAG", ""):       # (timing diagnosis only: wrong results)
+        W, CH = self.world, 1 << self.chunk_log2
+        todo = [c for c in range(self.nrows * W) if not self._chunk_pushed[c] and all(self._bucket_ready[x] for x in self._chunk_buckets[c])]
+        for c in todo:
+            self._chunk_pushed[c] = True
+        todo = [c for c in todo if c % W != self.rank]
+        if not todo or "nopush" in os.environ.get("VQA_P2P_DIAG", ""):       # (timing diagnosis only: wrong results)
             return
-        for k in rows:
-            self._row_pushed[k] = True
-        runs, k0 = [], rows[0]
-        for prev, k in zip(rows, rows[1:] + [None]):
-            if k != prev + 1:
-                runs.append((k0, prev + 1))
-                k0 = k
-        CH, W, es = 1 << self.chunk_log2, self.world, self.flat.element_size()
         cur = torch.cuda.current_stream(self.flat.device)
         self.comm_stream.wait_stream(cur)
         with torch.cuda.stream(self.comm_stream):
-            for d in range(1, W):                                # staggered: at any moment the ranks write to different peers
-                r = (self.rank + d) % W
-                for k0, k1 in runs:
-                    kn.memcpy2d_async(self.peer_recv_addrs[r] + (self.rank * self.n_own + k0 * CH) * es, CH * es,
-                                      self.flat.data_ptr() + (k0 * W * CH + r * CH) * es, W * CH * es, CH * es, k1 - k0)
+            for c in sorted(todo, key=lambda c: ((c % W - self.rank) % W, c)):     # staggered: the ranks start with different peers
+                r, k = c % W, c // W
+                o = self.rank * self.n_own + k * CH
+                self._peer_recv[r][o:o + CH].copy_(self.flat[c * CH:(c + 1) * CH], non_blocking=True)
 
     def _launch(self, b: int) -> None:
         self._launched_now[b] = True
@@ -238,7 +235,7 @@ class GradReducer:
         self._issued = [False] * len(self.params)
         self._launched_now = [False] * len(self.bucket_size)
         if self.p2p:
-            self._row_pushed = [False] * self.nrows
+            self._chunk_pushed = [False] * (self.nrows * self.world)
             self._bucket_ready = [False] * len(self.bucket_size)
 
     def finish(self) -> None:
