@@ -271,10 +271,19 @@ int vqa_mlsm_loss_bwd_f32(const float* logits, const float* target, const float*
  * q's gradients for the rank's elements in that order (pushed there by rank q before the barrier, e.g. with vqa_memcpy2d_async;
  * stride `rank` is unused); param_addrs: HOST array of `world` addresses - every rank's flat parameter buffer (layout of the
  * gradients) as mapped into THIS process; exp_avg / exp_avg_sq local, same layout.  g = grad_scale * sum over ranks in rank order,
- * Adam, P_q[i] = p for every q.  lr / state as in vqa_adam_flat_f32.  Bracket with vqa_p2p_barrier on every rank. */
-int vqa_adam_flat_p2p(const float* grad, const float* recv, long long n_own, int chunk_log2, const long long* param_addrs, float* exp_avg,
-                      float* exp_avg_sq, int rank, int world, const float* lr, float beta1, float beta2, float eps, float weight_decay,
+ * Adam, P_q[i] = p for every q.  lr / state as in vqa_adam_flat_f32.  Bracket with vqa_p2p_barrier on every rank.
+ * mc_param (optional): the MULTICAST address of the parameter buffers (NVLS); when given, the all-gather is one multimem.st per
+ * element instead of `world` stores. */
+int vqa_adam_flat_p2p(const float* grad, const float* recv, long long n_own, int chunk_log2, const long long* param_addrs, float* mc_param,
+                      float* exp_avg, float* exp_avg_sq, int rank, int world, const float* lr, float beta1, float beta2, float eps, float weight_decay,
                       float grad_scale, int* state, vqa_stream_t stream);
+/* The same exchange through NVSwitch multicast objects (NVLS): mc_grad / mc_param are the MULTICAST addresses of the ranks' flat gradient
+ * / parameter buffers (symmetric allocations bound to one multicast object), param / exp_avg / exp_avg_sq the local ones.  The rank
+ * owns the contiguous flat slice [lo, hi): one multimem.ld_reduce per element returns the sum over all ranks (added in the switch),
+ * one multimem.st delivers the updated parameter to every rank.  Bracket with vqa_p2p_barrier on every rank. */
+int vqa_adam_flat_mc(const float* mc_grad, float* mc_param, const float* param, float* exp_avg, float* exp_avg_sq, long long lo,
+                     long long hi, const float* lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, int* state,
+                     vqa_stream_t stream);
 /* cudaMemcpy2DAsync, device to device (pitches / width in bytes): the strided pushes of the interleaved layout above as ONE copy per
  * (bucket, peer) on the copy engines; capturable into a CUDA graph as a memcpy node. */
 int vqa_memcpy2d_async(void* dst, long long dpitch, const void* src, long long spitch, long long width, long long height,

@@ -71,7 +71,23 @@ timeit("flag barrier", lambda: kn.p2p_barrier(faddr, rank, world, epoch))
 timeit("copy-engine push of the gradient slices to their owners", push)
 timeit("sum + Adam on my slice + parameter stores to all ranks (one kernel)", kernel)
 timeit("the same kernel with all parameter stores local", lambda: kernel([paddr[rank]] * world))
+if h2.multicast_ptr:
+    timeit("the same kernel with ONE multicast store (multimem.st) instead of world stores",
+           lambda: kn.adam_flat_p2p(G, R_, n_own, CHL, paddr, m, v, rank, world, lr, 0.9, 0.999, 1e-8, 0.0, 1.0 / world, state, h2.multicast_ptr))
 timeit("whole tail, nothing hidden: push + barrier + kernel + barrier", fused)
+Gm, gmaddr, h5 = symmetric_empty(n, torch.float32, dev)
+Gm.copy_(G)
+per_c = (n // 4 + world - 1) // world * 4
+lo_c, hi_c = min(n, rank * per_c), min(n, (rank + 1) * per_c)
+if h5.multicast_ptr and h2.multicast_ptr:
+    def mc():
+        kn.adam_flat_mc(h5.multicast_ptr, h2.multicast_ptr, P, m, v, lo_c, hi_c, lr, 0.9, 0.999, 1e-8, 0.0, 1.0 / world, state)
+    def mc_tail():
+        kn.p2p_barrier(faddr, rank, world, epoch); mc(); kn.p2p_barrier(faddr, rank, world, epoch)
+    timeit("multicast kernel: multimem.ld_reduce + Adam + multimem.st", mc)
+    timeit("whole multicast tail: barrier + kernel + barrier", mc_tail)
+elif rank == 0:
+    print(json.dumps({"world": world, "what": "no multicast support on this box"}), flush=True)
 timeit("NCCL all-reduce (121 MB) + Adam on the whole buffer", nccl)
 timeit("Adam on the whole buffer (N = 1 work)", lambda: kn.adam_flat(chunks, G, m, v, lr, 0.9, 0.999, 1e-8, 0.0, 1.0, state))
 timeit("NCCL all-reduce (121 MB) alone", lambda: dist.all_reduce(G))

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(const AdamChunk* __restr
 // Two flag barriers (p2p_barrier_kernel) bracket it: all pushes landed before anyone sums, all parameters written before anyone's
 // next forward.
 constexpr int P2P_MAX_WORLD = 16;
-struct P2PPtrs { float* p[P2P_MAX_WORLD]; };
+struct P2PPtrs { float* p[P2P_MAX_WORLD]; float* mc; };   // mc: multicast address of the parameter buffers (NVLS) or null
 
 // Ownership is interleaved: the flat index space is cut into chunks of 2^ch_log2 floats, chunk c belongs to rank c % world ("row" k =
 // chunks k * world .. k * world + world - 1), so every gradient bucket spreads evenly over the owners and its push can start the
@@ -230,10 +230,61 @@ __global__ void __launch_bounds__(256) adam_p2p_kernel(const __grid_constant__ P
     adam_one(w.w, gg.w, mm.w, vv.w, grad_scale, wd, b1, b2, step_size, isb2, eps);
     reinterpret_cast<float4*>(exp_avg)[i] = mm;
     reinterpret_cast<float4*>(exp_avg_sq)[i] = vv;
+    if (pp.mc) {                                            // one multicast store: the switch delivers it to every rank
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                   ::"l"(pp.mc + 4 * i), "f"(w.x), "f"(w.y), "f"(w.z), "f"(w.w) : "memory");
+    } else {
 #pragma unroll 4
-    for (int q = 0; q < world; ++q) reinterpret_cast<float4*>(pp.p[q])[i] = w;
+      for (int q = 0; q < world; ++q) reinterpret_cast<float4*>(pp.p[q])[i] = w;
+    }
   }
   __threadfence_system();                                   // my parameter stores are performed before the barrier kernel announces them
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(state + 1, 1) == (int)gridDim.x - 1) {
+      state[0] = s_step;
+      state[1] = 0;
+    }
+  }
+}
+
+// The same step through the NVSwitch's multicast objects (NVLS): with the gradient and parameter buffers bound to a multicast address,
+// ONE multimem.ld_reduce returns the sum of an element over all ranks (added inside the switch: the rank receives its 1/N slice once
+// instead of N-1 copies of it) and ONE multimem.st delivers the updated parameter to every rank.  No pushes, no receive buffers, one
+// store instruction instead of N.  The rank owns the contiguous flat slice [lo4, hi4) (float4 units).
+__global__ void __launch_bounds__(256) adam_mc_kernel(const float* __restrict__ mc_grad, float* __restrict__ mc_param,
+                                                      const float* __restrict__ param, float* __restrict__ exp_avg,
+                                                      float* __restrict__ exp_avg_sq, long long lo4, long long hi4,
+                                                      const float* __restrict__ hyper, float b1, float b2, float eps, float wd,
+                                                      float grad_scale, int* __restrict__ state) {
+  __shared__ float s_step_size, s_inv_sqrt_bc2;
+  __shared__ int s_step;
+  if (threadIdx.x == 0) {
+    const int step = state[0] + 1;
+    const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
+    s_step = step;
+    s_step_size = (float)((double)__ldg(hyper) / bc1);
+    s_inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  }
+  __syncthreads();
+  const float step_size = s_step_size, isb2 = s_inv_sqrt_bc2;
+  for (long long i = lo4 + (long long)blockIdx.x * 256 + threadIdx.x; i < hi4; i += (long long)gridDim.x * 256) {
+    float4 gg;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(gg.x), "=f"(gg.y), "=f"(gg.z), "=f"(gg.w) : "l"(mc_grad + 4 * i) : "memory");
+    float4 w = reinterpret_cast<const float4*>(param)[i];
+    float4 mm = reinterpret_cast<float4*>(exp_avg)[i];
+    float4 vv = reinterpret_cast<float4*>(exp_avg_sq)[i];
+    adam_one(w.x, gg.x, mm.x, vv.x, grad_scale, wd, b1, b2, step_size, isb2, eps);
+    adam_one(w.y, gg.y, mm.y, vv.y, grad_scale, wd, b1, b2, step_size, isb2, eps);
+    adam_one(w.z, gg.z, mm.z, vv.z, grad_scale, wd, b1, b2, step_size, isb2, eps);
+    adam_one(w.w, gg.w, mm.w, vv.w, grad_scale, wd, b1, b2, step_size, isb2, eps);
+    reinterpret_cast<float4*>(exp_avg)[i] = mm;
+    reinterpret_cast<float4*>(exp_avg_sq)[i] = vv;
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+                 ::"l"(mc_param + 4 * i), "f"(w.x), "f"(w.y), "f"(w.z), "f"(w.w) : "memory");
+  }
+  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
     if (atomicAdd(state + 1, 1) == (int)gridDim.x - 1) {
@@ -326,7 +377,7 @@ extern "C" int vqa_p2p_barrier(const long long* flag_addrs, int rank, int world,
 }
 
 extern "C" int vqa_adam_flat_p2p(const float* grad, const float* recv, long long n_own, int chunk_log2, const long long* param_addrs,
-                                 float* exp_avg, float* exp_avg_sq, int rank, int world, const float* lr, float beta1, float beta2,
+                                 float* mc_param, float* exp_avg, float* exp_avg_sq, int rank, int world, const float* lr, float beta1, float beta2,
                                  float eps, float weight_decay, float grad_scale, int* state, cudaStream_t stream) {
   VQA_CHECK_ARG(grad && recv && param_addrs && exp_avg && exp_avg_sq && lr && state, "vqa_adam_flat_p2p: null pointer");
   VQA_CHECK_ARG(world >= 1 && world <= P2P_MAX_WORLD && rank >= 0 && rank < world, "vqa_adam_flat_p2p: rank %d of %d (at most %d ranks)", rank, world, P2P_MAX_WORLD);
@@ -339,6 +390,7 @@ extern "C" int vqa_adam_flat_p2p(const float* grad, const float* recv, long long
     VQA_CHECK_ARG(param_addrs[q] && (param_addrs[q] & 15) == 0, "vqa_adam_flat_p2p: rank %d's parameter buffer must be mapped and 16-byte aligned", q);
     pp.p[q] = reinterpret_cast<float*>(param_addrs[q]);
   }
+  pp.mc = mc_param;
   const long long n4 = n_own >> 2;
   if (n4 == 0) return VQA_OK;
   long long blocks = (n4 + 255) / 256;
@@ -353,5 +405,22 @@ extern "C" int vqa_memcpy2d_async(void* dst, long long dpitch, const void* src, 
                                   cudaStream_t stream) {
   VQA_CHECK_ARG(dst && src && width > 0 && height > 0 && dpitch >= width && spitch >= width, "vqa_memcpy2d_async: bad arguments");
   VQA_CUDA(cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width, (size_t)height, cudaMemcpyDeviceToDevice, stream));
+  return VQA_OK;
+}
+
+extern "C" int vqa_adam_flat_mc(const float* mc_grad, float* mc_param, const float* param, float* exp_avg, float* exp_avg_sq, long long lo,
+                                long long hi, const float* lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                                int* state, cudaStream_t stream) {
+  VQA_CHECK_ARG(mc_grad && mc_param && param && exp_avg && exp_avg_sq && lr && state, "vqa_adam_flat_mc: null pointer");
+  VQA_CHECK_ARG(lo >= 0 && hi >= lo && (lo & 3) == 0 && (hi & 3) == 0, "vqa_adam_flat_mc: the slice [%lld, %lld) must be float4 aligned", lo, hi);
+  VQA_CHECK_ARG(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "vqa_adam_flat_mc: betas must be in [0,1) and eps >= 0");
+  VQA_CHECK_ARG(aligned16(mc_grad) && aligned16(mc_param) && aligned16(param) && aligned16(exp_avg) && aligned16(exp_avg_sq), "vqa_adam_flat_mc: buffers must be 16-byte aligned");
+  const long long n4 = (hi - lo) >> 2;
+  if (n4 == 0) return VQA_OK;
+  long long blocks = (n4 + 255) / 256;
+  if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+  adam_mc_kernel<<<(unsigned)blocks, 256, 0, stream>>>(mc_grad, mc_param, param, exp_avg, exp_avg_sq, lo >> 2, hi >> 2, lr, beta1, beta2, eps,
+                                                       weight_decay, grad_scale, state);
+  VQA_LAUNCH_CHECK("adam_mc_kernel");
   return VQA_OK;
 }

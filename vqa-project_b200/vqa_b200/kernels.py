@@ -662,16 +662,25 @@ def p2p_barrier(flag_addrs, rank: int, world: int, epoch: torch.Tensor) -> None:
 
 def adam_flat_p2p(grad: torch.Tensor, recv: torch.Tensor, n_own: int, chunk_log2: int, param_addrs, exp_avg: torch.Tensor,
                   exp_avg_sq: torch.Tensor, rank: int, world: int, lr: torch.Tensor, beta1: float, beta2: float, eps: float,
-                  weight_decay: float, grad_scale: float, state: torch.Tensor) -> None:
+                  weight_decay: float, grad_scale: float, state: torch.Tensor, mc_param_addr: int = 0) -> None:
     """Sum of the pushed gradient chunks + Adam on the rank's elements + all-gather of the new parameters over NVLink peer memory, one
     launch (include/vqa_b200.h)."""
     _chk(grad, "adam grad"); _chk(recv, "adam recv"); _chk(exp_avg, "adam exp_avg"); _chk(exp_avg_sq, "adam exp_avg_sq")
     _chk(lr, "adam lr"); _chk(state, "adam state", torch.int32)
     if recv.numel() < world * n_own:
         raise RuntimeError("adam_flat_p2p: the receive buffer must hold world strides of n_own floats")
-    _call("vqa_adam_flat_p2p", grad.data_ptr(), recv.data_ptr(), int(n_own), int(chunk_log2), _addr_array(param_addrs), exp_avg.data_ptr(),
-          exp_avg_sq.data_ptr(), int(rank), int(world), lr.data_ptr(), float(beta1), float(beta2), float(eps), float(weight_decay),
+    _call("vqa_adam_flat_p2p", grad.data_ptr(), recv.data_ptr(), int(n_own), int(chunk_log2), _addr_array(param_addrs),
+          int(mc_param_addr) or None, exp_avg.data_ptr(), exp_avg_sq.data_ptr(), int(rank), int(world), lr.data_ptr(), float(beta1), float(beta2), float(eps), float(weight_decay),
           float(grad_scale), state.data_ptr(), _stream())
+
+
+def adam_flat_mc(mc_grad_addr: int, mc_param_addr: int, param: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, lo: int, hi: int,
+                 lr: torch.Tensor, beta1: float, beta2: float, eps: float, weight_decay: float, grad_scale: float, state: torch.Tensor) -> None:
+    """In-switch sum of the ranks' gradients (multimem.ld_reduce) + Adam on flat elements [lo, hi) + multicast store of the new
+    parameters (multimem.st), one launch (include/vqa_b200.h)."""
+    _chk(param, "adam param"); _chk(exp_avg, "adam exp_avg"); _chk(exp_avg_sq, "adam exp_avg_sq"); _chk(lr, "adam lr"); _chk(state, "adam state", torch.int32)
+    _call("vqa_adam_flat_mc", int(mc_grad_addr), int(mc_param_addr), param.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), int(lo), int(hi),
+          lr.data_ptr(), float(beta1), float(beta2), float(eps), float(weight_decay), float(grad_scale), state.data_ptr(), _stream())
 
 
 def memcpy2d_async(dst_addr: int, dpitch: int, src_addr: int, spitch: int, width: int, height: int) -> None:

@@ -70,7 +70,10 @@ class FlatAdam(torch.optim.Optimizer):
         from .ddp import symmetric_empty
         r = self.reducer
         dev = r.flat.device
+        import os
         self.pflat, self.peer_param_addrs, h = symmetric_empty(r.total, torch.float32, dev, r.group)
+        # NVLS: when the switch offers a multicast address for the buffer, the all-gather is one multimem.st per element
+        self.mc_param_addr = int(getattr(h, "multicast_ptr", 0) or 0) if os.environ.get("VQA_P2P_MULTICAST", "1") != "0" else 0
         self.flags, self.peer_flag_addrs, h2 = symmetric_empty(64, torch.int32, dev, r.group)
         r._symm += [h, h2]
         self.epoch = torch.zeros(1, device=dev, dtype=torch.int32)
@@ -141,7 +144,7 @@ class FlatAdam(torch.optim.Optimizer):
                 return loss
             kn.p2p_barrier(self.peer_flag_addrs, r.rank, r.world, self.epoch)      # every rank's gradients are written
             kn.adam_flat_p2p(r.flat, r.recv, r.n_own, r.chunk_log2, self.peer_param_addrs, self.exp_avg, self.exp_avg_sq, r.rank, r.world,
-                             self._lr, g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], 1.0 / r.world, self._state)
+                             self._lr, g["betas"][0], g["betas"][1], g["eps"], g["weight_decay"], 1.0 / r.world, self._state, self.mc_param_addr)
             kn.p2p_barrier(self.peer_flag_addrs, r.rank, r.world, self.epoch)      # every rank's parameters are complete
             return loss
         moved = [p.data_ptr() for p in self.reducer.params] != self._ptrs
