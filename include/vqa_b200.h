@@ -20,7 +20,7 @@ extern "C" {
 
 typedef struct CUstream_st* vqa_stream_t; /* cudaStream_t */
 
-#define VQA_ABI_VERSION 9
+#define VQA_ABI_VERSION 10
 
 /* GEMM precision modes */
 #define VQA_PREC_TF32X3 0 /* 3-pass split TF32 on tcgen05: fp32-grade results (parity mode)      */
