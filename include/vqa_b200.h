@@ -198,6 +198,12 @@ int vqa_graphconv_mma_bwd_edges(const void* dO_hi, const void* dO_lo, long long 
 
 /* Gaussian patch weights for explicit pseudo-coordinates (n,2) -> (n,nk): NeighbourhoodGraphConvolution.
  * get_gaussian_weights, layers.py:100-125 (layer-level API). */
+/* The patch operator of the layer-level API on MATERIALISED neighbourhoods, layers.py:127-137 (torch.bmm(weights^T, neighbourhood)):
+ * Z[n,k,:] = sum_m w[n,m,k] X[n,m,:]  with X (n, nb, F), w (n, nb, nk) -> Z (n, nk, F), all contiguous fp32.
+ * Backward: dX[n,m,:] = sum_k w[n,m,k] dZ[n,k,:] (optional), dw[n,m,k] = <X[n,m,:], dZ[n,k,:]> (optional). */
+int vqa_patch_operator_fwd_f32(const float* X, const float* w, float* Z, long long n, int nb, int nk, int F, vqa_stream_t stream);
+int vqa_patch_operator_bwd_f32(const float* X, const float* w, const float* dZ, float* dX, float* dw, long long n, int nb, int nk,
+                               int F, vqa_stream_t stream);
 int vqa_gaussian_weights_f32(const float* pseudo, const float* gauss, float* w, long long n, int nk,
                              vqa_stream_t stream);
 

@@ -657,3 +657,18 @@ def test_out_of_range_token_is_flagged_like_nn_embedding(kn):
     kn.embed_gather_split(q, wemb, 7)
     with pytest.raises(IndexError):
         kn.check_device_errors()
+
+
+@pytest.mark.parametrize("n,nb,nk,F", [(72, 16, 8, 2052), (24, 5, 4, 20), (9, 19, 32, 132), (5, 3, 2, 7)])
+def test_patch_operator_fwd_bwd(kn, n, nb, nk, F):
+    """The layer API's patch operator (reference layers.py:136-137: torch.bmm(weights^T, neighbourhood)) and its backward vs fp64."""
+    g = torch.Generator().manual_seed(n + nb)
+    X = torch.randn(n, nb, F, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.rand(n, nb, nk, generator=g, dtype=torch.float64, requires_grad=True)
+    Z = torch.bmm(w.transpose(1, 2), X)
+    dZ = torch.randn(n, nk, F, generator=g, dtype=torch.float64)
+    gX, gw = torch.autograd.grad((Z * dZ).sum(), [X, w])
+    Zc = kn.patch_operator_fwd(X.detach().float().to(DEV), w.detach().float().to(DEV))
+    assert rel_err(Zc.cpu(), Z.detach()) < 2e-6
+    dX, dw = kn.patch_operator_bwd(X.detach().float().to(DEV), w.detach().float().to(DEV), dZ.float().to(DEV))
+    assert rel_err(dX.cpu(), gX) < 2e-6 and rel_err(dw.cpu(), gw) < 5e-6

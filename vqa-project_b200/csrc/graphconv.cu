@@ -995,3 +995,96 @@ extern "C" int vqa_gaussian_weights_f32(const float* pseudo, const float* gauss,
   VQA_LAUNCH_CHECK("gaussian_weights_kernel");
   return VQA_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ layer-level patch operator
+// layers.py:127-137 on MATERIALISED neighbourhoods (the module API `NeighbourhoodGraphConvolution.convolution`): per node n
+//   Z[n, k, :] = sum_m w[n, m, k] * X[n, m, :]          (torch.bmm(weights^T, neighbourhood) in the reference)
+// HBM-bound: X (n, nb, F) is read once, Z (n, nk, F) written once; one CTA per node, a thread owns float4 columns and keeps up
+// to 8 kernels' accumulators in registers.  Backward: dX[n,m,:] = sum_k w[n,m,k] dZ[n,k,:], dw[n,m,k] = <X[n,m,:], dZ[n,k,:]>.
+namespace vqa {
+constexpr int PO_THREADS = 256;
+
+__global__ void __launch_bounds__(PO_THREADS) patch_operator_fwd_kernel(const float* __restrict__ X, const float* __restrict__ w,
+                                                                        float* __restrict__ Z, int nb, int nk, int F) {
+  extern __shared__ float ws[];                         // [nb][nk]
+  const long long n = blockIdx.x;
+  for (int v = threadIdx.x; v < nb * nk; v += PO_THREADS) ws[v] = w[n * nb * nk + v];
+  __syncthreads();
+  const float* Xn = X + n * (long long)nb * F;
+  float* Zn = Z + n * (long long)nk * F;
+  const bool vec = (F & 3) == 0 && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Z)) & 15) == 0;
+  if (vec) {
+    const int F4 = F >> 2;
+    for (int c = threadIdx.x; c < F4; c += PO_THREADS)
+      for (int k0 = 0; k0 < nk; k0 += 8) {
+        float4 acc[8];
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) acc[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int m = 0; m < nb; ++m) {
+          const float4 x = reinterpret_cast<const float4*>(Xn + (long long)m * F)[c];
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const float wk = k0 + kk < nk ? ws[m * nk + k0 + kk] : 0.f;
+            acc[kk].x = fmaf(wk, x.x, acc[kk].x); acc[kk].y = fmaf(wk, x.y, acc[kk].y);
+            acc[kk].z = fmaf(wk, x.z, acc[kk].z); acc[kk].w = fmaf(wk, x.w, acc[kk].w);
+          }
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          if (k0 + kk < nk) reinterpret_cast<float4*>(Zn + (long long)(k0 + kk) * F)[c] = acc[kk];
+      }
+  } else {
+    for (int c = threadIdx.x; c < F; c += PO_THREADS)
+      for (int k = 0; k < nk; ++k) {
+        float acc = 0.f;
+        for (int m = 0; m < nb; ++m) acc = fmaf(ws[m * nk + k], Xn[(long long)m * F + c], acc);
+        Zn[(long long)k * F + c] = acc;
+      }
+  }
+}
+
+__global__ void __launch_bounds__(PO_THREADS) patch_operator_bwd_kernel(const float* __restrict__ X, const float* __restrict__ w,
+                                                                        const float* __restrict__ dZ, float* __restrict__ dX,
+                                                                        float* __restrict__ dw, int nb, int nk, int F) {
+  extern __shared__ float ws[];                         // [nb][nk]
+  const long long n = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int v = threadIdx.x; v < nb * nk; v += PO_THREADS) ws[v] = w[n * nb * nk + v];
+  __syncthreads();
+  const float* Xn = X + n * (long long)nb * F;
+  const float* dZn = dZ + n * (long long)nk * F;
+  if (dX) {
+    float* dXn = dX + n * (long long)nb * F;
+    for (int c = threadIdx.x; c < F; c += PO_THREADS)
+      for (int m = 0; m < nb; ++m) {
+        float acc = 0.f;
+        for (int k = 0; k < nk; ++k) acc = fmaf(ws[m * nk + k], dZn[(long long)k * F + c], acc);   // dZ rows of this node stay in L1
+        dXn[(long long)m * F + c] = acc;
+      }
+  }
+  if (dw) {
+    for (int pr = warp; pr < nb * nk; pr += PO_THREADS / 32) {       // one (m, k) pair per warp pass
+      const int m = pr / nk, k = pr - m * nk;
+      float acc = 0.f;
+      for (int c = lane; c < F; c += 32) acc = fmaf(Xn[(long long)m * F + c], dZn[(long long)k * F + c], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) dw[n * nb * nk + pr] = acc;
+    }
+  }
+}
+}  // namespace vqa
+
+extern "C" int vqa_patch_operator_fwd_f32(const float* X, const float* w, float* Z, long long n, int nb, int nk, int F, cudaStream_t stream) {
+  VQA_CHECK_ARG(X && w && Z && n > 0 && nb > 0 && nk > 0 && F > 0 && nb * nk <= 8192, "vqa_patch_operator_fwd_f32: bad arguments");
+  vqa::patch_operator_fwd_kernel<<<(unsigned)n, vqa::PO_THREADS, (size_t)nb * nk * sizeof(float), stream>>>(X, w, Z, nb, nk, F);
+  VQA_LAUNCH_CHECK("patch_operator_fwd_kernel");
+  return VQA_OK;
+}
+
+extern "C" int vqa_patch_operator_bwd_f32(const float* X, const float* w, const float* dZ, float* dX, float* dw, long long n, int nb,
+                                          int nk, int F, cudaStream_t stream) {
+  VQA_CHECK_ARG(X && w && dZ && (dX || dw) && n > 0 && nb > 0 && nk > 0 && F > 0 && nb * nk <= 8192, "vqa_patch_operator_bwd_f32: bad arguments");
+  vqa::patch_operator_bwd_kernel<<<(unsigned)n, vqa::PO_THREADS, (size_t)nb * nk * sizeof(float), stream>>>(X, w, dZ, dX, dw, nb, nk, F);
+  VQA_LAUNCH_CHECK("patch_operator_bwd_kernel");
+  return VQA_OK;
+}

@@ -132,13 +132,11 @@ class NeighbourhoodGraphConvolution(nn.Module):
         return ops.GaussianWeightsFn.apply(pseudo_coord.contiguous(), *self.gaussian_parameters())
 
     def convolution(self, neighbourhood, weights):
-        """(B*K, nb, in), (B*K, nb, nk) -> (B*K, out): project every neighbour with the stacked weight on the
-        tensor cores, then weight and sum over the neighbourhood per kernel chunk."""
+        """(B*K, nb, in), (B*K, nb, nk) -> (B*K, out), in the reference's own order (layers.py:127-144): the patch operator
+        Z[:, k] = sum_m weights[:, m, k] * neighbourhood[:, m] as one HBM-bound kernel (the reference's ``torch.bmm``), then the
+        k-th bias-free linear map on Z[:, k] as a tcgen05 GEMM reading its slice of Z in place."""
         n, nb, fin = neighbourhood.shape
         nk, d = self.n_kernels, self.out_feat_dim // self.n_kernels
-        w_all = torch.cat([lin.weight for lin in self.conv_weights], dim=0)
-        y = ops.LinearFn.apply(neighbourhood.reshape(n * nb, fin), w_all, None, False).view(n, nb, nk, d)
-        out = (weights.unsqueeze(-1) * y).sum(dim=1)
-        if self.bias:
-            out = out + torch.stack([lin.bias for lin in self.conv_weights], dim=0)
-        return out.reshape(n, self.out_feat_dim)
+        z = ops.PatchOperatorFn.apply(neighbourhood, weights)                  # (n, nk, in)
+        wb = [lin.weight for lin in self.conv_weights] + ([lin.bias for lin in self.conv_weights] if self.bias else [])
+        return ops.PerKernelLinearFn.apply(z, nk, bool(self.bias), *wb)

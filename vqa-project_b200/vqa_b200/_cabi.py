@@ -63,6 +63,8 @@ SIGNATURES = {
     "vqa_gate_bwd_f32": [_p, _p, _p, _p, _p, _ll, _p],
     "vqa_mlsm_loss_blocks": [_ll],
     "vqa_set_sm_budget": [_i],
+    "vqa_patch_operator_fwd_f32": [_p, _p, _p, _ll, _i, _i, _i, _p],
+    "vqa_patch_operator_bwd_f32": [_p, _p, _p, _p, _p, _ll, _i, _i, _i, _p],
     "vqa_adam_flat_p2p": [_p, _p, _ll, _i, _p, _p, _p, _p, _i, _i, _p, _f, _f, _f, _f, _f, _p, _p],
     "vqa_memcpy2d_async": [_p, _ll, _p, _ll, _ll, _ll, _p],
     "vqa_adam_flat_mc": [_p, _p, _p, _p, _p, _ll, _ll, _p, _f, _f, _f, _f, _f, _p, _p],

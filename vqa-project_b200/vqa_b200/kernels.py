@@ -489,6 +489,28 @@ def graphconv_bwd_edges_s(Ys: SplitT, idx, alpha, image, gauss, B, K, dOs: Optio
     return dalpha, colsum(partial)
 
 
+def patch_operator_fwd(X: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """X (n, nb, F), w (n, nb, nk) -> Z (n, nk, F): Z[n,k] = sum_m w[n,m,k] X[n,m]  (layers.py:136-137)."""
+    X = _chk(X, "patch operator X").contiguous(); w = _chk(w, "patch operator w").contiguous()
+    n, nb, F = X.shape
+    if w.shape[:2] != (n, nb):
+        raise RuntimeError(f"patch_operator: weights {tuple(w.shape)} do not match neighbourhoods {tuple(X.shape)}")
+    nk = w.shape[2]
+    Z = torch.empty((n, nk, F), device=X.device, dtype=torch.float32)
+    _call("vqa_patch_operator_fwd_f32", X.data_ptr(), w.data_ptr(), Z.data_ptr(), n, nb, nk, F, _stream())
+    return Z
+
+
+def patch_operator_bwd(X: torch.Tensor, w: torch.Tensor, dZ: torch.Tensor, want_dX: bool = True, want_dw: bool = True):
+    X = _chk(X, "patch operator X").contiguous(); w = _chk(w, "patch operator w").contiguous(); dZ = _chk(dZ, "patch operator dZ").contiguous()
+    n, nb, F = X.shape
+    nk = w.shape[2]
+    dX = torch.empty_like(X) if want_dX else None
+    dw = torch.empty_like(w) if want_dw else None
+    _call("vqa_patch_operator_bwd_f32", X.data_ptr(), w.data_ptr(), dZ.data_ptr(), _ptr(dX), _ptr(dw), n, nb, nk, F, _stream())
+    return dX, dw
+
+
 def gaussian_weights(pseudo: torch.Tensor, gauss: torch.Tensor) -> torch.Tensor:
     pseudo = _chk(pseudo, "pseudo").contiguous().view(-1, 2)
     nk = gauss.numel() // 4

@@ -572,6 +572,63 @@ class AdjacencyFn(torch.autograd.Function):
         return kn.adjacency_topk_bwd(h, idx, alpha, torch.zeros_like(alpha), dadj.contiguous())
 
 
+class PatchOperatorFn(torch.autograd.Function):
+    """Z[n,k,:] = sum_m w[n,m,k] X[n,m,:] on materialised neighbourhoods (reference layers.py:136-137), kernels both ways."""
+
+    @staticmethod
+    def forward(ctx, X, w):
+        X = X.contiguous(); w = w.contiguous()
+        ctx.save_for_backward(X, w)
+        return kn.patch_operator_fwd(X, w)
+
+    @staticmethod
+    def backward(ctx, dZ):
+        X, w = ctx.saved_tensors
+        return kn.patch_operator_bwd(X, w, dZ.contiguous(), ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+
+
+class PerKernelLinearFn(torch.autograd.Function):
+    """out[:, k*D:(k+1)*D] = Z[:, k, :] W_k^T (+ b_k) for the nk bias-free (by default) linear maps of layers.py:139-142, every product
+    a tcgen05 GEMM that reads its slice of Z / writes its slice of the output in place.  The backward writes dZ slice by slice too:
+    the reference's autograd zero-fills a Z-sized tensor per kernel here (``select_backward``)."""
+
+    @staticmethod
+    def forward(ctx, z, nk, has_bias, *wb):
+        z = z.contiguous()
+        n, _, fin = z.shape
+        ws, bs = wb[:nk], (wb[nk:] if has_bias else (None,) * nk)
+        d = ws[0].shape[0]
+        if fin % 4 or d % 4:
+            raise RuntimeError(f"NeighbourhoodGraphConvolution.convolution: in_feat_dim ({fin}) and out_feat_dim / n_kernels ({d}) must be "
+                               "multiples of 4 (16-byte aligned rows for the TMA loads)")
+        z2 = z.view(n, nk * fin)
+        out = torch.empty((n, nk * d), device=z.device, dtype=torch.float32)
+        for k in range(nk):
+            _gemm(z2[:, k * fin:(k + 1) * fin], ws[k].contiguous(), out=out[:, k * d:(k + 1) * d], bias=bs[k])
+        ctx.nk, ctx.has_bias = nk, has_bias
+        ctx.save_for_backward(z, *ws)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        z, *ws = ctx.saved_tensors
+        nk = ctx.nk
+        n, _, fin = z.shape
+        d = ws[0].shape[0]
+        dout = dout.contiguous()
+        z2 = z.view(n, nk * fin)
+        dz = torch.empty_like(z) if ctx.needs_input_grad[0] else None
+        dws, dbs = [], []
+        for k in range(nk):
+            dk = dout[:, k * d:(k + 1) * d]
+            if dz is not None:
+                _gemm(dk, ws[k].contiguous(), b_mn=True, out=dz.view(n, nk * fin)[:, k * fin:(k + 1) * fin])
+            dws.append(_gemm(dk, z2[:, k * fin:(k + 1) * fin], a_mn=True, b_mn=True, split_k=_split_for(d, fin, n)))
+            if ctx.has_bias:
+                dbs.append(kn.colsum(dk))
+        return (dz, None, None, *dws, *dbs)
+
+
 def _gaussian_weights_torch(pseudo, mr, pr, mt, pt):
     """Differentiable re-evaluation (torch ops) used only for the BACKWARD of the layer-level API."""
     import math
