@@ -866,6 +866,14 @@ struct PParams {
   int off_stage, a_plane, b_plane, stage_bytes, off_pd, off_pacc, off_red, off_misc, off_bars, tmem_cols;
 };
 
+#ifdef VQA_EDGE_TRACE
+// Development build only (make EXTRA=-DVQA_EDGE_TRACE, tools/edge_trace.py): %globaltimer stamps of the phases of each CTA.
+__device__ unsigned long long g_edge_trace[16 * 4096];
+#define EDGE_STAMP(T, I) do { if (tid == (T) && b < 4096) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_edge_trace[b * 16 + (I)] = t_; } } while (0)
+#else
+#define EDGE_STAMP(T, I) do { } while (0)
+#endif
+
 template <bool POOLED>
 __global__ void __launch_bounds__(THREADS)
 edge_p_kernel(const __grid_constant__ PMaps tm, const PParams p) {
@@ -876,6 +884,10 @@ edge_p_kernel(const __grid_constant__ PMaps tm, const PParams p) {
   const int planes = p.with_lo ? 2 : 1;
   const int nblk = p.nblk;                                 // 64-column blocks per kernel chunk
   const int total = nk * nblk;                             // pipeline items
+  EDGE_STAMP(0, 0);
+#ifdef VQA_EDGE_TRACE
+  if (tid == 0 && b < 4096) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_edge_trace[b * 16 + 15] = sm_; }
+#endif
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + p.off_bars);
   uint64_t* full = bars;
@@ -925,6 +937,7 @@ edge_p_kernel(const __grid_constant__ PMaps tm, const PParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  EDGE_STAMP(0, 1);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer: item = (kernel k, 64-column block)
@@ -1004,6 +1017,7 @@ edge_p_kernel(const __grid_constant__ PMaps tm, const PParams p) {
         }
       }
       mbar_wait(&tfull[acc], (k >> 1) & 1);
+      if (k < 8) EDGE_STAMP(64, 2 + k);
       tc_fence_after();
       if (q4 * 32 < K) {                                    // warp-uniform: the .sync.aligned loads need the whole warp
         for (int j0 = 0; j0 < K; j0 += 16) {
@@ -1025,6 +1039,7 @@ edge_p_kernel(const __grid_constant__ PMaps tm, const PParams p) {
     }
   }
   __syncthreads();
+  EDGE_STAMP(0, 10);
 
   // ------------------------------------------------------------ edge finish (all threads): dalpha and Gaussian-parameter partials
   // per-kernel constants without divisions in the edge loop: gs[6nk..10nk) = 1/vr | sr/vr^2 | 1/vt | st/vt^2
@@ -1080,6 +1095,7 @@ edge_p_kernel(const __grid_constant__ PMaps tm, const PParams p) {
         }
       }
     }
+    EDGE_STAMP(0, 11);
     // transposed reduction through shared memory: thread t writes its 32 partials, then 32 threads sum a column each
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -1096,6 +1112,7 @@ edge_p_kernel(const __grid_constant__ PMaps tm, const PParams p) {
   }
   tc_fence_before();
   __syncthreads();
+  EDGE_STAMP(0, 12);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
   }
@@ -1398,3 +1415,11 @@ extern "C" int vqa_graphconv_pool_bwd_data(const float* dpooled, const long long
   VQA_LAUNCH_CHECK("graphconv pool_bwd_data_kernel");
   return VQA_OK;
 }
+
+#ifdef VQA_EDGE_TRACE
+extern "C" int vqa_debug_edge_trace(unsigned long long* out, int n_ctas) {
+  if (n_ctas > 4096) n_ctas = 4096;
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, gm::g_edge_trace, (size_t)n_ctas * 16 * sizeof(unsigned long long)) == cudaSuccess ? VQA_OK : VQA_ERR_CUDA;
+}
+#endif
