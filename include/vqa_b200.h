@@ -20,7 +20,7 @@ extern "C" {
 
 typedef struct CUstream_st* vqa_stream_t; /* cudaStream_t */
 
-#define VQA_ABI_VERSION 10
+#define VQA_ABI_VERSION 11
 
 /* GEMM precision modes */
 #define VQA_PREC_TF32X3 0 /* 3-pass split TF32 on tcgen05: fp32-grade results (parity mode)      */
@@ -187,9 +187,9 @@ int vqa_graphconv_pool_bwd_data(const float* dpooled, const long long* argmax, c
 /* Edge part of the backward on the tensor cores: P[i,m,k] = <dO[i,chunk k], Y[idx[i,m],chunk k]> per image as
  * dO_k Y_k^T, then dalpha (B,K,nb) (NULL when alpha is NULL) and the per-image partial sums of the Gaussian-parameter
  * gradients dgauss_partial (B, 4*nk) (reduce over B with vqa_colsum_f32).  Upstream: dO planes, or (dpooled, argmax)
- * with dO_hi == NULL for the pooled layer.  p_scratch: (B,K,nb,nk) floats, needed only when K*nb*nk*4 B > 48 KB
- * (the selected products then round-trip through L2 instead of shared memory).  Requires (out_dim / nk) % 64 == 0.
- * SURVEY.md 9.2. */
+ * with dO_hi == NULL for the pooled layer.  p_scratch: (B, nk, K*nb) floats, required: the selected products, written by the
+ * streaming kernel (persistent, one CTA per SM over B*nk units) and read by the edge-finish kernel of the same call.
+ * Requires (out_dim / nk) % 64 == 0.  SURVEY.md 9.2. */
 int vqa_graphconv_mma_bwd_edges(const void* dO_hi, const void* dO_lo, long long lddo, const float* dpooled,
                                 const long long* argmax, const void* Y_hi, const void* Y_lo, long long ldy, const int* idx,
                                 const float* alpha, const float* boxes, long long ldbox, const float* gauss, float* dalpha,

@@ -1,12 +1,12 @@
-"""Phase timeline of the backward edge kernel (`edge_p_kernel`, csrc/graphconv_mma.cu), per CTA, from %globaltimer stamps.
+"""Where the backward edge kernel (`edge_p_kernel`, csrc/graphconv_mma.cu) waits: cycles each role of a CTA spends on each barrier.
 
-Needs the tracing build of the library (never the shipped one: the stamps are compiled out of it):
+Needs the tracing build of the library (never the shipped one: the counters are compiled out of it):
 
     make -C vqa-project_b200/csrc EXTRA=-DVQA_EDGE_TRACE BUILD=build_trace OUT=../vqa_b200/libvqa_trace.so
     python tools/edge_trace.py [--shape vqa2|med|k100] > gpurun_out/edge_trace.txt
 
-Prints, for the plain (layer 1) and pooled (layer 2) variants: the kernel's span, CTAs per SM, and the median / p90 length of each
-phase of a CTA (set-up, the wait for each Gaussian kernel's accumulator, the edge finish loop, the reduction)."""
+The role that (almost) never waits is the bottleneck: the TMA producer waits for free stages, the MMA issuer for filled stages and
+for a free accumulator, the TMEM readers for a finished accumulator, the A-tile builders (pooled upstream) for free stages."""
 import argparse
 import ctypes as C
 import os
@@ -50,23 +50,14 @@ def trace(name, fn):
     flush.zero_()
     torch.cuda.synchronize()
     fn()
-    out = np.zeros((B, 16), dtype=np.uint64)
-    assert lib.vqa_debug_edge_trace(out.ctypes.data, B) == 0
-    t = out[:, :13].astype(np.int64)
-    t0 = t[:, 0].min()
-    span = (t[:, 12].max() - t0) / 1e3
-    sm = out[:, 15].astype(np.int64)
-    print(f"== {name} ({args.shape}: B={B} K={K} nb={nb} nk={nk}): span {span:.1f} us, {len(set(sm.tolist()))} SMs, CTA life median "
-          f"{np.median(t[:, 12] - t[:, 0]) / 1e3:.1f} us")
-    names = ["set-up"] + [f"acc k={k} ready" for k in range(8)] + ["main loop drained", "finish edge loop", "reduction + exit"]
-    prev = t[:, 0]
-    for i, nm in enumerate(names, start=1):
-        d = (t[:, i] - prev) / 1e3
-        print(f"   {nm:22s} median {np.median(d):7.2f} us   p90 {np.percentile(d, 90):7.2f}   max {d.max():7.2f}")
-        prev = t[:, i]
-    # concurrency: how many CTAs were alive at the median start time of the second wave
-    starts = np.sort(t[:, 0] - t0) / 1e3
-    print(f"   CTA start times: first {starts[0]:.1f}, #296 {starts[min(295, B - 1)]:.1f}, #297 {starts[min(296, B - 1)]:.1f}, last {starts[-1]:.1f} us")
+    out = np.zeros((148, 8), dtype=np.int64)
+    assert lib.vqa_debug_edge_trace(out.ctypes.data, 148) == 0
+    med = np.median(out, axis=0)
+    print(f"== {name} ({args.shape}: B={B} K={K} nb={nb} nk={nk}): CTA life {med[0]:.0f} cycles for {med[7]:.0f} units "
+          f"= {med[0] / max(med[7], 1):.0f} cycles per unit")
+    for slot, nm in ((1, "TMA producer waits for a free stage"), (2, "MMA issuer waits for a filled stage"), (3, "MMA issuer waits for a free accumulator"),
+                     (4, "TMEM readers wait for a finished accumulator"), (5, "A-tile builders wait for a free stage")):
+        print(f"   {nm:46s} {med[slot]:9.0f} cycles = {100 * med[slot] / max(med[0], 1):5.1f} % of the CTA's life")
 
 
 trace("edge_p<plain> layer 1", lambda: kn.graphconv_bwd_edges_s(Y1, idx, alpha, img, gauss, B, K, dOs=dO1))

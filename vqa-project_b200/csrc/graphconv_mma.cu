@@ -25,7 +25,7 @@
 // agg_persistent_kernel (the streaming aggregate, forward / pooled forward / transposed backward: one warp-specialised CTA
 // per SM), agg_kernel (the same per (image, slab) CTA, used when no precomputed edge coefficients are passed or the shapes do
 // not fit the persistent kernel's shared-memory plan), pool_bwd_data_kernel (backward data path of the max-pooled layer),
-// edge_p_kernel (edge products + edge finish of the backward).
+// edge_p_kernel (edge products of the backward, persistent) and edge_finish_kernel (what depends on them).
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -852,42 +852,63 @@ agg_persistent_kernel(const __grid_constant__ Maps tm, const Agg2Params p) {
 //
 // Dense per (image, kernel): Pd = dO_k Y_k^T  (K x K, contraction over the D columns of chunk k) on the tensor cores:
 //   A = dO tile [i, c] and B = Y tile [j, c], both K-major straight from TMA (rows past K of either tile only produce
-//   rows / columns of Pd that are never read).  The selected entries Pd[i, idx[i,m]] are gathered into shared memory
-//   for all nk kernels, then the same CTA finishes the edges: dalpha[i,m] = sum_k w_k P_k and the per-image partial
-//   sums of the four Gaussian-parameter gradients.  dO and Y are read exactly once.
+//   rows / columns of Pd that are never read).  The selected entries Pd[i, idx[i,m]] go to a (B, nk, K*nb) scratch
+//   (L2-resident: 9 MB at the VQA2 shapes), and edge_finish_kernel turns them into dalpha[i,m] = sum_k w_k P_k and the
+//   per-image partial sums of the four Gaussian-parameter gradients.  dO and Y are read exactly once.
 // POOLED upstream (layer 2): dO[i, c] = (argmax[c] == i) ? dpooled[c] : 0 is synthesised straight into the A tile.
+//
+// The tensor core takes ~100 cycles for one M=128, K=16 instruction whatever N is (measured with the tracing build below: with one
+// image per instruction the MMA issuer was busy 78 % of the kernel and everything else waited for it), so G = floor(128 / K)
+// consecutive images share an instruction: their dO rows are stacked in the A tile and their Y rows in the B tile -- one TMA box
+// each, the rows of consecutive images are contiguous -- and only the G diagonal K x K blocks of the product are read back.
+//
+// One persistent warp-specialised CTA per SM walks a contiguous range of (image group, kernel) units with one TMA stream across
+// unit and group boundaries:
+//   warp 0    TMA producer (item = 64 columns of a unit: the dO and Y boxes of K rows, hi and lo planes)
+//   warp 1    MMA issuer (accumulators double-buffered in TMEM by unit parity)
+//   warps 2-5 read Pd out of TMEM and pick the selected entries
+//   warps 6-9 (pooled upstream only) build the A tiles
+// (Round 2 trace, profiles/r02_edge_trace_before_*.txt: the previous one-CTA-per-image kernel ran in two lock-step waves,
+// all CTAs streaming and then all CTAs finishing their edges with HBM idle, 97 us against 46 us of HBM time.)
 struct PMaps { CUtensorMap d_hi, d_lo, y_hi, y_lo; };
 struct PParams {
   const int* idx; const float* alpha; const float* boxes; long long ldbox; const float* gauss;
   const float* dpooled; const long long* argmax;           // pooled upstream (else NULL)
   float* dalpha; float* partial;                           // (B,K,nb) or NULL ; (B, 4*nk)
-  float* pacc_global;                                      // optional (B,K,nb,nk) scratch for shapes whose products exceed shared memory
-  int B, K, NP, nb, nk, out_dim, D, nblk, nstage, with_lo;
-  int off_stage, a_plane, b_plane, stage_bytes, off_pd, off_pacc, off_red, off_misc, off_bars, tmem_cols;
+  float* pacc;                                             // (B, nk, K*nb) selected products
+  int B, K, G, GK, NP, nb, nk, out_dim, D, nblk, nstage, with_lo;   // G images per unit, GK = G * K stacked rows, NP = round16(GK)
+  int off_stage, a_plane, b_plane, stage_bytes, off_pd, off_idx, off_prev, off_ring, off_bars, tmem_cols;
 };
-
+constexpr int EP_THREADS = 320;
+constexpr int EP_MAX_G = 4;
+constexpr int EP_PF = 6;                // pooled A-tile builders: items of look-ahead for argmax / dpooled
 #ifdef VQA_EDGE_TRACE
-// Development build only (make EXTRA=-DVQA_EDGE_TRACE, tools/edge_trace.py): %globaltimer stamps of the phases of each CTA.
-__device__ unsigned long long g_edge_trace[16 * 4096];
-#define EDGE_STAMP(T, I) do { if (tid == (T) && b < 4096) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_edge_trace[b * 16 + (I)] = t_; } } while (0)
+// Tracing build only (make EXTRA=-DVQA_EDGE_TRACE BUILD=build_trace OUT=../vqa_b200/libvqa_trace.so; tools/edge_trace.py): cycles each
+// role of a CTA spent waiting on each of its barriers -- the role that never waits is the bottleneck.
+__device__ long long g_edge_trace[8 * 256];
+#define EDGE_T0() const long long t0_ = clock64()
+#define EDGE_WAIT(SLOT, STMT) do { const long long w0_ = clock64(); STMT; tr_[SLOT] += clock64() - w0_; } while (0)
+#define EDGE_DECL() long long tr_[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define EDGE_FLUSH(SLOT, COND) do { if ((COND) && blockIdx.x < 256) g_edge_trace[blockIdx.x * 8 + (SLOT)] = tr_[SLOT]; } while (0)
 #else
-#define EDGE_STAMP(T, I) do { } while (0)
+#define EDGE_T0() do { } while (0)
+#define EDGE_WAIT(SLOT, STMT) STMT
+#define EDGE_DECL() do { } while (0)
+#define EDGE_FLUSH(SLOT, COND) do { } while (0)
 #endif
+constexpr int EF_THREADS = 576;          // edge_finish_kernel: at most this many threads (one per edge) per image
 
 template <bool POOLED>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(EP_THREADS, 1)
 edge_p_kernel(const __grid_constant__ PMaps tm, const PParams p) {
   extern __shared__ uint8_t gsm_raw[];
   uint8_t* sm = gsm_raw + ((1024u - (smem_u32(gsm_raw) & 1023u)) & 1023u);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x, K = p.K, NP = p.NP, nb = p.nb, nk = p.nk, S = p.nstage;
+  const int K = p.K, G = p.G, GK = p.GK, NP = p.NP, nb = p.nb, nk = p.nk, S = p.nstage;
   const int planes = p.with_lo ? 2 : 1;
-  const int nblk = p.nblk;                                 // 64-column blocks per kernel chunk
-  const int total = nk * nblk;                             // pipeline items
-  EDGE_STAMP(0, 0);
-#ifdef VQA_EDGE_TRACE
-  if (tid == 0 && b < 4096) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); g_edge_trace[b * 16 + 15] = sm_; }
-#endif
+  const int nblk = p.nblk;                                 // 64-column blocks per kernel chunk = pipeline items per unit
+  const long long units = (long long)((p.B + G - 1) / G) * nk;
+  const int u0 = (int)(units * blockIdx.x / gridDim.x), nu = (int)(units * (blockIdx.x + 1) / gridDim.x) - u0;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + p.off_bars);
   uint64_t* full = bars;
@@ -895,11 +916,8 @@ edge_p_kernel(const __grid_constant__ PMaps tm, const PParams p) {
   uint64_t* tfull = bars + 2 * S;
   uint64_t* tempty = bars + 2 * S + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
-  float* Pd = reinterpret_cast<float*>(sm + p.off_pd);     // [K][NP+1]
-  float* Pacc = p.off_pacc >= 0 ? reinterpret_cast<float*>(sm + p.off_pacc) : p.pacc_global + (long long)b * K * nb * nk;   // [K*nb][nk]
-  uint8_t* idx8 = sm + p.off_misc;
-  float* cen = reinterpret_cast<float*>(sm + p.off_misc + ((K * nb + 15) & ~15));
-  float* gs = cen + 2 * ((K + 1) & ~1);                    // mean_rho | cr | mean_theta | ct | sigma_rho | sigma_theta | 4 derived
+  float* Pd = reinterpret_cast<float*>(sm + p.off_pd);     // [GK][K+1]: the diagonal blocks
+  uint8_t* idx8 = sm + p.off_idx;
 
   if (warp == 1) {
     if (lane == 0) {
@@ -917,204 +935,309 @@ edge_p_kernel(const __grid_constant__ PMaps tm, const PParams p) {
     if (p.with_lo) tma_prefetch_desc(&tm.y_lo);
     if (!POOLED) { tma_prefetch_desc(&tm.d_hi); if (p.with_lo) tma_prefetch_desc(&tm.d_lo); }
   }
-  for (int v = tid; v < K * nb; v += THREADS) idx8[v] = (uint8_t)p.idx[(long long)b * K * nb + v];
-  for (int i = tid; i < K; i += THREADS) {
-    const float* bx = p.boxes + ((long long)b * K + i) * p.ldbox;
-    const float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3];
-    cen[2 * i] = x1 + 0.5f * (x2 - x1);
-    cen[2 * i + 1] = y1 + 0.5f * (y2 - y1);
-  }
-  for (int k = tid; k < nk; k += THREADS) {
-    const float sr = p.gauss[nk + k], st = p.gauss[3 * nk + k];
-    gs[k] = p.gauss[k];
-    gs[nk + k] = -0.5f * 1.4426950408889634f / (GM_EPS_F + sr * sr);
-    gs[2 * nk + k] = p.gauss[2 * nk + k];
-    gs[3 * nk + k] = -0.5f * 1.4426950408889634f / (GM_EPS_F + st * st);
-    gs[4 * nk + k] = sr;
-    gs[5 * nk + k] = st;
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  EDGE_STAMP(0, 1);
+  EDGE_DECL();
+  EDGE_T0();
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer: item = (kernel k, 64-column block)
+    // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      const uint32_t tx = (uint32_t)(planes * K * 128) * (POOLED ? 1u : 2u);
-      for (int it = 0; it < total; ++it) {
-        const int s = it % S;
-        mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
-        mbar_arrive_expect_tx(&full[s], tx);
-        uint8_t* st = sm + p.off_stage + (size_t)s * p.stage_bytes;
-        const int c0 = it * 64;                            // items walk the columns in order: k = it / nblk
-        for (int pl = 0; pl < planes; ++pl) {
-          if (!POOLED) tma_load_2d(st + pl * p.a_plane, pl ? &tm.d_lo : &tm.d_hi, &full[s], c0, b * K);
-          tma_load_2d(st + planes * p.a_plane + pl * p.b_plane, pl ? &tm.y_lo : &tm.y_hi, &full[s], c0, b * K);
+      const uint32_t tx = (uint32_t)(planes * GK * 128) * (POOLED ? 1u : 2u);   // (rows past the last image are zero-filled and counted)
+      int it = 0;
+      for (int n = 0; n < nu; ++n) {
+        const int u = u0 + n, grp = u / nk, k = u - grp * nk, b = grp * G;
+        for (int blk = 0; blk < nblk; ++blk, ++it) {
+          const int s = it % S;
+          EDGE_WAIT(1, mbar_wait(&empty[s], ((it / S) & 1) ^ 1));
+          mbar_arrive_expect_tx(&full[s], tx);
+          uint8_t* st = sm + p.off_stage + (size_t)s * p.stage_bytes;
+          const int c0 = (k * nblk + blk) * 64;
+          for (int pl = 0; pl < planes; ++pl) {
+            if (!POOLED) tma_load_2d(st + pl * p.a_plane, pl ? &tm.d_lo : &tm.d_hi, &full[s], c0, b * K);
+            tma_load_2d(st + planes * p.a_plane + pl * p.b_plane, pl ? &tm.y_lo : &tm.y_hi, &full[s], c0, b * K);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer: Pd(k) += A_blk B_blk^T
+    // ------------------------------------------------------------ MMA issuer: Pd(unit) += A_blk B_blk^T
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    for (int it = 0; it < total; ++it) {
-      const int s = it % S, k = it / nblk, blk = it - k * nblk, acc = k & 1;
-      if (blk == 0) mbar_wait(&tempty[acc], ((k >> 1) & 1) ^ 1);
-      mbar_wait(&full[s], (it / S) & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_hi = smem_u32(sm + p.off_stage + (size_t)s * p.stage_bytes), a_lo = a_hi + p.a_plane;
-        const uint32_t b_hi = a_hi + planes * p.a_plane, b_lo = b_hi + p.b_plane;
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NP);
+    int it = 0;
+    for (int n = 0; n < nu; ++n) {
+      const int acc = n & 1;
+      for (int blk = 0; blk < nblk; ++blk, ++it) {
+        const int s = it % S;
+        if (blk == 0) EDGE_WAIT(3, mbar_wait(&tempty[acc], ((n >> 1) & 1) ^ 1));
+        EDGE_WAIT(2, mbar_wait(&full[s], (it / S) & 1));
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_hi = smem_u32(sm + p.off_stage + (size_t)s * p.stage_bytes), a_lo = a_hi + p.a_plane;
+          const uint32_t b_hi = a_hi + planes * p.a_plane, b_lo = b_hi + p.b_plane;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NP);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t dah = desc_kmajor(a_hi + ks * 32), dbh = desc_kmajor(b_hi + ks * 32);
-          const uint32_t accum = (blk > 0 || ks > 0) ? 1u : 0u;
-          if (p.with_lo) {
-            const uint64_t dal = desc_kmajor(a_lo + ks * 32), dbl = desc_kmajor(b_lo + ks * 32);
-            tc_mma<1>(d_tmem, dal, dbh, idesc, accum);
-            tc_mma<1>(d_tmem, dah, dbl, idesc, 1u);
-            tc_mma<1>(d_tmem, dah, dbh, idesc, 1u);
-          } else {
-            tc_mma<1>(d_tmem, dah, dbh, idesc, accum);
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t dah = desc_kmajor(a_hi + ks * 32), dbh = desc_kmajor(b_hi + ks * 32);
+            const uint32_t accum = (blk > 0 || ks > 0) ? 1u : 0u;
+            if (p.with_lo) {
+              const uint64_t dal = desc_kmajor(a_lo + ks * 32), dbl = desc_kmajor(b_lo + ks * 32);
+              tc_mma<1>(d_tmem, dal, dbh, idesc, accum);
+              tc_mma<1>(d_tmem, dah, dbl, idesc, 1u);
+              tc_mma<1>(d_tmem, dah, dbh, idesc, 1u);
+            } else {
+              tc_mma<1>(d_tmem, dah, dbh, idesc, accum);
+            }
           }
+          tc_commit(&empty[s]);
+          if (blk == nblk - 1) tc_commit(&tfull[acc]);
         }
-        tc_commit(&empty[s]);
-        if (blk == nblk - 1) tc_commit(&tfull[acc]);
+        __syncwarp();
       }
-      __syncwarp();
     }
-  } else {
-    // ------------------------------------------------------------ warps 2-5: (pooled: build A tiles) + gather Pd -> Pacc
-    const int q4 = warp & 3, et = tid - 64;                 // et: 0..127
-    const int row = q4 * 32 + lane;                         // TMEM lane = node i
-    for (int k = 0; k < nk; ++k) {
-      const int acc = k & 1;
-      if (POOLED) {
-        for (int blk = 0; blk < nblk; ++blk) {
-          const int it = k * nblk + blk, s = it % S;
-          mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
-          uint8_t* a_hi = sm + p.off_stage + (size_t)s * p.stage_bytes;
-          // zero rows [0, K) of the A tile(s), then drop dpooled[c] into row argmax[c]
-          const int n16 = K * 8;                            // 16-byte chunks per plane (K rows x 128 B)
-          for (int v = et; v < planes * n16; v += 128) {
-            const int pl = v / n16, w = v - pl * n16;
-            *reinterpret_cast<uint4*>(a_hi + pl * p.a_plane + w * 16) = make_uint4(0u, 0u, 0u, 0u);
-          }
-          epi_bar_sync();
-          if (et < 64) {
-            const long long o = (long long)b * p.out_dim + (long long)it * 64 + et;
-            const int n = (int)p.argmax[o];
-            const float v = p.dpooled[o];
-            const uint32_t off = coef_off(n, et, 128);      // K-major 128B-swizzled tile with 128-row pitch layout
-            const __nv_bfloat16 h = __float2bfloat16_rn(v);
-            *reinterpret_cast<__nv_bfloat16*>(a_hi + off) = h;
-            if (p.with_lo) *reinterpret_cast<__nv_bfloat16*>(a_hi + p.a_plane + off) = __float2bfloat16_rn(v - __bfloat162float(h));
-          }
-          fence_proxy_async();
-          mbar_arrive(&full[s]);
+  } else if (warp < 6) {
+    // ------------------------------------------------------------ warps 2-5: Pd out of TMEM, selected entries -> scratch
+    // Thread = stacked row (TMEM lane).  Its row of the diagonal block and its neighbour ids live in row-private shared memory,
+    // so the phases below need no barrier between them.
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;                         // image t = row / K of the group, node i = row - t K
+    const int nedge = K * nb;
+    const int t_row = row / K, i_row = row - t_row * K, c_row = t_row * K;   // this row's diagonal block: columns [c_row, c_row + K)
+    const int w_lo = ((q4 * 32) / K) * K, w_hi = min((min(q4 * 32 + 31, GK - 1) / K) * K + K, GK);   // columns this warp needs
+    float* Prow = Pd + row * (K + 1);
+    uint8_t* irow = idx8 + row * nb;
+    int cur_b = -1;
+    for (int n = 0; n < nu; ++n) {
+      const int u = u0 + n, grp = u / nk, k = u - grp * nk, b = grp * G, acc = n & 1;
+      const bool live = row < GK && b + t_row < p.B;
+      if (b != cur_b) {
+        if (live) {
+          const int* src = p.idx + ((long long)(b + t_row) * K + i_row) * nb;
+          for (int m = 0; m < nb; ++m) irow[m] = (uint8_t)src[m];
         }
+        cur_b = b;
       }
-      mbar_wait(&tfull[acc], (k >> 1) & 1);
-      if (k < 8) EDGE_STAMP(64, 2 + k);
+      EDGE_WAIT(4, mbar_wait(&tfull[acc], (n >> 1) & 1));
       tc_fence_after();
-      if (q4 * 32 < K) {                                    // warp-uniform: the .sync.aligned loads need the whole warp
-        for (int j0 = 0; j0 < K; j0 += 16) {
+      if (q4 * 32 < GK) {                                   // warp-uniform: the .sync.aligned loads need the whole warp
+        for (int j0 = w_lo & ~15; j0 < w_hi; j0 += 16) {
           uint32_t r[16];
           tc_ld_32x16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(acc * NP + j0), r);
           tc_wait_ld();
-          if (row < K) {
+          if (row < GK) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (j0 + e < K) Pd[row * (NP + 1) + j0 + e] = __uint_as_float(r[e]);
+            for (int e = 0; e < 16; ++e) {
+              const int j = j0 + e - c_row;
+              if (j >= 0 && j < K) Prow[j] = __uint_as_float(r[e]);
+            }
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
-      epi_bar_sync();
-      for (int e = et; e < K * nb; e += 128) Pacc[e * nk + k] = Pd[(e / nb) * (NP + 1) + idx8[e]];
-      epi_bar_sync();
-    }
-  }
-  __syncthreads();
-  EDGE_STAMP(0, 10);
-
-  // ------------------------------------------------------------ edge finish (all threads): dalpha and Gaussian-parameter partials
-  // per-kernel constants without divisions in the edge loop: gs[6nk..10nk) = 1/vr | sr/vr^2 | 1/vt | st/vt^2
-  for (int k = tid; k < nk; k += THREADS) {
-    const float sr = gs[4 * nk + k], st = gs[5 * nk + k];
-    const float vr = GM_EPS_F + sr * sr, vt = GM_EPS_F + st * st;
-    gs[6 * nk + k] = 1.f / vr; gs[7 * nk + k] = sr / (vr * vr); gs[8 * nk + k] = 1.f / vt; gs[9 * nk + k] = st / (vt * vt);
-  }
-  __syncthreads();
-  float* red = reinterpret_cast<float*>(sm + p.off_red);   // [THREADS][33]
-  const int nedge = K * nb;
-  for (int kc = 0; kc < nk; kc += 8) {                      // kernels in chunks of 8: 32 per-thread accumulators
-    const int kn_ = min(8, nk - kc);
-    float a_mr[8], a_sr[8], a_mt[8], a_st[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) a_mr[u] = a_sr[u] = a_mt[u] = a_st[u] = 0.f;
-    for (int e = tid; e < nedge; e += THREADS) {
-      const int i = e / nb, j = idx8[e];
-      const float dx = cen[2 * i] - cen[2 * j], dy = cen[2 * i + 1] - cen[2 * j + 1];
-      const float rho = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-      const float theta = atan2f(dx, dy);
-      const float* Pe = Pacc + e * nk;
-      float Ssum = 0.f, da = 0.f;
-      for (int k = 0; k < nk; ++k) {
-        const float g = gauss_val(rho, theta, gs[k], gs[nk + k], gs[2 * nk + k], gs[3 * nk + k]);
-        Ssum += g;
-        da = fmaf(g, Pe[k], da);
-      }
-      const float invS = __fdiv_rn(1.f, Ssum);               // Ssum == 0 -> inf -> NaN below, as the reference
-      da *= invS;                                          // dalpha = sum_k w_k P_k
-      const float a = p.alpha ? p.alpha[(long long)b * nedge + e] : 1.f;
-      if (kc == 0 && p.dalpha) p.dalpha[(long long)b * nedge + e] = da;
-      const float T = a * da;                              // sum_k dw_k w_k
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (u < kn_) {
-          const int k = kc + u;
-          const float mr = gs[k], mt = gs[2 * nk + k];
-          const float g = gauss_val(rho, theta, mr, gs[nk + k], mt, gs[3 * nk + k]);
-          const float gam = g * (a * Pe[k] - T) * invS;    // g_k * dL/dg_k ; masked (NaN->0) kernels contribute 0
-          const float dr = rho - mr;
-          const float df = theta - mt;
-          const float phi = fabsf(df), two = GM_TWO_PI_F - phi, psi = fabsf(two);
-          const float sgn = df > 0.f ? 1.f : (df < 0.f ? -1.f : 0.f);
-          const float ddel = phi < psi ? -sgn : (two > 0.f ? 1.f : (two < 0.f ? -1.f : 0.f)) * sgn;   // d(delta)/d(mean_theta)
-          const float del = fminf(phi, psi);
-          float c_mr = gam * dr * gs[6 * nk + k];
-          float c_sr = gam * dr * dr * gs[7 * nk + k];
-          float c_mt = -gam * del * gs[8 * nk + k] * ddel;
-          float c_st = gam * del * del * gs[9 * nk + k];
-          if (gam != gam) { c_mr = c_sr = c_mt = c_st = gam; }   // keep NaN visible (S == 0 rows), as autograd would
-          a_mr[u] += c_mr; a_sr[u] += c_sr; a_mt[u] += c_mt; a_st[u] += c_st;
+      if (live) {
+        float* out = p.pacc + ((long long)(b + t_row) * nk + k) * nedge + i_row * nb;
+        if ((nb & 3) == 0) {
+          for (int m = 0; m < nb; m += 4) {
+            const uchar4 j4 = *reinterpret_cast<const uchar4*>(irow + m);
+            *reinterpret_cast<float4*>(out + m) = make_float4(Prow[j4.x], Prow[j4.y], Prow[j4.z], Prow[j4.w]);
+          }
+        } else {
+          for (int m = 0; m < nb; ++m) out[m] = Prow[irow[m]];
         }
       }
     }
-    EDGE_STAMP(0, 11);
-    // transposed reduction through shared memory: thread t writes its 32 partials, then 32 threads sum a column each
+  } else if (POOLED) {
+    // ------------------------------------------------------------ warps 6-9: A tile = dpooled[c] at row argmax[c], zero elsewhere
+    // Entry w = (image t = w / 64 of the group, column c = w % 64) always belongs to thread w % 128 and lands in column c of the
+    // rows of image t: entries never share a byte, so each thread keeps its own entries of a stage up to date -- clear where the
+    // entry was the last time this stage was used, write where it is now -- and the tile is zeroed only once.
+    const int bt = tid - 192;                               // 0..127
+    uint32_t* prev = reinterpret_cast<uint32_t*>(sm + p.off_prev);   // [S][256]: offset of each entry in its stage, ~0 = none
+    for (int s = 0; s < S; ++s) {
+      uint8_t* a_hi = sm + p.off_stage + (size_t)s * p.stage_bytes;
+      for (int w = bt; w < planes * (p.a_plane >> 4); w += 128) *reinterpret_cast<uint4*>(a_hi + w * 16) = make_uint4(0u, 0u, 0u, 0u);
+      prev[s * 256 + bt] = ~0u; prev[s * 256 + 128 + bt] = ~0u;
+    }
+    // argmax / dpooled of an item come from HBM (~1 us under load): each thread copies its two entries EP_PF - 1 items ahead into
+    // a private slot of a small ring with cp.async, so their latency never sits on the chain stage-free -> tile-ready.
+    long long* aring = reinterpret_cast<long long*>(sm + p.off_ring);           // [EP_PF][256]
+    float* vring = reinterpret_cast<float*>(sm + p.off_ring + EP_PF * 256 * 8); // [EP_PF][256]
+    const int nit = nu * nblk;
+    auto issue = [&](int itn) {
+      if (itn < nit) {
+        const int n = itn / nblk, blk = itn - n * nblk;
+        const int u = u0 + n, grp = u / nk, k = u - grp * nk, b = grp * G;
+        const int gn = min(G, p.B - b), slot = (itn % EP_PF) * 256;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      red[tid * 33 + u] = a_mr[u]; red[tid * 33 + 8 + u] = a_sr[u]; red[tid * 33 + 16 + u] = a_mt[u]; red[tid * 33 + 24 + u] = a_st[u];
+        for (int h = 0; h < 2; ++h) {
+          const int w = bt + h * 128, t = w >> 6;
+          if (t < gn) {
+            const long long o = (long long)(b + t) * p.out_dim + (long long)(k * nblk + blk) * 64 + (w & 63);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(aring + slot + w)), "l"(p.argmax + o) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(vring + slot + w)), "l"(p.dpooled + o) : "memory");
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");   // (an empty group keeps the count uniform)
+    };
+    for (int i = 0; i < EP_PF - 1; ++i) issue(i);
+    for (int it = 0; it < nit; ++it) {
+      issue(it + EP_PF - 1);
+      asm volatile("cp.async.wait_group %0;" ::"n"(EP_PF - 1) : "memory");
+      int arg[2]; float v[2];
+      {
+        const int n = it / nblk, grp = (u0 + n) / nk, b = grp * G, gn = min(G, p.B - b), slot = (it % EP_PF) * 256;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int w = bt + h * 128, t = w >> 6;
+          arg[h] = -1; v[h] = 0.f;
+          if (t < gn) { arg[h] = t * K + (int)aring[slot + w]; v[h] = vring[slot + w]; }
+        }
+      }
+      const int s = it % S;
+      EDGE_WAIT(5, mbar_wait(&empty[s], ((it / S) & 1) ^ 1));
+      uint8_t* a_hi = sm + p.off_stage + (size_t)s * p.stage_bytes;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t* slot = prev + s * 256 + h * 128 + bt;
+        const uint32_t po = *slot;
+        if (po != ~0u) {
+          *reinterpret_cast<uint16_t*>(a_hi + po) = 0;
+          if (p.with_lo) *reinterpret_cast<uint16_t*>(a_hi + p.a_plane + po) = 0;
+        }
+        uint32_t no = ~0u;
+        if (arg[h] >= 0) {
+          no = coef_off(arg[h], bt & 63, 128);              // K-major 128B-swizzled tile with 128-row pitch layout
+          const __nv_bfloat16 hi = __float2bfloat16_rn(v[h]);
+          *reinterpret_cast<__nv_bfloat16*>(a_hi + no) = hi;
+          if (p.with_lo) *reinterpret_cast<__nv_bfloat16*>(a_hi + p.a_plane + no) = __float2bfloat16_rn(v[h] - __bfloat162float(hi));
+        }
+        *slot = no;
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[s]);
+    }
+  }
+  EDGE_FLUSH(1, tid == 0); EDGE_FLUSH(2, tid == 32); EDGE_FLUSH(3, tid == 32); EDGE_FLUSH(4, tid == 64); EDGE_FLUSH(5, tid == 192);
+  tc_fence_before();
+  __syncthreads();
+#ifdef VQA_EDGE_TRACE
+  if (tid == 0 && blockIdx.x < 256) { g_edge_trace[blockIdx.x * 8] = clock64() - t0_; g_edge_trace[blockIdx.x * 8 + 7] = nu; }
+#endif
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
+  }
+}
+
+// Edge finish, one CTA per image, one thread per edge: dalpha[i,m] = sum_k w_k P_k and the per-image partial sums of the
+// gradients of the four Gaussian parameters (mean_rho, precision_rho, mean_theta, precision_theta; layers.py:100-125
+// differentiated).  With g_k the Gaussian value, S = sum_k g_k, w_k = g_k / S and gam_k = w_k (alpha P_k - alpha dalpha):
+//   d/d mean_rho_k   = sum_e gam_k (rho - mr_k) / vr_k            d/d sigma_rho_k   = sum_e gam_k (rho - mr_k)^2 sr_k / vr_k^2
+//   d/d mean_theta_k = sum_e gam_k x_k / vt_k                     d/d sigma_theta_k = sum_e gam_k del_k^2 st_k / vt_k^2
+// where del = min(|df|, |2 pi - |df||), df = theta - mt_k, and x = -del * d del / d mt = df on the first branch of the min and
+// -(2 pi - |df|) sign(df) on the second; the per-kernel factors are applied once per image, after the sums.  A NaN gam (S == 0,
+// as the reference) poisons its four sums like autograd would.  The sums run in a fixed order (each thread's 32 terms go to its
+// row of a shared-memory table; a warp sums 32 rows of a column, then the warps in turn): same bits every run.
+__global__ void __launch_bounds__(EF_THREADS, 2)
+edge_finish_kernel(const PParams p) {
+  extern __shared__ float red[];                           // [blockDim][33]
+  __shared__ float cen[2 * 128];
+  __shared__ float gs[8 * MAX_NK];                         // mean_rho | cr | mean_theta | ct | 1/vr | sr/vr^2 | 1/vt | st/vt^2
+  __shared__ float part[EF_THREADS / 32][32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+  const int b = blockIdx.x, K = p.K, nb = p.nb, nk = p.nk;
+  for (int i = tid; i < K; i += blockDim.x) {
+    const float* bx = p.boxes + ((long long)b * K + i) * p.ldbox;
+    const float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3];
+    cen[2 * i] = x1 + 0.5f * (x2 - x1);
+    cen[2 * i + 1] = y1 + 0.5f * (y2 - y1);
+  }
+  for (int k = tid; k < nk; k += blockDim.x) {
+    const float sr = p.gauss[nk + k], st = p.gauss[3 * nk + k];
+    const float vr = GM_EPS_F + sr * sr, vt = GM_EPS_F + st * st;
+    gs[k] = p.gauss[k];
+    gs[nk + k] = -0.5f * 1.4426950408889634f / vr;
+    gs[2 * nk + k] = p.gauss[2 * nk + k];
+    gs[3 * nk + k] = -0.5f * 1.4426950408889634f / vt;
+    gs[4 * nk + k] = 1.f / vr; gs[5 * nk + k] = sr / (vr * vr); gs[6 * nk + k] = 1.f / vt; gs[7 * nk + k] = st / (vt * vt);
+  }
+  __syncthreads();
+  const int nedge = K * nb;
+  const float* Pb = p.pacc + (long long)b * nk * nedge;    // [nk][nedge]
+  const int* idxb = p.idx + (long long)b * nedge;
+  const float* alb = p.alpha ? p.alpha + (long long)b * nedge : nullptr;
+  float* dab = p.dalpha ? p.dalpha + (long long)b * nedge : nullptr;
+  for (int kc = 0; kc < nk; kc += 8) {                      // kernels in chunks of 8: 32 sums per thread
+    const int kn_ = min(8, nk - kc);
+    float* acc = red + tid * 33;                            // [which][u]: mean_rho | sigma_rho | mean_theta | sigma_theta
+    bool first = true;
+    for (int e = tid; e < nedge; e += blockDim.x) {
+      const int i = e / nb, j = idxb[e];
+      const float a = alb ? alb[e] : 1.f;
+      float P[8];                                           // this chunk's kernels
+#pragma unroll
+      for (int u = 0; u < 8; ++u) P[u] = u < kn_ ? Pb[(kc + u) * nedge + e] : 0.f;
+      const float dx = cen[2 * i] - cen[2 * j], dy = cen[2 * i + 1] - cen[2 * j + 1];
+      const float rho = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+      const float theta = atan2f(dx, dy);
+      float g[8];
+      float Ssum = 0.f, da = 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {                         // (layers.py:109-117; one ex2 for both exponentials, NaN -> 0 as layers.py:120)
+        const int k = kc + u;
+        g[u] = 0.f;
+        if (u < kn_) {
+          g[u] = gauss_val(rho, theta, gs[k], gs[nk + k], gs[2 * nk + k], gs[3 * nk + k]);
+          Ssum += g[u];
+          da = fmaf(g[u], P[u], da);
+        }
+      }
+      if (nk > 8) {                                         // more than one chunk: S and dalpha need every kernel
+        Ssum = 0.f; da = 0.f;
+        for (int k = 0; k < nk; ++k) {
+          const float gk = gauss_val(rho, theta, gs[k], gs[nk + k], gs[2 * nk + k], gs[3 * nk + k]);
+          Ssum += gk;
+          da = fmaf(gk, Pb[k * nedge + e], da);
+        }
+      }
+      const float invS = __fdiv_rn(1.f, Ssum);               // Ssum == 0 -> inf -> NaN below, as the reference
+      da *= invS;                                          // dalpha = sum_k w_k P_k
+      if (kc == 0 && dab) dab[e] = da;
+      const float T = a * da;                              // sum_k dw_k w_k
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = min(kc + u, nk - 1);
+        const float gam = g[u] * invS * fmaf(a, P[u], -T);   // g_k * dL/dg_k ; masked (NaN->0) kernels contribute 0
+        const float d = rho - gs[k], df = theta - gs[2 * nk + k];          // (cheaper to recompute than to keep: registers)
+        const float phi = fabsf(df), two = GM_TWO_PI_F - phi, psi = fabsf(two), del = fminf(phi, psi);
+        const float x = phi < psi ? df : (df > 0.f ? -two : (df < 0.f ? two : 0.f));
+        const float c0 = gam * d, c1 = c0 * d, c2 = gam * x, c3 = gam * del * del;
+        if (first) { acc[u] = c0; acc[8 + u] = c1; acc[16 + u] = c2; acc[24 + u] = c3; }
+        else { acc[u] += c0; acc[8 + u] += c1; acc[16 + u] += c2; acc[24 + u] += c3; }
+      }
+      first = false;
+    }
+    if (first) {
+#pragma unroll
+      for (int u = 0; u < 32; ++u) acc[u] = 0.f;
+    }
+    __syncthreads();
+    {
+      float s_ = 0.f;
+#pragma unroll 8
+      for (int t = 0; t < 32; ++t) s_ += red[(warp * 32 + t) * 33 + lane];
+      part[warp][lane] = s_;
     }
     __syncthreads();
     if (tid < 32) {
       float s_ = 0.f;
-      for (int t = 0; t < THREADS; ++t) s_ += red[t * 33 + tid];
-      const int which = tid >> 3, u = tid & 7;              // 0: mean_rho, 1: precision_rho, 2: mean_theta, 3: precision_theta
-      if (u < kn_) p.partial[(long long)b * 4 * nk + which * nk + kc + u] = s_;
+      for (int w = 0; w < nwarp; ++w) s_ += part[w][tid];
+      const int which = tid >> 3, u = tid & 7;              // 0: mean_rho, 1: sigma_rho, 2: mean_theta, 3: sigma_theta
+      if (u < kn_) p.partial[(long long)b * 4 * nk + which * nk + kc + u] = s_ * gs[(4 + which) * nk + kc + u];
     }
     __syncthreads();
-  }
-  tc_fence_before();
-  __syncthreads();
-  EDGE_STAMP(0, 12);
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols));
   }
 }
 
@@ -1277,55 +1400,61 @@ static int edge_p_launch(const void* d_hi, const void* d_lo, long long ldd, cons
   p.D = p.out_dim / p.nk;
   if (p.D % 64 != 0) return vqa_fail(VQA_ERR_UNSUPPORTED, "%s: out_dim / n_kernels (%d) must be a multiple of 64 for the tensor-core edge products", who, p.D);
   VQA_CHECK_ARG(y_hi && aligned16(y_hi) && (!y_lo || aligned16(y_lo)) && (ldy & 7) == 0 && ldy >= p.out_dim, "%s: Y planes need 16-byte aligned rows", who);
+  VQA_CHECK_ARG(p.pacc, "%s: pass a (B, n_kernels, K*nb) float scratch buffer for the selected edge products", who);
   p.with_lo = y_lo != nullptr;
   if (!POOLED) VQA_CHECK_ARG(d_hi && aligned16(d_hi) && (!p.with_lo || (d_lo && aligned16(d_lo))) && (ldd & 7) == 0 && ldd >= p.out_dim, "%s: dO planes need 16-byte aligned rows and the same planes as Y", who);
   const int planes = p.with_lo ? 2 : 1;
-  p.NP = (K + 15) & ~15;
+  p.G = 128 / K < EP_MAX_G ? 128 / K : EP_MAX_G;           // images stacked in one MMA (M = 128 rows)
+  if (p.G > B) p.G = B;
+  p.GK = p.G * K;
+  p.NP = (p.GK + 15) & ~15;
   p.nblk = p.D / 64;
-  // The MMA has M = 128 but only the first K rows of the A tile matter (rows >= K only produce rows of Pd nobody reads), so
-  // an A plane is allotted round8(K) rows; the tensor core's reads of the other rows run on into the following planes /
+  // The MMA has M = 128 but only the first GK rows of the A tile matter (rows >= GK only produce rows of Pd nobody reads), so
+  // an A plane is allotted round8(GK) rows; the tensor core's reads of the other rows run on into the following planes /
   // stages (always inside the ring + slack below), whose contents are irrelevant for those junk rows.
-  p.a_plane = ((K + 7) & ~7) * 128;
+  p.a_plane = ((p.GK + 7) & ~7) * 128;
   p.b_plane = p.NP * 128;
   p.stage_bytes = planes * (p.a_plane + p.b_plane);
   int slack = (planes - 1) * p.a_plane + 128 * 128 - p.stage_bytes;      // junk-row reads of the last stage's last A plane
   if (slack < 0) slack = 0;
-  const int pd = K * (p.NP + 1) * 4;
-  int pacc = K * p.nb * p.nk * 4;                            // selected products of all kernels: shared memory when it fits,
-  if (pacc > 48 * 1024) pacc = 0;                            // else the caller's global scratch (L2-resident round trip)
-  VQA_CHECK_ARG(pacc > 0 || p.pacc_global, "%s: K*nb*nk = %d products do not fit in shared memory: pass a (B,K,nb,nk) scratch buffer", who, K * p.nb * p.nk);
-  const int red = THREADS * 33 * 4;                          // edge-finish reduction scratch: aliases the (by then idle) stage ring
-  const int misc = ((K * p.nb + 15) & ~15) + 2 * ((K + 1) & ~1) * 4 + 10 * p.nk * 4 + 64;
-  const int other = pd + pacc + misc + slack + 256;
-  int S = (226 * 1024 / 2 - 2048 - other) / p.stage_bytes;  // two CTAs per SM: one finishes its edges while the other streams tiles
-  if (S < 2) S = (226 * 1024 - 2048 - other) / p.stage_bytes;
+  const int pd = p.GK * (K + 1) * 4;
+  const int idxb = (p.GK * p.nb + 15) & ~15;
+  const int ring = POOLED ? EP_PF * 256 * 12 : 0;
+  const int other = pd + idxb + ring + slack + 512;
+  const int per_stage = p.stage_bytes + (POOLED ? 1024 : 0); // + where the pooled A tile's entries are
+  int S = (227 * 1024 - 2048 - other) / per_stage;           // one CTA per SM
   if (S < 1) return vqa_fail(VQA_ERR_UNSUPPORTED, "%s: no shared-memory plan for K=%d nb=%d nk=%d", who, K, p.nb, p.nk);
-  if (S > 6) S = 6;
+  if (S > 8) S = 8;
   p.nstage = S;
-  int ring = S * p.stage_bytes + slack;
-  if (ring < red) ring = red;
   int off = 0;
-  p.off_stage = off; off += (ring + 15) & ~15;
+  p.off_stage = off; off += (S * p.stage_bytes + slack + 15) & ~15;
   p.off_pd = off; off += (pd + 15) & ~15;
-  p.off_pacc = pacc ? off : -1; off += (pacc + 15) & ~15;
-  p.off_red = p.off_stage;
-  p.off_misc = off; off += misc; off = (off + 15) & ~15;
+  p.off_idx = off; off += idxb;
+  p.off_prev = off; off += POOLED ? S * 1024 : 0;
+  p.off_ring = off; off += ring;
   p.off_bars = off; off += (2 * S + 5) * 8;
   const size_t smem = (size_t)off + 1024;
   int tc = 2 * p.NP; p.tmem_cols = 32; while (p.tmem_cols < tc) p.tmem_cols <<= 1;
   PMaps tm;
   memset(&tm, 0, sizeof(tm));
   const long long rows = (long long)B * K;
-  int rc = make_plane_map(&tm.y_hi, y_hi, ldy, rows, p.out_dim, 64, K, true);
-  if (!rc && p.with_lo) rc = make_plane_map(&tm.y_lo, y_lo, ldy, rows, p.out_dim, 64, K, true);
+  int rc = make_plane_map(&tm.y_hi, y_hi, ldy, rows, p.out_dim, 64, p.GK, true);
+  if (!rc && p.with_lo) rc = make_plane_map(&tm.y_lo, y_lo, ldy, rows, p.out_dim, 64, p.GK, true);
   if (!POOLED) {
-    if (!rc) rc = make_plane_map(&tm.d_hi, d_hi, ldd, rows, p.out_dim, 64, K, true);
-    if (!rc && p.with_lo) rc = make_plane_map(&tm.d_lo, d_lo, ldd, rows, p.out_dim, 64, K, true);
+    if (!rc) rc = make_plane_map(&tm.d_hi, d_hi, ldd, rows, p.out_dim, 64, p.GK, true);
+    if (!rc && p.with_lo) rc = make_plane_map(&tm.d_lo, d_lo, ldd, rows, p.out_dim, 64, p.GK, true);
   }
   if (rc) return rc;
+  const long long units = (long long)((B + p.G - 1) / p.G) * p.nk;
+  const int grid = (int)(units < g_vqa_sm_budget ? units : g_vqa_sm_budget);
   VQA_CUDA(cudaFuncSetAttribute(edge_p_kernel<POOLED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  edge_p_kernel<POOLED><<<B, THREADS, smem, stream>>>(tm, p);
+  edge_p_kernel<POOLED><<<grid, POOLED ? EP_THREADS : 192, smem, stream>>>(tm, p);     // warps 6-9 only exist to build pooled A tiles
   VQA_LAUNCH_CHECK("graphconv edge_p_kernel");
+  const int nedge32 = (K * p.nb + 31) & ~31;
+  const int fthreads = nedge32 < EF_THREADS ? nedge32 : EF_THREADS;
+  VQA_CUDA(cudaFuncSetAttribute(edge_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EF_THREADS * 33 * 4));
+  edge_finish_kernel<<<B, fthreads, (size_t)fthreads * 33 * 4, stream>>>(p);
+  VQA_LAUNCH_CHECK("graphconv edge_finish_kernel");
   return VQA_OK;
 }
 
@@ -1344,7 +1473,7 @@ extern "C" int vqa_graphconv_mma_bwd_edges(const void* dO_hi, const void* dO_lo,
   VQA_CHECK_ARG(!pooled || (dpooled && argmax), "%s: need either dO planes or (dpooled, argmax)", who);
   gm::PParams p{};
   p.idx = idx; p.alpha = alpha; p.boxes = boxes; p.ldbox = ldbox; p.gauss = gauss; p.dpooled = dpooled; p.argmax = argmax;
-  p.dalpha = dalpha; p.partial = dgauss_partial; p.pacc_global = p_scratch;
+  p.dalpha = dalpha; p.partial = dgauss_partial; p.pacc = p_scratch;
   p.B = B; p.K = K; p.nb = nb; p.nk = nk; p.out_dim = out_dim;
   return pooled ? gm::edge_p_launch<true>(nullptr, nullptr, 0, Y_hi, Y_lo, ldy, p, stream, who)
                 : gm::edge_p_launch<false>(dO_hi, dO_lo, lddo, Y_hi, Y_lo, ldy, p, stream, who);
@@ -1417,9 +1546,9 @@ extern "C" int vqa_graphconv_pool_bwd_data(const float* dpooled, const long long
 }
 
 #ifdef VQA_EDGE_TRACE
-extern "C" int vqa_debug_edge_trace(unsigned long long* out, int n_ctas) {
-  if (n_ctas > 4096) n_ctas = 4096;
+extern "C" int vqa_debug_edge_trace(long long* out, int n_ctas) {
+  if (n_ctas > 256) n_ctas = 256;
   cudaDeviceSynchronize();
-  return cudaMemcpyFromSymbol(out, gm::g_edge_trace, (size_t)n_ctas * 16 * sizeof(unsigned long long)) == cudaSuccess ? VQA_OK : VQA_ERR_CUDA;
+  return cudaMemcpyFromSymbol(out, gm::g_edge_trace, (size_t)n_ctas * 8 * sizeof(long long)) == cudaSuccess ? VQA_OK : VQA_ERR_CUDA;
 }
 #endif

@@ -482,7 +482,7 @@ def graphconv_bwd_edges_s(Ys: SplitT, idx, alpha, image, gauss, B, K, dOs: Optio
     partial = torch.empty((B, 4 * nk), device=dev, dtype=torch.float32)
     if dOs is None:
         dpooled = _chk(dpooled, "dpooled").contiguous()
-    scratch = torch.empty((B, K, nb, nk), device=dev, dtype=torch.float32) if K * nb * nk * 4 > 48 * 1024 else None
+    scratch = torch.empty((B, nk, K * nb), device=dev, dtype=torch.float32)       # selected edge products, written and read within the call
     _call("vqa_graphconv_mma_bwd_edges", None if dOs is None else dOs.hi.data_ptr(), None if dOs is None else _ptr(dOs.lo),
           0 if dOs is None else dOs.ld, _ptr(dpooled), _ptr(argmax), Ys.hi.data_ptr(), _ptr(Ys.lo), Ys.ld, idx.data_ptr(), _ptr(alpha),
           bptr, ldbox, gauss.data_ptr(), _ptr(dalpha), partial.data_ptr(), _ptr(scratch), B, K, nb, nk, out_dim, _stream())
