@@ -76,3 +76,8 @@ for sname in args.shapes.split(","):
     timeit(tag, "graphconv_mma_bwd_edges L2 pooled", lambda: kn.graphconv_bwd_edges_s(Y2, idx, None, img, gauss, B, K, dpooled=dp, argmax=arg), M * H * 4 + 2 * M * nb * 4)
     timeit(tag, "graphconv_pool_bwd_data L2", lambda: kn.graphconv_pool_bwd_data_s(dp, arg, idx, ec2, B, K, H), M * H * 4 + M * nb * nk * 4)
     del Y1, Y2, dO1
+
+# column sums of the step tail (bias gradients): GRU gate gradients (T*B, 3H), graph-learner hidden gradients (B*K, 512), logits
+for rows, cols in ((7168, 3072), (18432, 512), (512, 3000), (512, 32)):
+    x = torch.randn(rows, cols, device=dev)
+    timeit("tail", f"colsum {rows}x{cols}", lambda: kn.colsum(x), rows * cols * 4 + cols * 4)

@@ -235,6 +235,19 @@ __global__ void __launch_bounds__(256) colsum_stage1_v4(const float* __restrict_
   if (cq * 4 < cols) {
     const float* px = x + (long long)cq * 4;
     long long r = r0 + ry;
+    for (; r + 28 < r1; r += 32) {                           // 8 loads (128 B) in flight per thread
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldcs(reinterpret_cast<const float4*>(px + (r + 4 * i) * ldx));
+      a0.x += v[0].x; a0.y += v[0].y; a0.z += v[0].z; a0.w += v[0].w;
+      a1.x += v[1].x; a1.y += v[1].y; a1.z += v[1].z; a1.w += v[1].w;
+      a2.x += v[2].x; a2.y += v[2].y; a2.z += v[2].z; a2.w += v[2].w;
+      a3.x += v[3].x; a3.y += v[3].y; a3.z += v[3].z; a3.w += v[3].w;
+      a0.x += v[4].x; a0.y += v[4].y; a0.z += v[4].z; a0.w += v[4].w;
+      a1.x += v[5].x; a1.y += v[5].y; a1.z += v[5].z; a1.w += v[5].w;
+      a2.x += v[6].x; a2.y += v[6].y; a2.z += v[6].z; a2.w += v[6].w;
+      a3.x += v[7].x; a3.y += v[7].y; a3.z += v[7].z; a3.w += v[7].w;
+    }
     for (; r + 12 < r1; r += 16) {
       const float4 v0 = *reinterpret_cast<const float4*>(px + r * ldx), v1 = *reinterpret_cast<const float4*>(px + (r + 4) * ldx),
                    v2 = *reinterpret_cast<const float4*>(px + (r + 8) * ldx), v3 = *reinterpret_cast<const float4*>(px + (r + 12) * ldx);
@@ -270,7 +283,15 @@ __global__ void __launch_bounds__(256) colsum_stage1_v4(const float* __restrict_
   __threadfence();
   if (ry == 0 && cq * 4 < cols) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int b = 0; b < (int)gridDim.y; ++b) {
+    int b = 0;
+    for (; b + 8 <= (int)gridDim.y; b += 8) {               // loads batched, sums in block order
+      float4 t[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = __ldcg(reinterpret_cast<const float4*>(scratch + (long long)(b + i) * cols + cq * 4));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { acc.x += t[i].x; acc.y += t[i].y; acc.z += t[i].z; acc.w += t[i].w; }
+    }
+    for (; b < (int)gridDim.y; ++b) {
       const float4 t = __ldcg(reinterpret_cast<const float4*>(scratch + (long long)b * cols + cq * 4));
       acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
     }
@@ -363,10 +384,16 @@ extern "C" int vqa_weight_norm_bwd_f32(const float* dw, const float* v, const fl
 extern "C" int vqa_colsum_f32(const float* x, long long ldx, float* out, float* scratch, long long rows, int cols,
                               int* counters, cudaStream_t stream) {
   VQA_CHECK_ARG(x && out && scratch && rows > 0 && cols > 0 && ldx >= cols, "vqa_colsum_f32: bad arguments");
-  const int nblk = (int)min(256LL, (rows + 63) / 64);
-  const long long rpb = (rows + nblk - 1) / nblk;
+  int nblk = (int)min(256LL, (rows + 63) / 64);
+  long long rpb = (rows + nblk - 1) / nblk;
   if ((cols & 3) == 0 && (ldx & 3) == 0 && aligned16(x) && aligned16(scratch)) {
-    dim3 grid((cols / 4 + 63) / 64, nblk), block(64, 4);
+    // one resident wave: 8 blocks of 256 threads per SM; a second, nearly empty wave would cost as much as the first
+    const int cblk = (cols / 4 + 63) / 64;
+    const int one_wave = (kNumSMs * 8) / cblk;
+    if (nblk > one_wave) nblk = one_wave < 1 ? 1 : one_wave;
+    rpb = (rows + nblk - 1) / nblk;
+    nblk = (int)((rows + rpb - 1) / rpb);
+    dim3 grid(cblk, nblk), block(64, 4);
     const bool fused = counters != nullptr && aligned16(out);
     colsum_stage1_v4<<<grid, block, 0, stream>>>(x, ldx, scratch, rows, cols, rpb, out, fused ? counters : nullptr);
     VQA_LAUNCH_CHECK("colsum_stage1_v4");

@@ -1060,6 +1060,7 @@ edge_p_kernel(const __grid_constant__ PMaps tm, const PParams p) {
       for (int w = bt; w < planes * (p.a_plane >> 4); w += 128) *reinterpret_cast<uint4*>(a_hi + w * 16) = make_uint4(0u, 0u, 0u, 0u);
       prev[s * 256 + bt] = ~0u; prev[s * 256 + 128 + bt] = ~0u;
     }
+    asm volatile("bar.sync 2, 128;" ::: "memory");          // the zero fill is shared work: nobody writes an entry before all of it has landed
     // argmax / dpooled of an item come from HBM (~1 us under load): each thread copies its two entries EP_PF - 1 items ahead into
     // a private slot of a small ring with cp.async, so their latency never sits on the chain stage-free -> tile-ready.
     long long* aring = reinterpret_cast<long long*>(sm + p.off_ring);           // [EP_PF][256]
