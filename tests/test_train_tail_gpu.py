@@ -216,16 +216,20 @@ def test_captured_step_follows_the_plain_loop_trajectory():
         red.remove()
     (lg, pg), (lp, pp) = runs
     assert lg == pytest.approx(lp, rel=1e-6), (lg, lp)            # same kernels, same order: the first loss would already differ after a hidden update
-    # Parameters: the split-K weight-gradient products and the embedding scatter add with atomics, so two runs of the SAME loop differ in
-    # the last bits of the question-path gradients (measured: 1e-11), and Adam turns that into up to lr * dg / eps = 1e5 * dg for the
-    # elements whose gradient is itself rounding noise.  So: all but a sliver of the elements agree to 1e-6, and none moved further
-    # than Adam can move an element in six steps.
-    far = total = 0
+    # Parameters: the split-K weight-gradient products and the embedding scatter add with atomics, so two runs of the SAME loop differ
+    # in the last bits of the question-path gradients (measured: 1e-11 at step 0), Adam turns that into up to lr * dg / eps = 1e5 * dg
+    # for elements whose gradient is itself rounding noise, and a ReLU mask that flips on such an element changes later gradients
+    # discretely (measured between two plain runs as well as between graph and plain).  What a captured step must reproduce is
+    # the movement: per tensor, the two runs' distance is a small fraction of the distance travelled from the initial weights
+    # (one hidden or missing update would be ~1/6 of it), and no element moved further than Adam can move it in six steps.
+    torch.manual_seed(1000)
+    kw = w.model_kwargs(); kw["dropout"] = 0.0
+    init = {k: v.detach().clone() for k, v in M.Model(pretrained_wemb=make_wemb(w), **kw).to(DEV).state_dict().items()}
     for k in pp:
-        d = (pg[k].float() - pp[k].float()).abs()
-        far += int((d > 1e-6).sum()); total += d.numel()
-        assert float(d.max()) <= 2 * 6 * 1e-3, k
-    assert far <= 2e-3 * total, (far, total)
+        d = (pg[k].float() - pp[k].float())
+        moved = (pp[k].float() - init[k].float()).norm().item()
+        assert float(d.abs().max()) <= 2 * 6 * 1e-3, k
+        assert d.norm().item() <= 2e-2 * moved + 1e-7, (k, d.norm().item(), moved)
 
 
 def test_train_step_requires_max_question_len():

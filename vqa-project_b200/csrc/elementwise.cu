@@ -281,21 +281,31 @@ __global__ void __launch_bounds__(256) colsum_stage1_v4(const float* __restrict_
   __syncthreads();
   if (!last) return;
   __threadfence();
-  if (ry == 0 && cq * 4 < cols) {
+  // the four row lanes each add a quarter of the row blocks' partials (in block order), then lane 0 adds the four quarters in order
+  {
+    const int nb_ = (int)gridDim.y, q = (nb_ + 3) >> 2, b1 = min(nb_, (ry + 1) * q);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int b = 0;
-    for (; b + 8 <= (int)gridDim.y; b += 8) {               // loads batched, sums in block order
-      float4 t[8];
+    if (cq * 4 < cols) {
+      int b = ry * q;
+      for (; b + 8 <= b1; b += 8) {                         // loads batched, sums in block order
+        float4 t[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) t[i] = __ldcg(reinterpret_cast<const float4*>(scratch + (long long)(b + i) * cols + cq * 4));
+        for (int i = 0; i < 8; ++i) t[i] = __ldcg(reinterpret_cast<const float4*>(scratch + (long long)(b + i) * cols + cq * 4));
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { acc.x += t[i].x; acc.y += t[i].y; acc.z += t[i].z; acc.w += t[i].w; }
+        for (int i = 0; i < 8; ++i) { acc.x += t[i].x; acc.y += t[i].y; acc.z += t[i].z; acc.w += t[i].w; }
+      }
+      for (; b < b1; ++b) {
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(scratch + (long long)b * cols + cq * 4));
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
     }
-    for (; b < (int)gridDim.y; ++b) {
-      const float4 t = __ldcg(reinterpret_cast<const float4*>(scratch + (long long)b * cols + cq * 4));
-      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-    }
-    *reinterpret_cast<float4*>(out + cq * 4) = acc;
+    part[ry][threadIdx.x] = acc;
+  }
+  __syncthreads();
+  if (ry == 0 && cq * 4 < cols) {
+    const float4 p0 = part[0][threadIdx.x], p1 = part[1][threadIdx.x], p2 = part[2][threadIdx.x], p3 = part[3][threadIdx.x];
+    *reinterpret_cast<float4*>(out + cq * 4) =
+        make_float4((p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y), (p0.z + p1.z) + (p2.z + p3.z), (p0.w + p1.w) + (p2.w + p3.w));
   }
 }
 __global__ void __launch_bounds__(256) colsum_stage2(const float* __restrict__ scratch, float* __restrict__ out, int nblk, int cols) {
