@@ -42,6 +42,7 @@ def parse():
                     help="criterion + optimiser: our single-launch kernels (vqa_b200.loss / vqa_b200.optim) or torch's modules")
     ap.add_argument("--no-resident-table", action="store_true", help="skip the ShardLoader (feature table in HBM) end-to-end leg")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying the captured CUDA graph")
+    ap.add_argument("--gemm-table", default="", help="write one line per dense product of a step (M, N, K, passes, event-bracketed us, TFLOP/s, fraction of the bf16 peak) to this file (diagnosis)")
     ap.add_argument("--kernel-totals", default="", help="also run 10 steps under torch.profiler on rank 0 and write per-kernel device time totals to this file (diagnosis)")
     ap.add_argument("--quick", action="store_true", help="device-resident and end-to-end legs only (scaling experiments)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="questions per CPU step (bounded sample of the workload)")
@@ -604,6 +605,16 @@ def run_b200(args, workload):
             raw += 2.0 * rows * N_ * K_ * ps
         raw, useful = raw / 6.0, useful / 6.0
         ach_tf = raw / (per_step * 1e-3) / 1e12
+        if args.gemm_table and len(gm) == len(gemm_log) and len(gm) % 6 == 0:
+            n = len(gm) // 6
+            with open(args.gemm_table, "w") as f:
+                for j in range(n):                                           # launch j of each of the 6 timed steps
+                    M_, N_, K_, ps, gate = gemm_log[j]
+                    rows = M_ if gate is None else min(M_, alive_rows(gate))
+                    ms = med([gm[i * n + j] for i in range(6)])
+                    tf = 2.0 * rows * N_ * K_ * ps / (ms * 1e-3) / 1e12
+                    f.write(json.dumps({"launch": j, "M": M_, "N": N_, "K": K_, "passes": ps, "row_gate_step": gate, "live_rows": rows, "us": round(ms * 1e3, 1),
+                                        "mma_tflops": round(tf, 1), "frac_of_bf16_peak": round(tf / tf_peak, 3)}) + "\n")
         roof_gemm = {"kernel": "gemm_bf16s_kernel / gemm_bf16s_persistent_kernel (all dense projections of one step, event-bracketed launches incl. gaps)",
                      "bound": "tensor", "ms_per_step": round(per_step, 3), "launches_per_step": len(gm) // 6, "passes": passes,
                      "useful_tflop_per_step": round(useful / 1e12, 4), "mma_tflop_per_step": round(raw / 1e12, 4),

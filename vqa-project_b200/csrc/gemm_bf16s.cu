@@ -55,10 +55,11 @@ struct Cfg {
   static constexpr int B_TILE = BN * 128;
   static constexpr int PLANE = A_TILE + B_TILE;               // [A | B] of one plane
   static constexpr int STAGE = PLANE * PLANES;
-  static constexpr int S_ = SMEM_BUDGET / STAGE;
+  static constexpr int BIAS_S = 4 * BN * 4;                   // one copy of the tile's bias columns per epilogue warp
+  static constexpr int S_ = (SMEM_BUDGET - BIAS_S) / STAGE;
   // BN = 64 is the small-problem tile (few CTAs, latency-bound): 2 x 48 KB stages so that 2 CTAs are resident per SM
   static constexpr int S = BN == 64 ? (PLANES == 2 ? 2 : 4) : (S_ > 8 ? 8 : S_);
-  static constexpr int SMEM = S * STAGE + 1024 + 256;
+  static constexpr int SMEM = S * STAGE + 1024 + 256 + BIAS_S;
 };
 
 // UMMA shared-memory descriptor, 16-bit operands, 128-byte swizzle.
@@ -83,8 +84,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 struct Epi {
   const Params& p;
   float* crow; __nv_bfloat16* hrow; __nv_bfloat16* lrow; const float* rb; const float* ax; const __nv_bfloat16* axh;
+  const float* bs;      // the bias, staged in shared memory by the caller and offset so that bs[col] is column col (NULL: no bias)
   bool vec_ok, relu, atomic;
-  __device__ __forceinline__ Epi(const Params& p_, int row) : p(p_) {
+  __device__ __forceinline__ Epi(const Params& p_, int row, const float* bias_smem) : p(p_), bs(bias_smem) {
     relu = p.flags & VQA_GEMM_RELU; atomic = p.flags & VQA_GEMM_ATOMIC_ADD;
     crow = p.C ? p.C + (long long)row * p.ldc : nullptr;
     hrow = p.Chi ? p.Chi + (long long)row * p.ldcs : nullptr;
@@ -109,20 +111,41 @@ struct Epi {
     return v;
   }
   __device__ __forceinline__ void store32(int cb, const float* r) const {
-    if (vec_ok && !atomic) {
+    if (vec_ok && !atomic && !(rb && ax)) {
+      // Loads first, arithmetic and stores second: with the loads interleaved group by group (and an early exit between the
+      // groups that keeps the compiler from hoisting them) every 8 columns waited for a global-memory round trip of their own -
+      // measured on GI = E W_ih^T (K = 300): 45 % of all stall samples sat on the FADD behind the bias load, and draining a
+      // 128 x 256 tile took ~20 us against 4 us to accumulate it.  The bias now comes from shared memory (staged per tile before
+      // the accumulator is waited for); the row broadcast / mask values of all 32 columns are requested in one go.
+      const int ng = min(4, (p.N - cb + 7) >> 3);           // 8-column groups inside N (cb < N)
+      const float* src = rb ? rb : ax;                      // (never both here)
+      float t[32];
+      uint4 mh[4];
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        const int col = cb + j;
-        if (col >= p.N) break;
+      for (int g = 0; g < 4; ++g) {
+        const int col = cb + 8 * g;
+        if (g < ng) {
+          if (src) {
+            const float4 a0 = *reinterpret_cast<const float4*>(src + col), a1 = *reinterpret_cast<const float4*>(src + col + 4);
+            t[8 * g] = a0.x; t[8 * g + 1] = a0.y; t[8 * g + 2] = a0.z; t[8 * g + 3] = a0.w;
+            t[8 * g + 4] = a1.x; t[8 * g + 5] = a1.y; t[8 * g + 6] = a1.z; t[8 * g + 7] = a1.w;
+          }
+          if (axh) mh[g] = *reinterpret_cast<const uint4*>(axh + col);
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int col = cb + 8 * g, j = 8 * g;
+        if (g >= ng) continue;
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = r[j + e];
         if (rb) {
-          const float4 a0 = *reinterpret_cast<const float4*>(rb + col), a1 = *reinterpret_cast<const float4*>(rb + col + 4);
-          v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] += t[j + e];
         }
-        if (p.bias) {
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.bias + col)), a1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
+        if (bs) {
+          const float4 a0 = *reinterpret_cast<const float4*>(bs + col), a1 = *reinterpret_cast<const float4*>(bs + col + 4);
           v[0] += a0.x; v[1] += a0.y; v[2] += a0.z; v[3] += a0.w; v[4] += a1.x; v[5] += a1.y; v[6] += a1.z; v[7] += a1.w;
         }
         if (relu) {
@@ -130,14 +153,11 @@ struct Epi {
           for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
         }
         if (ax) {
-          const float4 a0 = *reinterpret_cast<const float4*>(ax + col), a1 = *reinterpret_cast<const float4*>(ax + col + 4);
-          const float m[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = m[e] > 0.f ? v[e] * p.aux_scale : 0.f;
+          for (int e = 0; e < 8; ++e) v[e] = t[j + e] > 0.f ? v[e] * p.aux_scale : 0.f;
         }
         if (axh) {
-          const uint4 a = *reinterpret_cast<const uint4*>(axh + col);
-          const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+          const uint32_t w[4] = {mh[g].x, mh[g].y, mh[g].z, mh[g].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {     // bf16 > 0  <=>  sign clear and magnitude bits non-zero
             const uint32_t lo16 = w[e] & 0xFFFFu, hi16 = w[e] >> 16;
@@ -182,6 +202,21 @@ struct Epi {
     }
   }
 };
+
+// The bias columns [n0, n0 + BN) of a tile, copied by each epilogue warp into its own shared-memory row BEFORE it waits for the
+// accumulator; returns the pointer offset so that [col] addresses column col (NULL without a bias).
+template <int BN>
+__device__ __forceinline__ const float* stage_bias(const Params& p, float* warp_row, int lane, int n0) {
+  if (!p.bias) return nullptr;
+  __syncwarp();                                              // the previous tile's reads are done
+#pragma unroll
+  for (int i = 0; i < BN / 32; ++i) {
+    const int col = n0 + lane + 32 * i;
+    warp_row[lane + 32 * i] = col < p.N ? __ldg(p.bias + col) : 0.f;
+  }
+  __syncwarp();
+  return warp_row - n0;
+}
 
 struct Maps { CUtensorMap a_hi, a_lo, b_hi, b_lo; };
 
@@ -322,12 +357,13 @@ gemm_bf16s_kernel(const __grid_constant__ Maps tm, const Params p) {
     }
   } else {
     // ------------------------------------------------------------ warps 2-5: epilogue
+    const float* bs = stage_bias<BN>(p, reinterpret_cast<float*>(smem + S * C::STAGE + 256) + (warp - 2) * BN, lane, n0);
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < p.M;
-    const Epi epi(p, row_ok ? row : 0);
+    const Epi epi(p, row_ok ? row : 0, bs);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= p.N) break;            // warp-uniform
@@ -497,12 +533,13 @@ gemm_bf16s_persistent_kernel(const __grid_constant__ Maps tm, const Params p, co
       decode(u, n0, m0, kb_begin, nkb, live);
       if (!live) continue;
       const int acc = t & 1;
+      const float* bs = stage_bias<BN>(p, reinterpret_cast<float*>(smem + S * C::STAGE + 256) + (warp - 2) * BN, lane, n0);
       if (lane == 0) mbar_wait(&acc_full[acc], (t >> 1) & 1);
       __syncwarp();
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
-      const Epi epi(p, row_ok ? row : 0);
+      const Epi epi(p, row_ok ? row : 0, bs);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         if (n0 + c0 >= p.N) break;            // warp-uniform
