@@ -598,9 +598,15 @@ def run_b200(args, workload):
         def alive_rows(t):                                                   # rows of tiles with a question longer than t (batches are length-sorted)
             n = [sum(128 for r0 in range(0, len(q), 128) if q[r0] > t) for q in qh]
             return sum(n) / len(n)
+        def gated_rows(M_, gate):                                            # gate: None | step t of a per-step product | -1 = all steps of a (T*B, .) product
+            if gate is None:
+                return M_
+            if gate == -1:
+                return sum(min(B, alive_rows(t)) for t in range(M_ // B))
+            return min(M_, alive_rows(gate))
         raw = useful = 0.0
         for (M_, N_, K_, ps, gate) in gemm_log:
-            rows = M_ if gate is None else min(M_, alive_rows(gate))
+            rows = gated_rows(M_, gate)
             useful += 2.0 * rows * N_ * K_
             raw += 2.0 * rows * N_ * K_ * ps
         raw, useful = raw / 6.0, useful / 6.0
@@ -610,7 +616,7 @@ def run_b200(args, workload):
             with open(args.gemm_table, "w") as f:
                 for j in range(n):                                           # launch j of each of the 6 timed steps
                     M_, N_, K_, ps, gate = gemm_log[j]
-                    rows = M_ if gate is None else min(M_, alive_rows(gate))
+                    rows = gated_rows(M_, gate)
                     ms = med([gm[i * n + j] for i in range(6)])
                     tf = 2.0 * rows * N_ * K_ * ps / (ms * 1e-3) / 1e12
                     f.write(json.dumps({"launch": j, "M": M_, "N": N_, "K": K_, "passes": ps, "row_gate_step": gate, "live_rows": rows, "us": round(ms * 1e3, 1),

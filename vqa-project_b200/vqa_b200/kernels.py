@@ -174,7 +174,8 @@ def gemm_s(a: SplitT, b: SplitT, *, a_mn: bool = False, b_mn: bool = False, out:
     """C[M,N] = epi(A . B^T) on the split-bf16 tcgen05 GEMM (``accumulate``: ``out += A . B^T`` with fp32 atomics).  ``a`` is (M,K) [a_mn=False] or (K,M) [a_mn=True]; same
     for ``b`` with N.  ``aux`` (mask source) may be an fp32 tensor or a SplitT.  Returns ``out`` (fp32) or, when
     ``want_f32`` is False, ``out_split``.  ``row_gate`` = (int32 device tensor with one entry per 128-row tile of the output,
-    t): row tiles with entry <= t are skipped entirely (padded recurrences)."""
+    t): row tiles with entry <= t are skipped entirely (padded recurrences; a third element "all_steps" marks a gate tensor that
+    covers the row tiles of every time step of a (T*B, .) product - only bench.py's FLOP count reads it)."""
     M, Ka = (a.cols, a.rows) if a_mn else (a.rows, a.cols)
     N, Kb = (b.cols, b.rows) if b_mn else (b.rows, b.cols)
     if Ka != Kb:
@@ -202,7 +203,7 @@ def gemm_s(a: SplitT, b: SplitT, *, a_mn: bool = False, b_mn: bool = False, out:
     ldrb = ldaux = ldauxh = 0
     aux_f = aux_h = None
     if GEMM_LOG is not None:
-        GEMM_LOG.append((M, N, Ka, passes, None if row_gate is None else int(row_gate[1])))
+        GEMM_LOG.append((M, N, Ka, passes, None if row_gate is None else (-1 if len(row_gate) > 2 else int(row_gate[1]))))
     if rowbcast is not None:
         rowbcast, ldrb = _rows_view(_chk(rowbcast, "gemm_s rowbcast"), "gemm_s rowbcast")
     if isinstance(aux, SplitT):

@@ -404,6 +404,20 @@ def _unit_block_perm(H: int, device) -> torch.Tensor:
     return _UB_PERM[key]
 
 
+_STEP_INDEX = {}
+
+
+def _all_steps_gate(tile_len: torch.Tensor, T: int, B: int):
+    """Row-tile gate of a product over all T*B rows (time-major): tile (t, j) is live while tile_len[j] - t > 0.  Only when a step
+    is a whole number of 128-row tiles; otherwise None (no gating)."""
+    if B % 128 != 0:
+        return None
+    key = (T, str(tile_len.device))
+    if key not in _STEP_INDEX:
+        _STEP_INDEX[key] = torch.arange(T, device=tile_len.device, dtype=torch.int32).view(T, 1)
+    return ((tile_len.view(1, -1) - _STEP_INDEX[key]).reshape(-1).contiguous(), 0, "all_steps")
+
+
 class QuestionEncoderFn(torch.autograd.Function):
     """(question tokens, lengths, embedding + GRU parameters) -> final GRU state per question (B, H).
 
@@ -445,7 +459,8 @@ class QuestionEncoderFn(torch.autograd.Function):
             # every question's state at its OWN last step (rows of skipped tiles are not carried forward)
             out = Hall[qlen.to(torch.int64).clamp(min=0, max=T), torch.arange(B, device=dev)]
         else:
-            GI = kn.gemm_s(Es, Wihs, bias=b_ih)                                   # (T*B, 3H), all steps at once
+            # (T*B, 3H), all steps at once; like the per-step products it skips the row tiles of (step t, tile j) whose questions have all ended
+            GI = kn.gemm_s(Es, Wihs, bias=b_ih, row_gate=_all_steps_gate(tile_len, T, B))
             Hs = kn.empty_split((T + 1) * B, H, dev)
             Hall[0].zero_(); Hs.hi[:B].zero_(); Hs.lo[:B].zero_()
             # per-step product h W_hh^T: L2-bandwidth bound at M = B rows (measured sweep, tools/gru_gemm_sweep.py): 128-wide tiles, no split
@@ -491,7 +506,8 @@ class QuestionEncoderFn(torch.autograd.Function):
         # weight-gradient products below instead of after them
         dwemb = None
         if ctx.needs_input_grad[3]:
-            dE = kn.gemm_s(dGIs, Wihs, b_mn=True, **_plan(TB, Wihs.cols, Wihs.rows))   # (T*B, E)
+            # (T*B, E); rows of ended questions are never read by the scatter below: their row tiles are skipped
+            dE = kn.gemm_s(dGIs, Wihs, b_mn=True, row_gate=_all_steps_gate(ctx.tile_len, T, B), **_plan(TB, Wihs.cols, Wihs.rows))
             dwemb = _sink(wemb)
             sunk = dwemb is not None
             if dwemb is None:
