@@ -518,7 +518,13 @@ class QuestionEncoderFn(torch.autograd.Function):
             if sunk:
                 _ready(wemb)
         db_ih = kn.colsum(dGI, out=_sink(b_ih_))
-        db_hh = kn.colsum(dGH, out=_sink(b_hh_))
+        # dgh equals dgi in the r and z thirds (the reset gate only scales the candidate's hidden term, gru.cu): only the last third
+        # of b_hh's gradient needs a column sum of its own
+        db_hh = _sink(b_hh_)
+        if db_hh is None:
+            db_hh = torch.empty_like(db_ih)
+        db_hh[:2 * H].copy_(db_ih[:2 * H])
+        kn.colsum(dGH[:, 2 * H:], out=db_hh[2 * H:])
 
         def wgrad(a, b, prm):
             plan = _plan(a.cols, b.cols, TB)
