@@ -55,7 +55,7 @@ struct Cfg {
   static constexpr int B_TILE = BN * 128;
   static constexpr int PLANE = A_TILE + B_TILE;               // [A | B] of one plane
   static constexpr int STAGE = PLANE * PLANES;
-  static constexpr int BIAS_S = 4 * BN * 4;                   // one copy of the tile's bias columns per epilogue warp
+  static constexpr int BIAS_S = 8 * BN * 4;                   // one copy of the tile's bias columns per epilogue warp (up to 8 of them)
   static constexpr int S_ = (SMEM_BUDGET - BIAS_S) / STAGE;
   // BN = 64 is the small-problem tile (few CTAs, latency-bound): 2 x 48 KB stages so that 2 CTAs are resident per SM
   static constexpr int S = BN == 64 ? (PLANES == 2 ? 2 : 4) : (S_ > 8 ? 8 : S_);
@@ -415,8 +415,14 @@ gemm_bf16s_kernel(const __grid_constant__ Maps tm, const Params p) {
 // 54 % of the tensor peak on dG1 (K = 1024, mask + planes), 30-35 % on the short-K products (K = 300 / 512).
 struct PSched { int tiles_n, tiles_m, units_m, splits, units, nclusters; };
 
+// Epilogue warps: four (one per TMEM lane quarter) or eight (two per quarter, each half of the tile's columns), chosen by the block
+// size the host launches with.  A drain is a latency-bound instruction stream (one warp per scheduler has nothing to hide its
+// loads and conversions behind): eight warps drain a tile in about half the time, which is what the short-contraction products
+// need (their tile is accumulated in 4-6 us and drained in 10-20); the long ones hide the drain anyway and ran 7 % slower with
+// eight (measured in round 1), so they keep four.
+constexpr int THREADS_EPI8 = 32 * 10;
 template <int BN, int PASSES, int CL>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS_EPI8, 1)
 gemm_bf16s_persistent_kernel(const __grid_constant__ Maps tm, const Params p, const PSched sc) {
   using C = Cfg<BN, PASSES>;
   constexpr int S = C::S;
@@ -439,7 +445,7 @@ gemm_bf16s_persistent_kernel(const __grid_constant__ Maps tm, const Params p, co
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
-      for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+      for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], (blockDim.x >> 5) - 2); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -550,8 +556,10 @@ gemm_bf16s_persistent_kernel(const __grid_constant__ Maps tm, const Params p, co
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------ warps 2-5: epilogue of tile t while tile t + 1 is being accumulated
+    // ------------------------------------------------------------ warps 2-5 (2-9): epilogue of tile t while tile t + 1 is being accumulated
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const bool epi8 = blockDim.x == THREADS_EPI8;
+    const int c_begin = epi8 ? ((warp - 2) >> 2) * (BN / 2) : 0, c_end = epi8 ? c_begin + BN / 2 : BN;   // this warp's columns of the tile
     int t = 0;
     for (int u = cluster; u < sc.units; u += sc.nclusters) {
       int n0, m0, kb_begin, nkb; bool live;
@@ -566,7 +574,7 @@ gemm_bf16s_persistent_kernel(const __grid_constant__ Maps tm, const Params p, co
       const bool row_ok = row < p.M;
       const Epi epi(p, row_ok ? row : 0, bs);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
         if (n0 + c0 >= p.N) break;            // warp-uniform
         uint32_t r[32];
         tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
@@ -906,7 +914,10 @@ static int launch(const Maps& tm, const Params& p, int splits, cudaStream_t st) 
       attr_set_p = true;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(sc.nclusters * CL); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
+    // eight epilogue warps when a tile is accumulated faster than four warps drain it (contraction of at most 8 k-blocks = 512 per split; VQA_GEMM_EPI8_MAX_KB overrides for measurements)
+    static const int epi8_max_kb = getenv("VQA_GEMM_EPI8_MAX_KB") ? atoi(getenv("VQA_GEMM_EPI8_MAX_KB")) : 8;
+    const bool epi8 = BN >= 128 && p.kb_per_split <= epi8_max_kb;
+    cfg.gridDim = dim3(sc.nclusters * CL); cfg.blockDim = dim3(epi8 ? THREADS_EPI8 : THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
