@@ -595,7 +595,12 @@ def test_graphconv_mma_bwd_data(kn, B, K, nb, nk, out_dim, use_alpha):
     assert rel_err(dY.float().view(B, K, -1).cpu(), dY_ref) < 3e-5
 
 
-@pytest.mark.parametrize("B,K,nb,nk,out_dim", MMA_CASES)
+# the edge kernel stacks G = min(floor(128 / K), 4, B) consecutive images in one MMA: batches that end inside a group, the cap of
+# four, one image per group (K > 64), groups whose rows straddle the 32-lane quarters of TMEM, nb not a multiple of 4
+EDGE_GROUP_CASES = [(5, 36, 16, 8, 1024), (7, 12, 4, 2, 256), (9, 20, 8, 4, 512), (1, 36, 16, 8, 512), (4, 64, 16, 4, 256), (3, 65, 9, 2, 128), (6, 31, 7, 2, 128)]
+
+
+@pytest.mark.parametrize("B,K,nb,nk,out_dim", MMA_CASES + EDGE_GROUP_CASES)
 @pytest.mark.parametrize("mode", ["dense_alpha", "dense", "pooled"])
 def test_graphconv_mma_bwd_edges(kn, B, K, nb, nk, out_dim, mode):
     image, Y, idx, alpha, gp = _gc_inputs(B, K, nb, nk, out_dim, seed=3 * K + nb)
