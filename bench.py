@@ -454,8 +454,8 @@ def run_b200(args, workload):
 
             def stage(i):
                 """Assemble batch i on the copy stream (index H2D + gather/scatter kernels) and hand it to the step's idle slot."""
-                with torch.cuda.stream(step.copy_stream):
-                    q, a, _nv, _qid, image, k, qlen, _idx = ld.assemble(order[i % len(order)])
+                with torch.cuda.stream(step.copy_stream):                # the image batch is gathered straight into the step's idle input slot
+                    q, a, _nv, _qid, image, k, qlen, _idx = ld.assemble(order[i % len(order)], image_out=step.input_slot("image"))
                 step.prefetch(q, image, k, qlen, a)
                 return q, image, k, qlen, a
 

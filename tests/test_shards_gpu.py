@@ -176,3 +176,38 @@ def test_medical_loader_reproduces_the_reference_golden_batches(tmp_path, varian
             assert batch[j].dtype == want.dtype and batch[j].shape == want.shape and torch.equal(batch[j].cpu(), want), (b, name)
         assert list(batch[7]) == [str(x) for x in z[f"{variant}.batch{b}.iid"]]
     ld.check_errors()
+
+
+def test_loader_gathers_the_image_batch_into_the_training_steps_input_slot(tmp_path):
+    """engine.TrainStep.input_slot + ShardLoader.assemble(image_out=...): from the second step on the image batch is gathered
+    straight into the captured step's idle input buffer (no second 151 MB copy at the VQA2 shapes) and training is unchanged."""
+    import sparse_graph_model as M
+    from vqa_b200.ddp import GradReducer
+    from vqa_b200.engine import TrainStep
+    from vqa_b200.loss import MultiLabelSoftMarginLoss
+    from vqa_b200.optim import FlatAdam
+    ds = SF.make_dataset(n_images=7, n_questions=40, K=12, D=16, n_answers=24)
+    _convert(ds, tmp_path, q_width=10)
+    runs = {}
+    for direct in (False, True):
+        torch.manual_seed(0)
+        model = M.Model(vocab_size=40, emb_dim=8, feat_dim=20, hid_dim=32, out_dim=24, pretrained_wemb=np.zeros((40, 8), np.float32) + 0.1,
+                        dropout=0.0, n_kernels=4, neighbourhood_size=5, n_obj=12).to(DEV).train()
+        model.max_question_len = 10
+        red = GradReducer(model.parameters())
+        step = TrainStep(model, FlatAdam(red, lr=1e-3), MultiLabelSoftMarginLoss(), reducer=red, use_graph=True, seed=3)
+        ld = shards.ShardLoader(str(tmp_path), 8, DEV, shuffle=False, order="none")
+        losses, in_place = [], 0
+        for ep in range(2):
+            for idx in ld.batches():
+                with torch.cuda.stream(step.copy_stream):
+                    slot = step.input_slot("image") if direct else None
+                    q, a, _nv, _qid, image, k, qlen, _ = ld.assemble(idx, image_out=slot)
+                in_place += int(slot is not None and image.data_ptr() == slot.data_ptr())
+                losses.append(step(q, image, k, qlen, a).item())
+        ld.check_errors()
+        step.close()
+        red.remove()
+        runs[direct] = (losses, in_place)
+    assert runs[False][1] == 0 and runs[True][1] == len(runs[True][0]) - 1        # every step but the one that builds the graphs
+    assert runs[True][0] == pytest.approx(runs[False][0], rel=1e-6)

@@ -712,8 +712,9 @@ def memcpy2d_async(dst_addr: int, dpitch: int, src_addr: int, spitch: int, width
 
 
 # ------------------------------------------------------------------------------------------- batch assembly (loader.cu)
-def gather_image(features: torch.Tensor, boxes: torch.Tensor, rows: torch.Tensor, err: torch.Tensor) -> torch.Tensor:
-    """image (B, K, D+4) fp32 = [features[rows] | boxes[rows]] from a (n, K, D) fp32/bf16 table and (n, K, 4) fp32 boxes."""
+def gather_image(features: torch.Tensor, boxes: torch.Tensor, rows: torch.Tensor, err: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """image (B, K, D+4) fp32 = [features[rows] | boxes[rows]] from a (n, K, D) fp32/bf16 table and (n, K, 4) fp32 boxes.  ``out``: write
+    into this contiguous (B, K, D+4) fp32 tensor (a training step's input slot) instead of a fresh one."""
     if features.dtype not in (torch.float32, torch.bfloat16):
         raise RuntimeError(f"gather_image: features must be fp32 or bf16, got {features.dtype}")
     _chk(features, "gather_image features", features.dtype); _chk(boxes, "gather_image boxes"); _chk(rows, "gather_image rows", torch.int64)
@@ -723,7 +724,12 @@ def gather_image(features: torch.Tensor, boxes: torch.Tensor, rows: torch.Tensor
     n, K, D = features.shape
     rows = rows.contiguous().reshape(-1)
     B = rows.numel()
-    out = torch.empty((B, K, D + 4), device=features.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((B, K, D + 4), device=features.device, dtype=torch.float32)
+    elif tuple(out.shape) != (B, K, D + 4) or not out.is_contiguous():
+        raise RuntimeError(f"gather_image: out must be a contiguous {(B, K, D + 4)} tensor, got {tuple(out.shape)}")
+    else:
+        _chk(out, "gather_image out")
     _call("vqa_gather_image_f32", features.data_ptr(), int(features.dtype == torch.bfloat16), boxes.data_ptr(), rows.data_ptr(), n,
           out.data_ptr(), B, K, D, err.data_ptr(), _stream())
     return out

@@ -341,8 +341,10 @@ class ShardLoader:
         return len(epoch_batches(len(self.set), self.batch_size, epoch=self.epoch, shuffle=False, rank=self.rank, world=self.world,
                                  drop_last=self.drop_last))
 
-    def assemble(self, idx: np.ndarray):
-        """One batch for the question indices ``idx`` (already ordered), enqueued on the current stream."""
+    def assemble(self, idx: np.ndarray, image_out: Optional[torch.Tensor] = None):
+        """One batch for the question indices ``idx`` (already ordered), enqueued on the current stream.  ``image_out``: a (B, K, D+4)
+        fp32 device tensor the image batch is gathered INTO (``engine.TrainStep.input_slot("image")``: the step then reads it in
+        place instead of copying 151 MB once more); ignored when its shape does not fit (the short last batch of an epoch)."""
         s, dev, kn = self.set, self.device, self._kn
         B = len(idx)
         sidx = np.sort(idx)                                             # memmap reads in file order
@@ -351,7 +353,7 @@ class ShardLoader:
         rows_np = np.asarray(s.image_row[sidx])[back]
         if self.resident:
             rows = torch.from_numpy(rows_np).to(dev, non_blocking=True)
-            image = kn.gather_image(self.features, self.boxes, rows, self._err)
+            image = kn.gather_image(self.features, self.boxes, rows, self._err, out=self._fits(image_out, B))
         else:
             self._staged.synchronize()                                  # the previous batch's H2D copy has left the staging buffers
             urows, inv = np.unique(rows_np, return_inverse=True)         # questions of one image share one staged row
@@ -361,7 +363,8 @@ class ShardLoader:
             f_dev = self._pin_f[:n].to(dev, non_blocking=True)
             b_dev = self._pin_b[:n].to(dev, non_blocking=True)
             self._staged.record()
-            image = kn.gather_image(f_dev, b_dev, torch.from_numpy(inv.astype(np.int64)).to(dev, non_blocking=True), self._err)
+            image = kn.gather_image(f_dev, b_dev, torch.from_numpy(inv.astype(np.int64)).to(dev, non_blocking=True), self._err,
+                                    out=self._fits(image_out, B))
         ap, ai, av = s.csr_rows("ans", idx)
         vp, vi, vv = s.csr_rows("vote", idx)
         a = kn.scatter_targets(*(torch.from_numpy(x).to(dev, non_blocking=True) for x in (ap, ai, av)), B, s.n_answers, self._err)
@@ -371,6 +374,12 @@ class ShardLoader:
         qlen = torch.from_numpy(np.asarray(s.qlen[sidx])[back].astype(np.int64))
         last = [s.last_element(int(n)) for n in idx] if s.variant != "vqa2" else torch.from_numpy(idx.astype(np.int64))
         return q, a, n_votes, qid, image, k, qlen, last
+
+    def _fits(self, image_out, B):
+        s = self.set
+        want = (B, s.n_obj, int(s.features.shape[-1]) + 4)
+        ok = image_out is not None and tuple(image_out.shape) == want and image_out.dtype == torch.float32 and image_out.is_contiguous()
+        return image_out if ok else None
 
     def check_errors(self) -> None:
         """Raise if a kernel met an index outside its table (synchronises; called at the end of every epoch)."""
