@@ -34,6 +34,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;                  // bf16 elements per k-block: one 128-byte swizzle row
 constexpr int A_TILE = BM * 128;        // bytes per plane
 constexpr int THREADS = 192;
+constexpr int THREADS_EPI8 = 32 * 10;    // with eight epilogue warps instead of four (see gemm_bf16s_persistent_kernel)
 constexpr int SMEM_BUDGET = 232448 - 1024 - 256;
 
 struct Params {
@@ -245,6 +246,16 @@ __device__ __forceinline__ const float* stage_bias(const Params& p, float* warp_
 
 struct Maps { CUtensorMap a_hi, a_lo, b_hi, b_lo; };
 
+#ifdef VQA_GEMM_TRACE
+// Tracing build only (make EXTRA=-DVQA_GEMM_TRACE BUILD=build_trace OUT=../vqa_b200/libvqa_trace.so; tools/gemm_timeline.py): clock64
+// stamps of the phases of each CTA of gemm_bf16s_kernel (the one-tile-per-CTA kernel the recurrence products run on).
+__device__ long long g_gemm_trace[8 * 512];
+#define GEMM_STAMP(COND, I) do { if ((COND)) { const int cta_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z); \
+    if (cta_ < 512) g_gemm_trace[cta_ * 8 + (I)] = clock64(); } } while (0)
+#else
+#define GEMM_STAMP(COND, I) do { } while (0)
+#endif
+
 // ---- thread-block-cluster helpers (CL = 2: the two CTAs of a pair own vertically adjacent output tiles and share B) ----
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -265,7 +276,7 @@ __device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
 }
 
 template <int BN, int PASSES, int CL>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(BN >= 128 ? THREADS_EPI8 : THREADS)
 gemm_bf16s_kernel(const __grid_constant__ Maps tm, const Params p) {
   using C = Cfg<BN, PASSES>;
   constexpr int S = C::S;
@@ -283,6 +294,7 @@ gemm_bf16s_kernel(const __grid_constant__ Maps tm, const Params p) {
   // touches a barrier.  Uniform per CTA; never combined with CTA pairs (host side).
   if (CL == 1 && p.tile_gate != nullptr && p.tile_gate[blockIdx.y] <= p.gate_t) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  GEMM_STAMP(threadIdx.x == 0, 0);
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int kb_stop = min(p.num_kb, kb_begin + p.kb_per_split);
@@ -307,6 +319,7 @@ gemm_bf16s_kernel(const __grid_constant__ Maps tm, const Params p) {
   if (CL == 2) cluster_sync_all();          // the peer's barriers are initialised before any multicast can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  GEMM_STAMP(threadIdx.x == 0, 1);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -357,6 +370,7 @@ gemm_bf16s_kernel(const __grid_constant__ Maps tm, const Params p) {
     for (int i = 0; i < nkb; ++i) {
       const int s = i % S, ph = (i / S) & 1;
       mbar_wait(&full[s], ph);
+      GEMM_STAMP(lane == 0 && i == 0, 2);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t a_hi = smem_u32(smem + s * C::STAGE), b_hi = a_hi + A_TILE;
@@ -377,6 +391,7 @@ gemm_bf16s_kernel(const __grid_constant__ Maps tm, const Params p) {
         if (CL == 2) tc_commit_mc(&empty[s], (uint16_t)3);   // the slot is refilled by both producers: release it in both CTAs
         else tc_commit(&empty[s]);                  // smem slot reusable once these MMAs retire
         if (i == nkb - 1) tc_commit(acc_full);      // accumulator complete
+        GEMM_STAMP(i == nkb - 1, 3);
       }
       __syncwarp();
     }
@@ -384,22 +399,69 @@ gemm_bf16s_kernel(const __grid_constant__ Maps tm, const Params p) {
     // ------------------------------------------------------------ warps 2-5: epilogue
     const float* bs = stage_bias<BN>(p, reinterpret_cast<float*>(smem + S * C::STAGE + 256) + (warp - 2) * BN, lane, n0);
     mbar_wait(acc_full, 0);
+    GEMM_STAMP(threadIdx.x == 64, 4);
     tc_fence_after();
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const bool epi8 = blockDim.x == THREADS_EPI8;     // eight epilogue warps: two per lane quarter, half of the tile's columns each
+    const int c_begin = epi8 ? ((warp - 2) >> 2) * (BN / 2) : 0, c_end = epi8 ? c_begin + BN / 2 : BN;
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < p.M;
-    const Epi epi(p, row_ok ? row : 0, bs);
+    // Plain fp32 destination (optionally + bias, ReLU, or a split-K / accumulate reduction): the drain of a one-tile CTA is never
+    // hidden, and stored one row per lane it is bound by the request rate of 32 scattered sectors per instruction (3.3 us of the
+    // recurrence product's 12 us, tools/gemm_timeline.py).  The pipeline's shared memory is free once the accumulator is complete
+    // (every stage fill has been consumed), so the warp parks its 32 rows there and writes them out row by row: every store
+    // instruction covers whole 128-byte lines of one or two rows.
+    const bool coalesced = BN >= 128 && p.C && !p.Chi && !p.rowb && !p.aux && !p.auxh && ((p.N & 3) == 0) && ((p.ldc & 3) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    if (coalesced) {
+      const int W = c_end - c_begin;                          // this warp's columns: 64, 128 or 256
+      float* st = reinterpret_cast<float*>(smem) + (warp - 2) * 32 * (W + 4);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= p.N) break;            // warp-uniform
-      uint32_t r[32];
-      tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      tc_wait_ld();
-      if (row_ok) epi.store32(n0 + c0, reinterpret_cast<const float*>(r));
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        if (n0 + c0 >= p.N) break;            // warp-uniform
+        uint32_t r[32];
+        tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tc_wait_ld();
+        float* mine = st + lane * (W + 4) + (c0 - c_begin);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(mine + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+      }
+      __syncwarp();
+      const int lpr = W >= 128 ? 32 : W / 4;                  // lanes per row
+      const bool relu = p.flags & VQA_GEMM_RELU, atomic = p.flags & VQA_GEMM_ATOMIC_ADD;
+      for (int seg = 0; seg < W; seg += 128) {
+        const int cl = seg + (lane % lpr) * 4, col = n0 + c_begin + cl;
+        if (col >= p.N) continue;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bs && !atomic) b4 = *reinterpret_cast<const float4*>(bs + col);
+        for (int rr = lane / lpr; rr < 32; rr += 32 / lpr) {
+          const int orow = m0 + q * 32 + rr;
+          if (orow >= p.M) break;
+          float4 v = *reinterpret_cast<const float4*>(st + rr * (W + 4) + cl);
+          float* dst = p.C + (long long)orow * p.ldc + col;
+          if (atomic) { atomicAdd(reinterpret_cast<float4*>(dst), v); continue; }
+          v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+          if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          *reinterpret_cast<float4*>(dst) = v;
+        }
+      }
+    } else {
+      const Epi epi(p, row_ok ? row : 0, bs);
+#pragma unroll 1
+      for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+        if (n0 + c0 >= p.N) break;            // warp-uniform
+        uint32_t r[32];
+        tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tc_wait_ld();
+        if (row_ok) epi.store32(n0 + c0, reinterpret_cast<const float*>(r));
+      }
     }
+    GEMM_STAMP(threadIdx.x == 64, 5);
   }
   tc_fence_before();
   __syncthreads();
+  GEMM_STAMP(threadIdx.x == 0, 6);
   if (CL == 2) cluster_sync_all();          // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
@@ -420,7 +482,6 @@ struct PSched { int tiles_n, tiles_m, units_m, splits, units, nclusters; };
 // loads and conversions behind): eight warps drain a tile in about half the time, which is what the short-contraction products
 // need (their tile is accumulated in 4-6 us and drained in 10-20); the long ones hide the drain anyway and ran 7 % slower with
 // eight (measured in round 1), so they keep four.
-constexpr int THREADS_EPI8 = 32 * 10;
 template <int BN, int PASSES, int CL>
 __global__ void __launch_bounds__(THREADS_EPI8, 1)
 gemm_bf16s_persistent_kernel(const __grid_constant__ Maps tm, const Params p, const PSched sc) {
@@ -932,11 +993,15 @@ static int launch(const Maps& tm, const Params& p, int splits, cudaStream_t st) 
     attr_set = true;
   }
   dim3 grid((p.N + BN - 1) / BN, mt, splits);
+  // one tile per CTA: the drain is never hidden, so the wide tiles always get eight epilogue warps (the recurrence product's 128 x 128
+  // tile: 3.5 us of its 12 us with four, tools/gemm_timeline.py); VQA_GEMM_EPI8=0 switches back for measurements
+  static const bool epi8_on = !(getenv("VQA_GEMM_EPI8") && atoi(getenv("VQA_GEMM_EPI8")) == 0);
+  const int threads = (BN >= 128 && epi8_on) ? THREADS_EPI8 : THREADS;
   if (CL == 1) {
-    gemm_bf16s_kernel<BN, PASSES, CL><<<grid, THREADS, C::SMEM, st>>>(tm, p);
+    gemm_bf16s_kernel<BN, PASSES, CL><<<grid, threads, C::SMEM, st>>>(tm, p);
   } else {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
+    cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 2; at[0].val.clusterDim.z = 1;
@@ -1174,3 +1239,11 @@ extern "C" int vqa_gru_seq_fused(const void* H_hi, const void* H_lo, long long l
   VQA_LAUNCH_CHECK("gru_seq_kernel");
   return VQA_OK;
 }
+
+#ifdef VQA_GEMM_TRACE
+extern "C" int vqa_debug_gemm_trace(long long* out, int n_ctas) {
+  if (n_ctas > 512) n_ctas = 512;
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, sb::g_gemm_trace, (size_t)n_ctas * 8 * sizeof(long long)) == cudaSuccess ? VQA_OK : VQA_ERR_CUDA;
+}
+#endif
