@@ -967,7 +967,13 @@ static int launch(const Maps& tm, const Params& p, int splits, cudaStream_t st) 
   sc.units = sc.tiles_n * sc.units_m * splits;
   const int cap = g_vqa_sm_budget / CL;            // one CTA per SM (the double-buffered accumulator takes 2 * BN TMEM columns)
   sc.nclusters = sc.units < cap ? sc.units : cap;
-  if (!one_tile_per_cta && BN >= 128 && sc.units > sc.nclusters) {   // more tiles than SMs: walk them persistently, epilogue overlapped
+  // A short contraction with a plain fp32 destination is drained faster than it could be overlapped: the one-tile kernel parks the
+  // tile in its (free) pipeline shared memory and writes whole lines, the persistent kernel's epilogue stores one row per lane.
+  static const int short_kb = getenv("VQA_GEMM_SHORT_KB") ? atoi(getenv("VQA_GEMM_SHORT_KB")) : 16;
+  const bool coalescible = p.C && !p.Chi && !p.rowb && !p.aux && !p.auxh && ((p.N & 3) == 0) && ((p.ldc & 3) == 0) &&
+                           ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+  const bool short_plain = coalescible && p.kb_per_split <= short_kb;
+  if (!one_tile_per_cta && !short_plain && BN >= 128 && sc.units > sc.nclusters) {   // more tiles than SMs: walk them persistently, epilogue overlapped
     // (BN = 64 is the small-problem tile: two co-resident CTAs per SM with shallow rings already overlap each other)
     static bool attr_set_p = false;
     if (!attr_set_p) {
