@@ -99,3 +99,18 @@ def test_conv_weights_are_rejoined_by_module_conversions():
     gc = torch.nn.Sequential(gc).float()[0]               # through a parent module's recursion
     assert consecutive(gc)
     assert all(torch.equal(a, lin.weight) for a, lin in zip(before, gc.conv_weights))
+
+
+def test_all_steps_row_gate_marks_the_tiles_of_ended_questions():
+    """ops._all_steps_gate: the gate of a product over all T*B time-major rows (the GRU's input projection and its data gradient):
+    128-row tile (t, j) is skipped (entry <= 0) exactly when every question of tile j is shorter than t + 1."""
+    from vqa_b200 import ops
+    T, B = 6, 384
+    tile_len = torch.tensor([6, 3, 1], dtype=torch.int32)                 # longest question per 128-row tile (batches are length-sorted)
+    gate, t0, tag = ops._all_steps_gate(tile_len, T, B)
+    assert t0 == 0 and tag == "all_steps" and gate.dtype == torch.int32 and gate.shape == (T * 3,)
+    live = (gate > 0).view(T, 3)
+    for t in range(T):
+        for j in range(3):
+            assert bool(live[t, j]) == (int(tile_len[j]) > t)
+    assert ops._all_steps_gate(torch.tensor([5], dtype=torch.int32), T, 100) is None      # a step is not a whole number of tiles: no gating
